@@ -1,0 +1,694 @@
+// kernels_solver.cu — K5-K8, K10-K12: CSR SpMV, fused conjugate gradients, pointwise preconditioners,
+// vector kernels, halo exchange and reductions.
+//
+// The CG recurrence is dealii::SolverCG<>::solve of the 8.4 series as called at
+// lib/include/PoroElasticPressureSolver.h:176-179, PoroElasticDisplacementSolver.h:300-305 and
+// StrainProjector.h:210-214 (g = Ax-b, h = P^-1 g, d = -h, ...; convergence is tested on the
+// recursively updated ||g||_2 after the x/g update; failure after max_steps mirrors
+// SolverControl::NoConvergence).  PreconditionSSOR (PS:177-178, DS:302-303, SP:211-212) is an
+// inherently sequential sweep; north_star allows its replacement by a Chebyshev-Jacobi polynomial
+// preconditioner, which is what runs here (PE_PRECOND_CHEBYSHEV), next to plain Jacobi.
+//
+// Fusion: SpMV + d.h in one kernel; x += a d, g += a h, ||g||^2 and (Jacobi) g.D^-1g in one kernel;
+// every Chebyshev step is one SpMV-fused kernel (r -= A d; d' = c1 d + c2 D^-1 r; z += d').
+// All dot products are reduced deterministically: per-block partials in a fixed slot, the last block
+// to arrive sums them in a fixed order.  Loop control lives on the device (CgState); the host only
+// polls a pinned copy every few iterations, one poll behind the launches, so the GPU never idles.
+#include <cmath>
+#include <deque>
+
+#include "pe_internal.cuh"
+
+namespace {
+
+constexpr int VEC_T = 256;
+constexpr int SPMV_T = 256;
+
+struct RedArgs {
+  double* partials;
+  unsigned* counter;
+  double* out;
+};
+
+// Block-reduce NV values; the last block of the grid adds the per-block partials in a fixed order
+// and stores the totals to out[slot0..slot0+NV).  Requires gridDim.x <= PE_MAX_RED_BLOCKS.
+template <int NV>
+__device__ __forceinline__ void grid_reduce(double (&v)[NV], RedArgs R, int slot0) {
+  __shared__ double s_part[NV][32];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double x = v[k];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) s_part[k][w] = x;
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double x = lane < nw ? s_part[k][lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (lane == 0) R.partials[(size_t)(slot0 + k) * PE_MAX_RED_BLOCKS + blockIdx.x] = x;
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned ticket = atomicAdd(R.counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double x = 0.0;
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) x += ((volatile double*)R.partials)[(size_t)(slot0 + k) * PE_MAX_RED_BLOCKS + i];
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      __syncthreads();
+      if (lane == 0) s_part[k][w] = x;
+      __syncthreads();
+      if (w == 0) {
+        double y = lane < nw ? s_part[k][lane] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
+        if (lane == 0) R.out[slot0 + k] = y;
+      }
+    }
+    if (threadIdx.x == 0) *R.counter = 0u;
+  }
+}
+
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// sum_j val[j] * x[col[j]] of one row, LPR lanes cooperating; result valid in every lane of the group
+template <int LPR>
+__device__ __forceinline__ double row_dot(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+                                          const double* __restrict__ x, int64_t row, int sub, bool valid) {
+  int start = 0, end = 0;
+  if (valid) { start = rowptr[row]; end = rowptr[row + 1]; }
+  double s0 = 0.0, s1 = 0.0;
+  int j = start + sub;
+  for (; j + LPR < end; j += 2 * LPR) {
+    const int c0 = ld_stream(col + j), c1 = ld_stream(col + j + LPR);
+    const double v0 = ld_stream(val + j), v1 = ld_stream(val + j + LPR);
+    s0 += v0 * x[c0];
+    s1 += v1 * x[c1];
+  }
+  if (j < end) s0 += ld_stream(val + j) * x[ld_stream(col + j)];
+  double s = s0 + s1;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+// epilogue kinds of the fused SpMV
+enum { EPI_PLAIN = 0, EPI_DOT = 1, EPI_RESID = 2, EPI_CHEB = 3 };
+
+struct SpmvArgs {
+  const int32_t* rowptr;
+  const int32_t* col;
+  const double* val;
+  const double* x;
+  double* y;
+  int64_t n;
+  // epilogue operands
+  const double* b;        // EPI_RESID: y = A x - b
+  const double* invdiag;  // EPI_CHEB
+  double* r;              // EPI_CHEB: residual (in/out)
+  double* d_out;          // EPI_CHEB: new direction
+  double* z;              // EPI_CHEB: accumulated result
+  double c1, c2;          // EPI_CHEB coefficients
+  const CgState* state;   // early exit when state->done != 0 (may be null)
+  RedArgs red;
+  int slot;
+};
+
+template <int LPR, int EPI>
+__global__ void __launch_bounds__(SPMV_T) k_spmv(SpmvArgs a) {
+  if (a.state && a.state->done) return;
+  constexpr int RPB = SPMV_T / LPR;
+  const int sub = threadIdx.x % LPR;
+  double acc[1] = {0.0};
+  // n_pad is a multiple of RPB, so the loop condition is uniform across the CTA (shuffles stay converged)
+  const int64_t n_pad = ((a.n + RPB - 1) / RPB) * RPB;
+  for (int64_t row = (int64_t)blockIdx.x * RPB + threadIdx.x / LPR; row < n_pad; row += (int64_t)gridDim.x * RPB) {
+    const bool valid = row < a.n;
+    const double s = row_dot<LPR>(a.rowptr, a.col, a.val, a.x, row, sub, valid);
+    if (valid && sub == 0) {
+      if (EPI == EPI_PLAIN) a.y[row] = s;
+      if (EPI == EPI_DOT) { a.y[row] = s; acc[0] += s * a.x[row]; }
+      if (EPI == EPI_RESID) { const double g = s - a.b[row]; a.y[row] = g; acc[0] += g * g; }
+      if (EPI == EPI_CHEB) {
+        const double rn = a.r[row] - s;
+        a.r[row] = rn;
+        const double dn = a.c1 * a.x[row] + a.c2 * a.invdiag[row] * rn;
+        a.d_out[row] = dn;
+        a.z[row] += dn;
+      }
+    }
+  }
+  if (EPI == EPI_DOT || EPI == EPI_RESID) grid_reduce<1>(acc, a.red, a.slot);
+}
+
+// pressure residual (PS:113-155): r = -( M t1 + kappa K p + f ), ||r||^2 -> slot
+template <int LPR>
+__global__ void __launch_bounds__(SPMV_T)
+k_pressure_residual(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ M,
+                    const double* __restrict__ K, const double* __restrict__ t1, const double* __restrict__ p, const double* __restrict__ f,
+                    double kappa, double* __restrict__ r, int64_t n, RedArgs red, int slot) {
+  constexpr int RPB = SPMV_T / LPR;
+  const int sub = threadIdx.x % LPR;
+  double acc[1] = {0.0};
+  const int64_t n_pad = ((n + RPB - 1) / RPB) * RPB;
+  for (int64_t row = (int64_t)blockIdx.x * RPB + threadIdx.x / LPR; row < n_pad; row += (int64_t)gridDim.x * RPB) {
+    double sm = 0.0, sk = 0.0;
+    if (row < n) {
+      const int start = rowptr[row], end = rowptr[row + 1];
+      for (int j = start + sub; j < end; j += LPR) {
+        const int c = ld_stream(col + j);
+        sm += ld_stream(M + j) * t1[c];
+        sk += ld_stream(K + j) * p[c];
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+      sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      sk += __shfl_xor_sync(0xffffffffu, sk, o);
+    }
+    if (row < n && sub == 0) {
+      double v = sm;        // mass_matrix.vmult(residual, tmp1)
+      v += sk * kappa;      // residual += (perm/visc) * laplace_matrix * solution
+      v += f[row];          // residual += source
+      v *= -1.0;            // residual *= -1
+      r[row] = v;
+      acc[0] += v * v;
+    }
+  }
+  grid_reduce<1>(acc, red, slot);
+}
+
+// t1 = (alpha/dt)(ev - ev0) + (p - p_old)/(M_b dt)      PS:120-131
+__global__ void k_residual_t1(int64_t n, const double* __restrict__ ev, const double* __restrict__ ev0, const double* __restrict__ p,
+                              const double* __restrict__ p_old, double a, double m, double* __restrict__ t1) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x1 = (ev[i] - ev0[i]) * a;
+  const double x2 = (p[i] - p_old[i]) * m;
+  t1[i] = x1 + x2;
+}
+
+// CG update (after h = A d): alpha = gh/dh; g += alpha h; x += alpha d; res2 = g.g; [Jacobi] z = D^-1 g, gz = g.z
+template <bool JACOBI>
+__global__ void __launch_bounds__(VEC_T)
+k_cg_update(int64_t n, const CgState* __restrict__ state, const double* __restrict__ red_in, const double* __restrict__ gh_cur,
+            double* __restrict__ x, double* __restrict__ g, const double* __restrict__ d, const double* __restrict__ h,
+            const double* __restrict__ invdiag, double* __restrict__ z, RedArgs red) {
+  if (state->done) return;
+  const double alpha = *gh_cur / red_in[0];
+  double acc[2] = {0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double gi = g[i] + alpha * h[i];
+    g[i] = gi;
+    x[i] += alpha * d[i];
+    acc[0] += gi * gi;
+    if (JACOBI) {
+      const double zi = gi * invdiag[i];
+      z[i] = zi;
+      acc[1] += gi * zi;
+    }
+  }
+  grid_reduce<2>(acc, red, 1);
+}
+
+// single thread: iteration bookkeeping after the update kernel (SolverControl::check)
+__global__ void k_cg_check(CgState* state, const double* __restrict__ red) {
+  if (state->done) return;
+  state->it += 1;
+  const double res = sqrt(red[1]);
+  state->res = res;
+  if (res <= state->tol) state->done = 1;
+  else if (state->it >= state->max_it || isnan(res)) state->done = -1;
+}
+
+// d = beta d - z with beta = gz_new / gh_old.  gh lives in a two-entry ring indexed by iteration parity
+// (the host knows the parity when it enqueues), so no thread reads a value another one is writing.
+__global__ void __launch_bounds__(VEC_T)
+k_cg_direction(int64_t n, const CgState* __restrict__ state, const double* __restrict__ red, const double* __restrict__ gh_cur,
+               double* __restrict__ gh_next, double* __restrict__ d, const double* __restrict__ z) {
+  if (state->done) return;
+  const double gz = red[2];
+  const double beta = gz / *gh_cur;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = beta * d[i] - z[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *gh_next = gz;
+}
+
+// start of a solve: z = P^-1 g was computed; d = -z ; gh = g.z (in red[2])
+__global__ void k_cg_start(int64_t n, const CgState* __restrict__ state, const double* __restrict__ red, double* __restrict__ gh0,
+                           double* __restrict__ d, const double* __restrict__ z) {
+  if (state->done) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = -z[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *gh0 = red[2];
+}
+__global__ void k_cg_init_state(CgState* state, const double* __restrict__ red, double tol, int tol_relative, int max_it) {
+  // red[0] = ||g0||^2, red[3] = ||b||^2 (when relative)
+  const double res = sqrt(red[0]);
+  state->res = res;
+  state->res0 = res;
+  state->tol = tol_relative ? tol * sqrt(red[3]) : tol;
+  state->it = 0;
+  state->max_it = max_it;
+  state->gh = 0.0;
+  state->done = 0;
+  if (res <= state->tol) state->done = 1;
+  else if (max_it <= 0 || isnan(res)) state->done = -1;
+}
+
+// z = D^-1 g, gz = g.z   (Jacobi at solve start)
+__global__ void __launch_bounds__(VEC_T)
+k_jacobi_dot(int64_t n, const CgState* __restrict__ state, const double* __restrict__ g, const double* __restrict__ invdiag,
+             double* __restrict__ z, RedArgs red) {
+  if (state && state->done) return;
+  double acc[1] = {0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double zi = g[i] * invdiag[i];
+    z[i] = zi;
+    acc[0] += g[i] * zi;
+  }
+  grid_reduce<1>(acc, red, 2);
+}
+
+// generic dot product into a slot
+__global__ void __launch_bounds__(VEC_T)
+k_dot(int64_t n, const CgState* __restrict__ state, const double* __restrict__ a, const double* __restrict__ b, RedArgs red, int slot) {
+  if (state && state->done) return;
+  double acc[1] = {0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc[0] += a[i] * b[i];
+  grid_reduce<1>(acc, red, slot);
+}
+
+// Chebyshev start: r = g ; d = (1/theta) D^-1 r ; z = d
+__global__ void __launch_bounds__(VEC_T)
+k_cheb_first(int64_t n, const CgState* __restrict__ state, const double* __restrict__ g, const double* __restrict__ invdiag, double inv_theta,
+             double* __restrict__ r, double* __restrict__ d, double* __restrict__ z) {
+  if (state && state->done) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double gi = g[i];
+    const double di = inv_theta * invdiag[i] * gi;
+    r[i] = gi;
+    d[i] = di;
+    z[i] = di;
+  }
+}
+
+__global__ void k_axpy(int64_t n, double a, const double* __restrict__ x, double* __restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += a * x[i];
+}
+__global__ void k_axpby(int64_t n, double a, const double* __restrict__ x, double b, const double* __restrict__ y, double* __restrict__ z) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) z[i] = a * x[i] + b * y[i];
+}
+__global__ void k_set(int64_t n, double a, double* __restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = a;
+}
+__global__ void k_scale_by(int64_t n, const double* __restrict__ s, double* __restrict__ y, double f) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] *= s[i] * f;
+}
+__global__ void k_distribute(int64_t n_lines, const int32_t* __restrict__ line_dof, const double* __restrict__ g, double* __restrict__ v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_lines) v[line_dof[i]] = g[i];
+}
+__global__ void k_pack(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ v, double* __restrict__ buf) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) buf[i] = v[idx[i]];
+}
+__global__ void k_invdiag(int64_t n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+                          double* __restrict__ invdiag) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int lo = rowptr[r], hi = rowptr[r + 1];
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (col[mid] < r) lo = mid + 1; else hi = mid;
+  }
+  invdiag[r] = 1.0 / val[lo];
+}
+// block-wise max |v| -> partials slot 0 ; finished on the host (tiny)
+__global__ void __launch_bounds__(VEC_T) k_absmax(int64_t n, const double* __restrict__ v, double* __restrict__ partials) {
+  __shared__ double s[VEC_T / 32];
+  double m = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmax(m, fabs(v[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < VEC_T / 32; ++w) m = fmax(m, s[w]);
+    partials[blockIdx.x] = m;
+  }
+}
+// sigma = C : eps pointwise (FSS:189-224)
+__global__ void k_stress(int64_t n, int dim, double lambda, double mu, const double* e0, const double* e1, const double* e2,
+                         const double* e3, const double* e4, const double* e5, double* s0, double* s1, double* s2, double* s3, double* s4,
+                         double* s5) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (dim == 2) {  // entries xx, xy, yy
+    const double tr = e0[i] + e2[i];
+    s0[i] = 2 * mu * e0[i] + lambda * tr;
+    s1[i] = 2 * mu * e1[i];
+    s2[i] = 2 * mu * e2[i] + lambda * tr;
+  } else {  // xx, xy, xz, yy, yz, zz
+    const double tr = e0[i] + e3[i] + e5[i];
+    s0[i] = 2 * mu * e0[i] + lambda * tr;
+    s1[i] = 2 * mu * e1[i];
+    s2[i] = 2 * mu * e2[i];
+    s3[i] = 2 * mu * e3[i] + lambda * tr;
+    s4[i] = 2 * mu * e4[i];
+    s5[i] = 2 * mu * e5[i] + lambda * tr;
+  }
+}
+
+inline RedArgs red_args(pe_ctx* c) { return RedArgs{c->red.partials.p, c->red.counter.p, c->red.out.p}; }
+
+inline int vec_grid(pe_ctx* c, int64_t n) {
+  int64_t want = (n + VEC_T - 1) / VEC_T;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sm_count * 8));
+}
+
+inline int lanes_per_row(const Field& F) {
+  const double avg = F.n_owned ? (double)F.nnz / (double)F.n_owned : 1.0;
+  if (avg > 48) return 32;
+  if (avg > 20) return 16;
+  if (avg > 10) return 8;
+  return 4;
+}
+
+inline int spmv_grid(pe_ctx* c, int64_t n, int lpr) {
+  const int rpb = SPMV_T / lpr;
+  int64_t want = (n + rpb - 1) / rpb;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min<int64_t>(PE_MAX_RED_BLOCKS, (int64_t)c->sm_count * 8)));
+}
+
+template <int EPI>
+void launch_spmv(pe_ctx* c, Field& F, SpmvArgs& a) {
+  a.rowptr = F.rowptr.p;
+  a.col = F.col.p;
+  a.n = F.n_owned;
+  a.red = red_args(c);
+  const int lpr = lanes_per_row(F);
+  const int grid = spmv_grid(c, a.n, lpr);
+  switch (lpr) {
+    case 32: k_spmv<32, EPI><<<grid, SPMV_T, 0, c->stream>>>(a); break;
+    case 16: k_spmv<16, EPI><<<grid, SPMV_T, 0, c->stream>>>(a); break;
+    case 8: k_spmv<8, EPI><<<grid, SPMV_T, 0, c->stream>>>(a); break;
+    default: k_spmv<4, EPI><<<grid, SPMV_T, 0, c->stream>>>(a); break;
+  }
+  c->st.kernel_launches++;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+void pe_allreduce_sum(pe_ctx* c, double* dev, int count) {
+  if (c->nranks > 1) PE_NCCL(ncclAllReduce(dev, dev, count, ncclDouble, ncclSum, c->comm, c->stream));
+}
+
+// K12: ghost values of v (entries [n_owned, n_local)) <- owners
+void pe_halo_exchange(pe_ctx* c, Field& F, double* v) {
+  if (c->nranks <= 1 || F.halo.n_neigh == 0) return;
+  Halo& H = F.halo;
+  const int64_t ns = H.n_send();
+  if (ns) {
+    k_pack<<<pe_div_up(ns, VEC_T), VEC_T, 0, c->stream>>>(ns, H.send_idx.p, v, H.send_buf.p);
+    c->st.kernel_launches++;
+  }
+  PE_NCCL(ncclGroupStart());
+  for (int k = 0; k < H.n_neigh; ++k) {
+    const int64_t s0 = H.send_ptr[k], s1 = H.send_ptr[k + 1], r0 = H.recv_ptr[k], r1 = H.recv_ptr[k + 1];
+    if (s1 > s0) PE_NCCL(ncclSend(H.send_buf.p + s0, (size_t)(s1 - s0), ncclDouble, H.rank[k], c->comm, c->stream));
+    if (r1 > r0) PE_NCCL(ncclRecv(v + F.n_owned + r0, (size_t)(r1 - r0), ncclDouble, H.rank[k], c->comm, c->stream));
+  }
+  PE_NCCL(ncclGroupEnd());
+}
+
+void pe_vec_axpy(pe_ctx* c, int64_t n, double a, const double* x, double* y) {
+  if (!n) return;
+  k_axpy<<<vec_grid(c, n), VEC_T, 0, c->stream>>>(n, a, x, y);
+  c->st.kernel_launches++;
+}
+void pe_vec_copy(pe_ctx* c, int64_t n, const double* x, double* y) {
+  if (n) PE_CUDA(cudaMemcpyAsync(y, x, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+}
+void pe_vec_set(pe_ctx* c, int64_t n, double a, double* y) {
+  if (!n) return;
+  k_set<<<vec_grid(c, n), VEC_T, 0, c->stream>>>(n, a, y);
+  c->st.kernel_launches++;
+}
+void pe_vec_axpby_vals(pe_ctx* c, int64_t n, double a, const double* x, double b, const double* y, double* z) {
+  if (!n) return;
+  k_axpby<<<vec_grid(c, n), VEC_T, 0, c->stream>>>(n, a, x, b, y, z);
+  c->st.kernel_launches++;
+}
+void pe_distribute(pe_ctx* c, Field& F, double* v) {
+  if (!F.n_lines) return;
+  k_distribute<<<pe_div_up(F.n_lines, VEC_T), VEC_T, 0, c->stream>>>(F.n_lines, F.line_dof.p, F.line_g.p, v);
+  c->st.kernel_launches++;
+}
+void pe_extract_invdiag(pe_ctx* c, Field& F, const double* val, double* invdiag) {
+  k_invdiag<<<pe_div_up(F.n_owned, VEC_T), VEC_T, 0, c->stream>>>(F.n_owned, F.rowptr.p, F.col.p, val, invdiag);
+  c->st.kernel_launches++;
+}
+
+double pe_linfty(pe_ctx* c, Field& F, const double* v) {
+  const int grid = std::min(vec_grid(c, F.n_owned), PE_MAX_RED_BLOCKS);
+  k_absmax<<<grid, VEC_T, 0, c->stream>>>(F.n_owned, v, c->red.partials.p);
+  c->st.kernel_launches++;
+  std::vector<double> h(grid);
+  PE_CUDA(cudaMemcpyAsync(h.data(), c->red.partials.p, grid * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PE_CUDA(cudaStreamSynchronize(c->stream));
+  double m = 0;
+  for (double x : h) m = std::max(m, x);
+  if (c->nranks > 1) {
+    double* dev = c->red.out.p + PE_RED_SLOTS;
+    PE_CUDA(cudaMemcpyAsync(dev, &m, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PE_NCCL(ncclAllReduce(dev, dev, 1, ncclDouble, ncclMax, c->comm, c->stream));
+    PE_CUDA(cudaMemcpyAsync(&m, dev, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PE_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return m;
+}
+
+void pe_stress_kernel(pe_ctx* c) {
+  const int64_t n = c->fp.n_owned;
+  auto E = [&](int i) { return i < c->n_stress ? c->strains[i].p : nullptr; };
+  auto S = [&](int i) { return i < c->n_stress ? c->stresses[i].p : nullptr; };
+  k_stress<<<pe_div_up(n, VEC_T), VEC_T, 0, c->stream>>>(n, c->dim, c->prm.lame_lambda, c->prm.shear_modulus, E(0), E(1), E(2), E(3), E(4), E(5),
+                                                        S(0), S(1), S(2), S(3), S(4), S(5));
+  c->st.kernel_launches++;
+}
+
+void pe_spmv_plain(pe_ctx* c, Field& F, const double* val, const double* x, double* y) {
+  SpmvArgs a{};
+  a.val = val;
+  a.x = x;
+  a.y = y;
+  a.state = nullptr;
+  launch_spmv<EPI_PLAIN>(c, F, a);
+}
+
+double pe_pressure_residual(pe_ctx* c, double dt) {
+  Field& F = c->fp;
+  const int64_t n = F.n_owned;
+  k_residual_t1<<<pe_div_up(n, VEC_T), VEC_T, 0, c->stream>>>(n, c->ev.p, c->ev0.p, c->p.p, c->p_old.p, c->prm.biot_coef / dt,
+                                                             1. / c->prm.m_modulus / dt, c->t1.p);
+  c->st.kernel_launches++;
+  pe_halo_exchange(c, F, c->t1.p);
+  pe_halo_exchange(c, F, c->p.p);
+  const int lpr = lanes_per_row(F);
+  const int grid = spmv_grid(c, n, lpr);
+  RedArgs R = red_args(c);
+  switch (lpr) {
+    case 32: k_pressure_residual<32><<<grid, SPMV_T, 0, c->stream>>>(F.rowptr.p, F.col.p, c->M.p, c->K.p, c->t1.p, c->p.p, c->frhs.p, c->prm.perm_over_visc, c->resid.p, n, R, 0); break;
+    case 16: k_pressure_residual<16><<<grid, SPMV_T, 0, c->stream>>>(F.rowptr.p, F.col.p, c->M.p, c->K.p, c->t1.p, c->p.p, c->frhs.p, c->prm.perm_over_visc, c->resid.p, n, R, 0); break;
+    case 8: k_pressure_residual<8><<<grid, SPMV_T, 0, c->stream>>>(F.rowptr.p, F.col.p, c->M.p, c->K.p, c->t1.p, c->p.p, c->frhs.p, c->prm.perm_over_visc, c->resid.p, n, R, 0); break;
+    default: k_pressure_residual<4><<<grid, SPMV_T, 0, c->stream>>>(F.rowptr.p, F.col.p, c->M.p, c->K.p, c->t1.p, c->p.p, c->frhs.p, c->prm.perm_over_visc, c->resid.p, n, R, 0); break;
+  }
+  c->st.kernel_launches++;
+  c->st.spmv_launches_p += 2;
+  pe_allreduce_sum(c, c->red.out.p, 1);
+  PE_CUDA(cudaMemcpyAsync(c->h_scalars, c->red.out.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PE_CUDA(cudaStreamSynchronize(c->stream));
+  PE_CUDA(cudaGetLastError());
+  return std::sqrt(c->h_scalars[0]);
+}
+
+// lambda_max(D^-1 A) by power iteration from a fixed start vector (upper-bounded by the Gershgorin-free
+// safety factor applied by the caller)
+double pe_estimate_eig_max(pe_ctx* c, Field& F, const double* val, const double* invdiag) {
+  const int64_t n = F.n_owned;
+  double* v = c->w_d.p;
+  double* y = c->w_h.p;
+  std::vector<double> h((size_t)n);
+  for (int64_t i = 0; i < n; ++i) h[i] = 0.5 + (double)((uint32_t)(i * 2654435761u) >> 22) / 1024.0;
+  PE_CUDA(cudaMemsetAsync(v, 0, F.n_local * sizeof(double), c->stream));
+  PE_CUDA(cudaMemcpyAsync(v, h.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  PE_CUDA(cudaStreamSynchronize(c->stream));
+  RedArgs R = red_args(c);
+  double lambda = 1.0;
+  for (int it = 0; it < 30; ++it) {
+    pe_halo_exchange(c, F, v);
+    pe_spmv_plain(c, F, val, v, y);
+    k_scale_by<<<vec_grid(c, n), VEC_T, 0, c->stream>>>(n, invdiag, y, 1.0);  // y = D^-1 A v
+    k_dot<<<std::min(vec_grid(c, n), PE_MAX_RED_BLOCKS), VEC_T, 0, c->stream>>>(n, nullptr, y, y, R, 0);
+    k_dot<<<std::min(vec_grid(c, n), PE_MAX_RED_BLOCKS), VEC_T, 0, c->stream>>>(n, nullptr, v, v, R, 1);
+    c->st.kernel_launches += 3;
+    pe_allreduce_sum(c, c->red.out.p, 2);
+    PE_CUDA(cudaMemcpyAsync(c->h_scalars, c->red.out.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PE_CUDA(cudaStreamSynchronize(c->stream));
+    const double ny = std::sqrt(c->h_scalars[0]), nv = std::sqrt(c->h_scalars[1]);
+    lambda = ny / nv;
+    k_axpby<<<vec_grid(c, n), VEC_T, 0, c->stream>>>(n, 1.0 / ny, y, 0.0, y, v);  // v = y / ||y||
+    c->st.kernel_launches++;
+  }
+  PE_CUDA(cudaGetLastError());
+  return lambda;
+}
+
+// Preconditioned CG.  x is n_local (ghost slots are scratch), b is read on owned rows.
+CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdiag, double eig_max, double* x, const double* b, double tol,
+                     bool tol_relative_to_b, int64_t* spmv_counter) {
+  const int64_t n = F.n_owned;
+  double *g = c->w_g.p, *h = c->w_h.p, *d = c->w_d.p, *z = c->w_z.p, *d2 = c->w_d2.p, *r = c->w_r.p;
+  CgState* st = c->cg_state.p;
+  RedArgs R = red_args(c);
+  double* red = c->red.out.p;
+  double* ghbuf = red + PE_RED_SLOTS + 2;  // two-entry ring for g.h
+  const int vg = std::min(vec_grid(c, n), PE_MAX_RED_BLOCKS);
+  const bool cheb = c->prm.preconditioner == PE_PRECOND_CHEBYSHEV && c->prm.chebyshev_degree > 1;
+  const int kdeg = c->prm.chebyshev_degree;
+  // Chebyshev interval [lmax/ratio, lmax] on D^-1 A
+  const double lmax = eig_max, lmin = eig_max / c->prm.chebyshev_eig_ratio;
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+
+  // z = P^-1 g (P = Jacobi or Chebyshev polynomial), gz -> red[2]
+  auto apply_precond_and_dot = [&]() {
+    if (!cheb) {
+      k_jacobi_dot<<<vg, VEC_T, 0, c->stream>>>(n, st, g, invdiag, z, R);
+      c->st.kernel_launches++;
+    } else {
+      k_cheb_first<<<vg, VEC_T, 0, c->stream>>>(n, st, g, invdiag, 1.0 / theta, r, d2, z);
+      c->st.kernel_launches++;
+      double rho = 1.0 / sigma;
+      double* din = d2;
+      double* dout = h;  // h is free between the update and the next SpMV
+      for (int k = 1; k < kdeg; ++k) {
+        const double rho_new = 1.0 / (2.0 * sigma - rho);
+        SpmvArgs a{};
+        a.val = val;
+        a.x = din;
+        a.invdiag = invdiag;
+        a.r = r;
+        a.d_out = dout;
+        a.z = z;
+        a.c1 = rho_new * rho;
+        a.c2 = 2.0 * rho_new / delta;
+        a.state = st;
+        pe_halo_exchange(c, F, din);
+        launch_spmv<EPI_CHEB>(c, F, a);
+        (*spmv_counter)++;
+        rho = rho_new;
+        std::swap(din, dout);
+      }
+      k_dot<<<vg, VEC_T, 0, c->stream>>>(n, st, g, z, R, 2);
+      c->st.kernel_launches++;
+    }
+    pe_allreduce_sum(c, red + 2, 1);
+  };
+
+  // g = A x - b, ||g||^2 -> red[0]; ||b||^2 -> red[3]
+  pe_halo_exchange(c, F, x);
+  {
+    SpmvArgs a{};
+    a.val = val;
+    a.x = x;
+    a.y = g;
+    a.b = b;
+    a.state = nullptr;
+    a.slot = 0;
+    launch_spmv<EPI_RESID>(c, F, a);
+    (*spmv_counter)++;
+  }
+  if (tol_relative_to_b) {
+    k_dot<<<vg, VEC_T, 0, c->stream>>>(n, nullptr, b, b, R, 3);
+    c->st.kernel_launches++;
+  }
+  pe_allreduce_sum(c, red, PE_RED_SLOTS);
+  k_cg_init_state<<<1, 1, 0, c->stream>>>(st, red, tol, tol_relative_to_b ? 1 : 0, c->prm.cg_max_iterations);
+  apply_precond_and_dot();
+  k_cg_start<<<vg, VEC_T, 0, c->stream>>>(n, st, red, ghbuf, d, z);
+  c->st.kernel_launches += 2;
+
+  const int max_it = c->prm.cg_max_iterations;
+  const int interval = c->prm.cg_check_interval > 0 ? c->prm.cg_check_interval : 8;
+  int launched = 0;
+  std::deque<int> inflight;  // pinned poll slots whose copy is enqueued but not yet consumed
+  int slot = 0;
+  auto launch_chunk = [&]() {
+    const int chunk = std::min(interval, max_it - launched);
+    for (int k = 0; k < chunk; ++k) {
+      double* gh_cur = ghbuf + ((launched + k) & 1);
+      double* gh_nxt = ghbuf + ((launched + k + 1) & 1);
+      SpmvArgs a{};
+      a.val = val;
+      a.x = d;
+      a.y = h;
+      a.state = st;
+      a.slot = 0;
+      pe_halo_exchange(c, F, d);
+      launch_spmv<EPI_DOT>(c, F, a);  // h = A d, red[0] = d.h
+      (*spmv_counter)++;
+      pe_allreduce_sum(c, red, 1);
+      if (!cheb) k_cg_update<true><<<vg, VEC_T, 0, c->stream>>>(n, st, red, gh_cur, x, g, d, h, invdiag, z, R);
+      else k_cg_update<false><<<vg, VEC_T, 0, c->stream>>>(n, st, red, gh_cur, x, g, d, h, invdiag, z, R);
+      pe_allreduce_sum(c, red + 1, cheb ? 1 : 2);
+      k_cg_check<<<1, 1, 0, c->stream>>>(st, red);
+      c->st.kernel_launches += 2;
+      if (cheb) apply_precond_and_dot();
+      k_cg_direction<<<vg, VEC_T, 0, c->stream>>>(n, st, red, gh_cur, gh_nxt, d, z);
+      c->st.kernel_launches++;
+    }
+    launched += chunk;
+    PE_CUDA(cudaMemcpyAsync(&c->h_state[slot], st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    PE_CUDA(cudaEventRecord(c->ev_poll[slot], c->stream));
+    inflight.push_back(slot);
+    slot ^= 1;
+  };
+  CgState last{};
+  launch_chunk();
+  while (true) {
+    if (launched < max_it && inflight.size() < 2) launch_chunk();  // stay one chunk ahead of the poll
+    const int s = inflight.front();
+    inflight.pop_front();
+    PE_CUDA(cudaEventSynchronize(c->ev_poll[s]));
+    last = c->h_state[s];
+    if (last.done != 0) break;
+    if (launched >= max_it && inflight.empty()) break;  // unreachable: k_cg_check flags failure at max_it
+  }
+  while (!inflight.empty()) {
+    PE_CUDA(cudaEventSynchronize(c->ev_poll[inflight.front()]));
+    inflight.pop_front();
+  }
+  PE_CUDA(cudaGetLastError());
+  CgResult out;
+  out.its = last.it;
+  out.res = last.res;
+  out.status = last.done == 1 ? PE_OK : (std::isnan(last.res) ? PE_ERR_NAN : PE_ERR_NO_CONVERGENCE);
+  return out;
+}

@@ -1,0 +1,212 @@
+// pe_internal.cuh — internal layout of the device library (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/poroel.h"
+
+#define PE_CUDA(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      throw PeError(PE_ERR_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+#define PE_NCCL(call)                                                                                   \
+  do {                                                                                                  \
+    ncclResult_t r_ = (call);                                                                           \
+    if (r_ != ncclSuccess)                                                                              \
+      throw PeError(PE_ERR_NCCL, std::string(#call) + " failed: " + ncclGetErrorString(r_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+struct PeError : std::runtime_error {
+  int code;
+  PeError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) PE_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+  }
+  void alloc_zero(size_t count, cudaStream_t s) {
+    alloc(count);
+    if (count) PE_CUDA(cudaMemsetAsync(p, 0, count * sizeof(T), s));
+  }
+  void upload(const T* h, size_t count, cudaStream_t s) {
+    alloc(count);
+    if (count) PE_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+};
+
+// reference-cell tables of one (finite element, quadrature) pair, all in device memory
+struct ShapeTab {
+  int ns = 0, nq = 0;
+  DBuf<double> N;   // nq*ns
+  DBuf<double> dN;  // nq*ns*dim
+};
+struct QuadTab {
+  int nq = 0;
+  DBuf<double> w;     // nq
+  DBuf<double> geoN;  // nq*vpc   (Q1 mapping shape values)
+  DBuf<double> geodN; // nq*vpc*dim
+};
+
+struct Halo {
+  int n_neigh = 0;
+  std::vector<int> rank;
+  std::vector<int64_t> send_ptr, recv_ptr;
+  DBuf<int32_t> send_idx;
+  DBuf<double> send_buf;
+  int64_t n_send() const { return send_ptr.empty() ? 0 : send_ptr.back(); }
+  void reset() {
+    n_neigh = 0;
+    rank.clear();
+    send_ptr.clear();
+    recv_ptr.clear();
+    send_idx.release();
+    send_buf.release();
+  }
+};
+
+struct Field {
+  int degree = 1, ncomp = 1, ns = 0, nloc = 0;
+  int64_t n_owned = 0, n_local = 0;
+  bool have_dofs = false, have_partition = false;
+  std::vector<int32_t> h_cell_dofs;
+  DBuf<int32_t> cell_dofs;
+  // pure-Dirichlet constraint lines
+  int64_t n_lines = 0;
+  std::vector<int32_t> h_line_dof;
+  std::vector<double> h_line_g;
+  DBuf<int32_t> cline;     // n_local: line index or -1
+  DBuf<int32_t> line_dof;  // n_lines
+  DBuf<double> line_g;     // n_lines
+  // CSR pattern of the owned rows, columns ascending (local ids)
+  DBuf<int32_t> rowptr, col;
+  int64_t nnz = 0;
+  Halo halo;
+};
+
+// device-resident scalar state of one CG solve
+struct CgState {
+  double gh, tol, res, res0;
+  int it, done, max_it, pad;
+};
+
+static constexpr int PE_MAX_RED_BLOCKS = 4096;
+static constexpr int PE_RED_SLOTS = 4;
+
+struct Reducer {
+  DBuf<double> partials;   // PE_RED_SLOTS * PE_MAX_RED_BLOCKS
+  DBuf<unsigned> counter;  // 1
+  DBuf<double> out;        // PE_RED_SLOTS (+ scratch)
+};
+
+struct pe_ctx {
+  int device = 0, rank = 0, nranks = 1;
+  cudaStream_t stream = nullptr;
+  ncclComm_t comm = nullptr;
+  std::string err;
+  pe_params prm{};
+  bool have_params = false, have_mesh = false, setup_done = false;
+  int sm_count = 148;
+
+  // mesh
+  int dim = 0, vpc = 0;
+  int64_t n_vertices = 0, n_cells = 0, n_bfaces = 0;
+  std::vector<int32_t> h_cell_vertices;
+  DBuf<double> xyz;
+  DBuf<int32_t> cell_vertices, bface_cell, bface_id;
+  DBuf<int8_t> bface_local;
+  std::vector<int32_t> h_bface_cell, h_bface_id;
+  std::vector<int8_t> h_bface_local;
+  // colouring
+  int n_colors = 0;
+  std::vector<int64_t> color_ptr;
+  DBuf<int32_t> color_cells;
+  // neumann
+  std::vector<int32_t> nm_label, nm_comp;
+  std::vector<double> nm_value;
+
+  Field fp, fu;  // pressure, displacement
+
+  // reference tables
+  QuadTab q2, qu;                       // QGauss(2); QGauss(degree_u+1)
+  ShapeTab p_q2, p_qu, us_q2, us_qu;    // pressure FE / displacement scalar FE at those points
+  DBuf<double> usup;                    // unit support points of the displacement scalar FE (ns*dim)
+
+  // matrices (values on the field patterns) and inverse diagonals
+  DBuf<double> M, K, J, A;
+  DBuf<double> invdiag_M, invdiag_J, invdiag_A;
+  double jac_dt = -1;
+  bool matrix_u_built = false, proj_matrix_ready = false;
+  double eig_M = 0, eig_J = 0, eig_A = 0;
+
+  // vectors (n_local of their field)
+  DBuf<double> p, p_old, dp, resid, ev, ev0, frhs, t1;
+  DBuf<double> u, b, b_const;
+  std::vector<DBuf<double>> strains, proj_rhs, stresses;
+  int n_stress = 0;
+  // CG work vectors sized for the larger field
+  DBuf<double> w_g, w_h, w_d, w_z, w_d2, w_r;
+
+  Reducer red;
+  DBuf<CgState> cg_state;
+  CgState* h_state = nullptr;  // pinned
+  double* h_scalars = nullptr; // pinned, PE_RED_SLOTS
+  cudaEvent_t ev_poll[2] = {nullptr, nullptr};
+
+  pe_stats st{};
+};
+
+// ---- kernels_pattern.cu
+void pe_build_pattern(pe_ctx* c, Field& F);
+int64_t pe_exclusive_scan_i32(pe_ctx* c, int32_t* data, int64_t n);  // in place, n+1 entries written (last = total)
+
+// ---- kernels_assembly.cu
+void pe_build_tables(pe_ctx* c);
+void pe_color_cells(pe_ctx* c);
+void pe_assemble_pressure_matrices(pe_ctx* c);  // M, K, well rhs
+void pe_assemble_elasticity(pe_ctx* c);         // A, b_const (Dirichlet + Neumann)
+void pe_assemble_u_rhs(pe_ctx* c);              // b = b_const + alpha * int p div(phi)
+void pe_assemble_projection_rhs(pe_ctx* c, int n_comp, const int32_t* comps, const int32_t* entries);
+
+// ---- kernels_solver.cu
+struct CgResult { int its; double res; int status; };
+void pe_halo_exchange(pe_ctx* c, Field& F, double* v);
+void pe_extract_invdiag(pe_ctx* c, Field& F, const double* val, double* invdiag);
+double pe_estimate_eig_max(pe_ctx* c, Field& F, const double* val, const double* invdiag);
+CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdiag, double eig_max, double* x, const double* b,
+                     double tol, bool tol_relative_to_b, int64_t* spmv_counter);
+void pe_spmv_plain(pe_ctx* c, Field& F, const double* val, const double* x, double* y);
+double pe_pressure_residual(pe_ctx* c, double dt);  // returns l2 norm (global)
+void pe_vec_axpy(pe_ctx* c, int64_t n, double a, const double* x, double* y);  // y += a x
+void pe_vec_copy(pe_ctx* c, int64_t n, const double* x, double* y);
+void pe_vec_set(pe_ctx* c, int64_t n, double a, double* y);
+void pe_vec_axpby_vals(pe_ctx* c, int64_t n, double a, const double* x, double b, const double* y, double* z);  // z = a x + b y
+void pe_distribute(pe_ctx* c, Field& F, double* v);  // constrained dofs <- inhomogeneity
+double pe_linfty(pe_ctx* c, Field& F, const double* v);
+void pe_stress_kernel(pe_ctx* c);
+void pe_allreduce_sum(pe_ctx* c, double* dev, int count);
+
+static inline int pe_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,175 @@
+// dofs.hpp — DoF numbering, support points and Dirichlet constraint tables without deal.II.
+//
+// Restates what the reference obtains from DoFHandler::distribute_dofs (PS:73, DS:110) for
+// FE_Q(k) / FESystem(FE_Q(k), dim), k in {1,2}: active cells are visited in order and indices
+// are handed out first-touch — the cell's vertices, then its lines, then (3D) its quads, then
+// the cell interior; each entity carries n_comp consecutive numbers.  No renumbering is
+// applied (the reference never calls DoFRenumbering).  Local dof (scalar s, component c) has
+// cell-local index s*n_comp + c (FESystem of identical Lagrange bases, vertex/line/quad/hex
+// blocks each with one scalar dof).
+// Dirichlet rows follow DS:117-135: VectorTools::interpolate_boundary_values per
+// (label, component, value) triple in list order; a dof constrained earlier is never
+// overwritten.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <unordered_map>
+#include <vector>
+
+#include "mesh.hpp"
+
+namespace dofs {
+
+// Reference-cell description of FE_Q(k), k<=2, in deal.II's local ordering.
+struct RefElement {
+  int dim = 0, degree = 0, n_scalar = 0;
+  std::vector<double> unit_support;  // n_scalar * dim
+  // entity -> reference vertices (for global identification)
+  std::vector<std::array<int, 2>> lines;
+  std::vector<std::array<int, 4>> quads;
+};
+
+inline RefElement make_ref_element(int dim, int degree) {
+  RefElement r;
+  r.dim = dim;
+  r.degree = degree;
+  if (dim == 2)
+    r.lines = {{0, 2}, {1, 3}, {0, 1}, {2, 3}};
+  else {
+    r.lines = {{0, 2}, {1, 3}, {0, 1}, {2, 3}, {4, 6}, {5, 7}, {4, 5}, {6, 7}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+    r.quads = {{0, 2, 4, 6}, {1, 3, 5, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}, {0, 1, 2, 3}, {4, 5, 6, 7}};
+  }
+  auto vcoord = [&](int v, int a) { return (double)((v >> a) & 1); };
+  int nv = 1 << dim;
+  for (int v = 0; v < nv; ++v)
+    for (int a = 0; a < dim; ++a) r.unit_support.push_back(vcoord(v, a));
+  if (degree == 2) {
+    for (auto& l : r.lines)
+      for (int a = 0; a < dim; ++a) r.unit_support.push_back(0.5 * (vcoord(l[0], a) + vcoord(l[1], a)));
+    for (auto& q : r.quads)
+      for (int a = 0; a < dim; ++a)
+        r.unit_support.push_back(0.25 * (vcoord(q[0], a) + vcoord(q[1], a) + vcoord(q[2], a) + vcoord(q[3], a)));
+    for (int a = 0; a < dim; ++a) r.unit_support.push_back(0.5);
+  }
+  r.n_scalar = (int)r.unit_support.size() / dim;
+  return r;
+}
+
+struct DofMap {
+  int degree = 1, n_comp = 1, n_loc = 0;
+  int64_t n_dofs = 0;
+  std::vector<int32_t> cell_dofs;  // n_cells * n_loc
+};
+
+struct PairHash {
+  size_t operator()(const std::pair<int64_t, int64_t>& p) const {
+    return std::hash<int64_t>()(p.first * 1000003LL ^ (p.second + 0x9e3779b97f4a7c15LL));
+  }
+};
+
+inline DofMap distribute_dofs(const mesh::Mesh& m, int degree, int n_comp) {
+  RefElement ref = make_ref_element(m.dim, degree);
+  DofMap d;
+  d.degree = degree;
+  d.n_comp = n_comp;
+  d.n_loc = ref.n_scalar * n_comp;
+  const int vpc = m.vpc();
+  const int64_t nc = m.n_cells();
+  d.cell_dofs.resize(nc * d.n_loc);
+  std::vector<int32_t> vdof(m.n_vertices(), -1);
+  std::unordered_map<std::pair<int64_t, int64_t>, int32_t, PairHash> line_dof, quad_dof;
+  int64_t next = 0;
+  for (int64_t c = 0; c < nc; ++c) {
+    const int32_t* cv = &m.cell_vertices[c * vpc];
+    int32_t* out = &d.cell_dofs[c * d.n_loc];
+    int s = 0;
+    for (int v = 0; v < vpc; ++v, ++s) {
+      if (vdof[cv[v]] < 0) { vdof[cv[v]] = (int32_t)next; next += n_comp; }
+      for (int k = 0; k < n_comp; ++k) out[s * n_comp + k] = vdof[cv[v]] + k;
+    }
+    if (degree == 2) {
+      for (auto& l : ref.lines) {
+        int64_t a = cv[l[0]], b = cv[l[1]];
+        if (a > b) std::swap(a, b);
+        auto it = line_dof.find({a, b});
+        int32_t base;
+        if (it == line_dof.end()) { base = (int32_t)next; line_dof[{a, b}] = base; next += n_comp; }
+        else base = it->second;
+        for (int k = 0; k < n_comp; ++k) out[s * n_comp + k] = base + k;
+        ++s;
+      }
+      for (auto& q : ref.quads) {
+        int64_t vs[4] = {cv[q[0]], cv[q[1]], cv[q[2]], cv[q[3]]};
+        std::sort(vs, vs + 4);
+        // a quad face is identified by its two smallest... all four vertices; pack (v0,v1) and (v2,v3)
+        std::pair<int64_t, int64_t> key{vs[0] * (int64_t)m.n_vertices() + vs[1], vs[2] * (int64_t)m.n_vertices() + vs[3]};
+        auto it = quad_dof.find(key);
+        int32_t base;
+        if (it == quad_dof.end()) { base = (int32_t)next; quad_dof[key] = base; next += n_comp; }
+        else base = it->second;
+        for (int k = 0; k < n_comp; ++k) out[s * n_comp + k] = base + k;
+        ++s;
+      }
+      for (int k = 0; k < n_comp; ++k) out[s * n_comp + k] = (int32_t)next + k;
+      next += n_comp;
+      ++s;
+    }
+  }
+  d.n_dofs = next;
+  return d;
+}
+
+// physical support point of every dof (Q1 mapping of the unit support points); n_dofs * dim
+inline std::vector<double> support_points(const mesh::Mesh& m, const DofMap& d) {
+  RefElement ref = make_ref_element(m.dim, d.degree);
+  const int dim = m.dim, vpc = m.vpc();
+  std::vector<double> sp(d.n_dofs * dim, 0.0);
+  for (int64_t c = 0; c < m.n_cells(); ++c)
+    for (int s = 0; s < ref.n_scalar; ++s) {
+      double x[3] = {0, 0, 0};
+      for (int v = 0; v < vpc; ++v) {
+        double N = 1;
+        for (int a = 0; a < dim; ++a) {
+          double xi = ref.unit_support[s * dim + a];
+          N *= ((v >> a) & 1) ? xi : 1 - xi;
+        }
+        for (int a = 0; a < dim; ++a) x[a] += N * m.xyz[(int64_t)m.cell_vertices[c * vpc + v] * dim + a];
+      }
+      for (int k = 0; k < d.n_comp; ++k) {
+        int32_t g = d.cell_dofs[c * d.n_loc + s * d.n_comp + k];
+        for (int a = 0; a < dim; ++a) sp[(int64_t)g * dim + a] = x[a];
+      }
+    }
+  return sp;
+}
+
+struct Constraints {  // pure-Dirichlet lines x_i = g_i, sorted by dof (ConstraintMatrix::close)
+  std::vector<int32_t> line_dof;
+  std::vector<double> inhomogeneity;
+};
+
+// DS:117-135
+inline Constraints make_dirichlet(const mesh::Mesh& m, const DofMap& d, const std::vector<int>& labels,
+                                  const std::vector<int>& comps, const std::vector<double>& values) {
+  RefElement ref = make_ref_element(m.dim, d.degree);
+  std::vector<uint8_t> is_c(d.n_dofs, 0);
+  std::vector<double> g(d.n_dofs, 0.0);
+  for (size_t cond = 0; cond < labels.size(); ++cond) {
+    for (int64_t b = 0; b < m.n_bfaces(); ++b) {
+      if (m.bface_id[b] != labels[cond]) continue;
+      int f = m.bface_local[b], axis = f / 2;
+      double side = f % 2;
+      for (int s = 0; s < ref.n_scalar; ++s) {
+        if (ref.unit_support[s * m.dim + axis] != side) continue;
+        int32_t dof = d.cell_dofs[(int64_t)m.bface_cell[b] * d.n_loc + s * d.n_comp + comps[cond]];
+        if (!is_c[dof]) { is_c[dof] = 1; g[dof] = values[cond]; }
+      }
+    }
+  }
+  Constraints c;
+  for (int64_t i = 0; i < d.n_dofs; ++i)
+    if (is_c[i]) { c.line_dof.push_back((int32_t)i); c.inhomogeneity.push_back(g[i]); }
+  return c;
+}
+
+}  // namespace dofs

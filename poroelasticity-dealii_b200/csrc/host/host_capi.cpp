@@ -1,0 +1,232 @@
+// host_capi.cpp — extern "C" surface of the host library (include/poroel_host.h).
+#include <cstring>
+#include <string>
+
+#include "../../../include/poroel_host.h"
+#include "dofs.hpp"
+#include "input_data.hpp"
+#include "mesh.hpp"
+#include "partition.hpp"
+#include "problem.hpp"
+
+static thread_local std::string g_err;
+
+struct peh_input {
+  input_data::InputDataPoroel d;
+  std::vector<int32_t> dl, dc, nl, nc;
+};
+struct peh_mesh { mesh::Mesh m; };
+struct peh_dofs { dofs::DofMap d; };
+struct peh_part { partition::Part p; };
+struct peh_problem {
+  std::unique_ptr<poro_elastisity::PoroElasticProblem> P;
+  peh_mesh local;  // view holder
+};
+
+#define PEH_TRY try {
+#define PEH_CATCH(ret)                 \
+  }                                    \
+  catch (const std::exception& e) {    \
+    g_err = e.what();                  \
+    return ret;                        \
+  }                                    \
+  catch (...) {                        \
+    g_err = "unknown exception";       \
+    return ret;                        \
+  }
+
+static void fill_mesh_view(const mesh::Mesh& m, peh_mesh_view* v) {
+  v->dim = m.dim;
+  v->morton = m.morton ? 1 : 0;
+  v->n_vertices = m.n_vertices();
+  v->n_cells = m.n_cells();
+  v->n_bfaces = m.n_bfaces();
+  v->xyz = m.xyz.data();
+  v->cell_vertices = m.cell_vertices.data();
+  v->bface_cell = m.bface_cell.data();
+  v->bface_local = m.bface_local.data();
+  v->bface_id = m.bface_id.data();
+}
+
+extern "C" {
+
+const char* peh_last_error(void) { return g_err.c_str(); }
+
+peh_input* peh_input_create(void) { return new peh_input(); }
+void peh_input_destroy(peh_input* p) { delete p; }
+int peh_input_read_file(peh_input* p, const char* path, int echo) {
+  PEH_TRY
+  p->d.read_input_file(path, echo != 0);
+  return 0;
+  PEH_CATCH(PE_ERR_BAD_INPUT)
+}
+int peh_input_read_string(peh_input* p, const char* text) {
+  PEH_TRY
+  p->d.read_input_string(text, false);
+  return 0;
+  PEH_CATCH(PE_ERR_BAD_INPUT)
+}
+int peh_input_view_get(peh_input* p, peh_input_view* v) {
+  const auto& d = p->d;
+  std::memset(v, 0, sizeof *v);
+  v->dim = d.dim;
+  v->initial_refinement_level = d.initial_refinement_level;
+  v->max_refinement_level = d.max_refinement_level;
+  v->max_fss_iterations = d.max_fss_iterations;
+  v->max_pressure_iterations = d.max_pressure_iterations;
+  v->displacement_degree = d.displacement_degree;
+  v->preconditioner = d.preconditioner;
+  v->chebyshev_degree = d.chebyshev_degree;
+  v->cg_max_iterations = d.cg_max_iterations;
+  v->mesh_from_file = d.mesh_from_file;
+  v->refine_every = d.refine_every;
+  v->couple_volumetric_strain = d.couple_volumetric_strain;
+  v->write_vtk = d.write_vtk;
+  v->max_time_steps = d.max_time_steps;
+  for (int i = 0; i < 3; ++i) {
+    v->cells_per_axis[i] = d.cells_per_axis[i];
+    v->domain_size[i] = i < (int)d.domain_size.size() ? d.domain_size[i] : 0.0;
+  }
+  v->perm = d.perm; v->poro = d.poro; v->visc = d.visc; v->f_comp = d.f_comp;
+  v->youngs_modulus = d.youngs_modulus; v->poisson_ratio = d.poisson_ratio; v->biot_coef = d.biot_coef;
+  v->bulk_density = d.bulk_density; v->r_well = d.r_well; v->flow_rate = d.flow_rate;
+  v->time_step = d.time_step; v->t_max = d.t_max; v->fss_tol = d.fss_tol; v->pressure_tol = d.pressure_tol; v->p_init = d.p_init;
+  v->lame_constant = d.lame_constant; v->shear_modulus = d.shear_modulus; v->bulk_modulus = d.bulk_modulus;
+  v->grain_bulk_modulus = d.grain_bulk_modulus; v->n_modulus = d.n_modulus; v->m_modulus = d.m_modulus;
+  v->chebyshev_eig_ratio = d.chebyshev_eig_ratio;
+  p->dl.assign(d.displacement_boundary_labels.begin(), d.displacement_boundary_labels.end());
+  p->dc.assign(d.displacement_boundary_components.begin(), d.displacement_boundary_components.end());
+  p->nl.assign(d.stress_boundary_labels.begin(), d.stress_boundary_labels.end());
+  p->nc.assign(d.stress_boundary_components.begin(), d.stress_boundary_components.end());
+  v->n_dirichlet = (int32_t)p->dl.size();
+  v->n_neumann = (int32_t)p->nl.size();
+  v->dirichlet_labels = p->dl.data(); v->dirichlet_components = p->dc.data(); v->dirichlet_values = d.displacement_boundary_values.data();
+  v->neumann_labels = p->nl.data(); v->neumann_components = p->nc.data(); v->neumann_values = d.stress_boundary_values.data();
+  return 0;
+}
+int peh_input_to_params(const peh_input* p, pe_params* out) { *out = poro_elastisity::params_from_input(p->d); return 0; }
+
+peh_mesh* peh_mesh_create_rectangle(int dim, const double* size, int refine_level) {
+  PEH_TRY
+  auto* m = new peh_mesh();
+  m->m = mesh::create_hyper_rectangle(dim, size, refine_level);
+  return m;
+  PEH_CATCH(nullptr)
+}
+peh_mesh* peh_mesh_create_subdivided(int dim, const double* size, const int32_t* n) {
+  PEH_TRY
+  auto* m = new peh_mesh();
+  int nn[3] = {n[0], n[1], dim == 3 ? n[2] : 1};
+  m->m = mesh::create_subdivided(dim, size, nn);
+  return m;
+  PEH_CATCH(nullptr)
+}
+peh_mesh* peh_mesh_read_msh(const char* path, int dim) {
+  PEH_TRY
+  auto* m = new peh_mesh();
+  m->m = mesh::read_msh(path, dim);
+  return m;
+  PEH_CATCH(nullptr)
+}
+void peh_mesh_destroy(peh_mesh* m) { delete m; }
+int peh_mesh_view_get(const peh_mesh* m, peh_mesh_view* v) { fill_mesh_view(m->m, v); return 0; }
+
+peh_dofs* peh_dofs_distribute(const peh_mesh* m, int degree, int n_comp) {
+  PEH_TRY
+  if (degree < 1 || degree > 2) throw std::runtime_error("degree must be 1 or 2");
+  auto* d = new peh_dofs();
+  d->d = dofs::distribute_dofs(m->m, degree, n_comp);
+  return d;
+  PEH_CATCH(nullptr)
+}
+void peh_dofs_destroy(peh_dofs* d) { delete d; }
+int peh_dofs_view_get(const peh_dofs* d, peh_dofs_view* v) {
+  v->degree = d->d.degree; v->n_comp = d->d.n_comp; v->n_loc = d->d.n_loc; v->reserved = 0;
+  v->n_dofs = d->d.n_dofs; v->cell_dofs = d->d.cell_dofs.data();
+  return 0;
+}
+int peh_dofs_support_points(const peh_mesh* m, const peh_dofs* d, double* out) {
+  PEH_TRY
+  std::vector<double> sp = dofs::support_points(m->m, d->d);
+  std::memcpy(out, sp.data(), sp.size() * sizeof(double));
+  return 0;
+  PEH_CATCH(PE_ERR_BAD_INPUT)
+}
+int64_t peh_make_dirichlet(const peh_mesh* m, const peh_dofs* d, int n, const int32_t* labels, const int32_t* comps, const double* values,
+                           int32_t* line_dof, double* inhomogeneity) {
+  PEH_TRY
+  std::vector<int> l(labels, labels + n), c(comps, comps + n);
+  std::vector<double> v(values, values + n);
+  dofs::Constraints cs = dofs::make_dirichlet(m->m, d->d, l, c, v);
+  if (line_dof) std::memcpy(line_dof, cs.line_dof.data(), cs.line_dof.size() * sizeof(int32_t));
+  if (inhomogeneity) std::memcpy(inhomogeneity, cs.inhomogeneity.data(), cs.inhomogeneity.size() * sizeof(double));
+  return (int64_t)cs.line_dof.size();
+  PEH_CATCH(-1)
+}
+
+peh_part* peh_partition(const peh_mesh* m, const peh_dofs* dp, const peh_dofs* du, int rank, int nranks) {
+  PEH_TRY
+  auto* p = new peh_part();
+  p->p = partition::make_part(m->m, dp->d, du->d, rank, nranks);
+  return p;
+  PEH_CATCH(nullptr)
+}
+void peh_part_destroy(peh_part* p) { delete p; }
+int peh_part_view_get(const peh_part* p, peh_part_view* v) {
+  fill_mesh_view(p->p.mesh, &v->mesh);
+  v->cell_global = p->p.cell_global.data();
+  v->n_owned_cells = p->p.n_owned_cells;
+  for (int f = 0; f < 2; ++f) {
+    const auto& F = p->p.field[f];
+    auto& o = v->field[f];
+    o.n_owned = F.n_owned; o.n_local = F.n_local; o.n_neighbors = (int32_t)F.neighbor_rank.size(); o.reserved = 0;
+    o.cell_dofs = F.cell_dofs.data(); o.local_to_global = F.local_to_global.data();
+    o.neighbor_rank = F.neighbor_rank.data(); o.send_ptr = F.send_ptr.data(); o.send_idx = F.send_idx.data(); o.recv_ptr = F.recv_ptr.data();
+  }
+  return 0;
+}
+
+peh_problem* peh_problem_create(const peh_input* in, int device, int rank, int nranks, const void* nccl_id, size_t id_bytes) {
+  PEH_TRY
+  auto* p = new peh_problem();
+  p->P.reset(new poro_elastisity::PoroElasticProblem(in->d, device, rank, nranks, nccl_id, id_bytes));
+  return p;
+  PEH_CATCH(nullptr)
+}
+void peh_problem_destroy(peh_problem* p) { delete p; }
+int peh_problem_initialize(peh_problem* p, int verbose) {
+  PEH_TRY
+  p->P->initialize(verbose != 0);
+  return 0;
+  PEH_CATCH(PE_ERR_STATE)
+}
+int peh_problem_step(peh_problem* p, int verbose, peh_step_report* out) {
+  PEH_TRY
+  poro_elastisity::StepReport R = p->P->step(verbose != 0);
+  if (out) {
+    out->time = R.time; out->time_step_number = R.time_step_number; out->fss_iterations = R.fss_iterations;
+    out->pressure_iterations = R.pressure_iterations; out->cg_its_pressure = R.cg_its_pressure;
+    out->cg_its_displacement = R.cg_its_displacement; out->cg_its_projection = R.cg_its_projection; out->status = 0;
+    out->pressure_error = R.pressure_error; out->pressure_linfty = R.pressure_linfty;
+  }
+  return 0;
+  PEH_CATCH(PE_ERR_STATE)
+}
+int peh_problem_run(peh_problem* p, int verbose) {
+  PEH_TRY
+  p->P->run(verbose != 0);
+  return 0;
+  PEH_CATCH(PE_ERR_STATE)
+}
+pe_ctx* peh_problem_ctx(peh_problem* p) { return p->P->ctx; }
+const peh_mesh* peh_problem_mesh(peh_problem* p) {
+  p->local.m = *p->P->local_mesh;
+  return &p->local;
+}
+int peh_problem_global_ids(peh_problem* p, int field, int64_t* out) {
+  const auto& g = p->P->global_ids[field];
+  std::memcpy(out, g.data(), g.size() * sizeof(int64_t));
+  return (int)g.size();
+}
+
+}  // extern "C"

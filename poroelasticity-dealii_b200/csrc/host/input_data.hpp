@@ -1,0 +1,317 @@
+// input_data.hpp — the reference's parameter-file surface without deal.II.
+//
+// Re-implements the grammar of dealii::ParameterHandler::read_input for exactly the keys,
+// defaults and ranges that InputDataPoroel declares (lib/include/InputDataPoroel.h:89-147),
+// the assignment incl. the milli-darcy conversion (ID:150-210) and the derived moduli
+// (ID:213-222).  A shipped `input.data` parses unchanged.  Extra keys for the GPU path live
+// in their own `subsection GPU`, which the reference would not know about.
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <limits>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace input_data {
+
+struct Entry {
+  std::string value, def;
+  char type = 'd';  // 'i' integer, 'd' double, 'I' list<int>, 'D' list<double>
+  double lo = -std::numeric_limits<double>::max(), hi = std::numeric_limits<double>::max();
+};
+
+inline std::string trim(const std::string& s) {
+  size_t a = s.find_first_not_of(" \t\r\n");
+  if (a == std::string::npos) return "";
+  size_t b = s.find_last_not_of(" \t\r\n");
+  return s.substr(a, b - a + 1);
+}
+inline std::string collapse_ws(const std::string& s) {
+  std::string out;
+  bool sp = false;
+  for (char c : trim(s)) {
+    if (c == ' ' || c == '\t') { sp = true; continue; }
+    if (sp && !out.empty()) out += ' ';
+    sp = false;
+    out += c;
+  }
+  return out;
+}
+
+// ID:9-25 parse_string_list<T> (boost::split on ',' then operator>>)
+template <typename T>
+std::vector<T> parse_string_list(const std::string& list_string) {
+  std::vector<T> list;
+  if (trim(list_string).empty()) return list;
+  std::stringstream ss(list_string);
+  std::string item;
+  while (std::getline(ss, item, ',')) {
+    std::stringstream convert(item);
+    T v{};
+    convert >> v;
+    list.push_back(v);
+  }
+  return list;
+}
+
+class InputDataPoroel {
+ public:
+  // mesh data (ID:49-52)
+  int dim = 2;
+  std::vector<double> domain_size;
+  int initial_refinement_level = 3, max_refinement_level = 5;
+  // equation data (ID:53-57)
+  double perm = 0, poro = 0, visc = 0, f_comp = 0;
+  double youngs_modulus = 0, poisson_ratio = 0, biot_coef = 0;
+  double bulk_density = 0, r_well = 0, flow_rate = 0;
+  // solver control (ID:58-61)
+  double time_step = 60, t_max = 60, fss_tol = 1e-8, pressure_tol = 1e-8;
+  int max_fss_iterations = 50, max_pressure_iterations = 50;
+  // in situ (ID:62-66)
+  double p_init = 0;
+  std::vector<int> stress_boundary_labels, displacement_boundary_labels;
+  std::vector<int> stress_boundary_components, displacement_boundary_components;
+  std::vector<double> stress_boundary_values, displacement_boundary_values;
+  // derived (ID:68-70)
+  double lame_constant = 0, shear_modulus = 0, bulk_modulus = 0, grain_bulk_modulus = 0, n_modulus = 0,
+         m_modulus = 0;
+
+  // --- GPU-path extensions (subsection GPU; not in the reference) ---
+  int displacement_degree = 2;      // DS:67 hard-codes 2; BASELINE configs 3-5 ask for 1
+  int cells_per_axis[3] = {0, 0, 0};// non-zero => lexicographic subdivided box instead of refine_global
+  int mesh_from_file = 0;           // 1 => read_mesh() "domain.msh" (FSS:438-445) instead of create_mesh()
+  std::string mesh_file = "domain.msh";
+  int preconditioner = 1;           // 0 Jacobi, 1 Chebyshev-Jacobi
+  int chebyshev_degree = 4;
+  double chebyshev_eig_ratio = 30.0;
+  int cg_max_iterations = 1000;     // PS:175, DS:299, SP:209
+  int refine_every = 0;             // reference: 5 (FSS:333); AMR is out of scope => 0 = never
+  int couple_volumetric_strain = 0; // 1 re-enables FSS:399
+  int write_vtk = 0;                // FSS:411
+  int max_time_steps = 0;           // 0 = until t_max
+
+  InputDataPoroel() { declare_parameters(); }
+
+  void read_input_file(const std::string& file_name, bool echo = true) {  // ID:77-86
+    std::ifstream f(file_name);
+    if (!f) throw std::runtime_error("cannot open input file " + file_name);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    read_input_string(ss.str(), echo);
+  }
+
+  void read_input_string(const std::string& text, bool echo = false) {
+    parse(text);
+    if (echo) print_parameters(stdout);
+    assign_parameters();
+    compute_derived_parameters();
+  }
+
+  void print_parameters(FILE* out) const {  // ParameterHandler::print_parameters(Text), ID:82
+    std::fprintf(out, "# Listing of Parameters\n# ---------------------\n");
+    for (const auto& sec : prm) {
+      size_t w = 0;
+      for (const auto& e : sec.second) w = std::max(w, e.first.size());
+      std::fprintf(out, "subsection %s\n", sec.first.c_str());
+      for (const auto& e : sec.second)
+        std::fprintf(out, "  set %-*s = %s\n", (int)w, e.first.c_str(), e.second.value.c_str());
+      std::fprintf(out, "end\n\n\n");
+    }
+  }
+
+  void compute_derived_parameters() {  // ID:213-222
+    double E = youngs_modulus, nu = poisson_ratio;
+    lame_constant = E * nu / ((1. + nu) * (1. - 2. * nu));
+    shear_modulus = 0.5 * E / (1 + nu);
+    bulk_modulus = lame_constant + 2. / 3. * shear_modulus;
+    grain_bulk_modulus = bulk_modulus / (1. - biot_coef);
+    n_modulus = grain_bulk_modulus / (biot_coef - poro);
+    m_modulus = (n_modulus / f_comp) / (n_modulus * poro + 1. / f_comp);
+  }
+
+ private:
+  std::map<std::string, std::map<std::string, Entry>> prm;
+
+  void declare(const std::string& sec, const std::string& key, const std::string& def, char type,
+               double lo = -std::numeric_limits<double>::max(), double hi = std::numeric_limits<double>::max()) {
+    Entry e;
+    e.value = e.def = def;
+    e.type = type;
+    e.lo = lo;
+    e.hi = hi;
+    prm[sec][key] = e;
+  }
+
+  void declare_parameters() {  // ID:89-147
+    declare("Mesh", "Dimensions", "2", 'i', 1, 3);
+    declare("Mesh", "Domain size", "10, 10", 'D');
+    declare("Mesh", "Initial refinement level", "3", 'i', 2);
+    declare("Mesh", "Max refinement level", "5", 'i', 2);
+    declare("Properties", "Young modulus", "7e9", 'd', 1);
+    declare("Properties", "Poisson ratio", "0.3", 'd', 0, 0.5);
+    declare("Properties", "Biot coefficient", "0.9", 'd', 0.1, 1);
+    declare("Properties", "Permeability", "1", 'd', 1e-20, 1e5);
+    declare("Properties", "Porosity", "0.3", 'd', 1e-5, 0.99999);
+    declare("Properties", "Viscosity", "1e-3", 'd', 1e-6, 1);
+    declare("Properties", "Bulk density", "2700", 'd', 5e2, 1e4);
+    declare("Properties", "Fluid compressibility", "45.8e-11", 'd', 1e-16, 1e-2);
+    declare("Properties", "Well radius", "0.1", 'd', 1e-2);
+    declare("Properties", "Flow rate", "1e-6", 'd');
+    declare("In situ", "Initial pressure", "10e6", 'd', 0);
+    declare("In situ", "Stress boundary labels", "", 'I');
+    declare("In situ", "Stress boundary components", "", 'I', 0, 2);
+    declare("In situ", "Stress boundary values", "", 'D');
+    declare("In situ", "Displacement boundary labels", "0, 2, 3, 1", 'I');
+    declare("In situ", "Displacement boundary components", "1, 1, 0, 0", 'I', 0, 2);
+    declare("In situ", "Displacement boundary values", "0, 0, 0, -0.1", 'D');
+    declare("Solver", "Time step", "60", 'd', 1e-8);
+    declare("Solver", "Time max", "60", 'd', 1e-8);
+    declare("Solver", "Max FSS iterations", "50", 'i', 1, 1000);
+    declare("Solver", "Max pressure iterations", "50", 'i', 1, 1000);
+    declare("Solver", "FSS tolerance", "1e-8", 'd', 1e-20, 1e-1);
+    declare("Solver", "Pressure tolerance", "1e-8", 'd', 1e-20, 1e-1);
+    // extensions
+    declare("GPU", "Displacement FE degree", "2", 'i', 1, 2);
+    declare("GPU", "Cells per axis", "", 'I', 1);
+    declare("GPU", "Read mesh file", "0", 'i', 0, 1);
+    declare("GPU", "Preconditioner", "1", 'i', 0, 1);
+    declare("GPU", "Chebyshev degree", "4", 'i', 1, 64);
+    declare("GPU", "Chebyshev eigenvalue ratio", "30", 'd', 1.0001);
+    declare("GPU", "CG max iterations", "1000", 'i', 1);
+    declare("GPU", "Refine every", "0", 'i', 0);
+    declare("GPU", "Couple volumetric strain", "0", 'i', 0, 1);
+    declare("GPU", "Write VTK", "0", 'i', 0, 1);
+    declare("GPU", "Max time steps", "0", 'i', 0);
+  }
+
+  static bool check_scalar(const std::string& v, const Entry& e) {
+    std::string t = trim(v);
+    if (t.empty()) return false;
+    char* end = nullptr;
+    if (e.type == 'i' || e.type == 'I') {
+      long x = std::strtol(t.c_str(), &end, 10);
+      if (*end) return false;
+      return x >= e.lo && x <= e.hi;
+    }
+    double x = std::strtod(t.c_str(), &end);
+    if (*end) return false;
+    return x >= e.lo && x <= e.hi;
+  }
+
+  static bool check(const std::string& v, const Entry& e) {
+    if (e.type == 'i' || e.type == 'd') return check_scalar(v, e);
+    if (trim(v).empty()) return true;
+    std::stringstream ss(v);
+    std::string item;
+    while (std::getline(ss, item, ','))
+      if (!check_scalar(item, e)) return false;
+    return true;
+  }
+
+  void parse(const std::string& text) {
+    std::vector<std::string> path;
+    std::stringstream ss(text);
+    std::string raw;
+    int lineno = 0;
+    while (std::getline(ss, raw)) {
+      ++lineno;
+      size_t hash = raw.find('#');
+      if (hash != std::string::npos) raw = raw.substr(0, hash);
+      std::string line = collapse_ws(raw);
+      if (line.empty()) continue;
+      auto fail = [&](const std::string& msg) {
+        throw std::runtime_error("input line " + std::to_string(lineno) + ": " + msg);
+      };
+      if (line.rfind("subsection ", 0) == 0 || line.rfind("SUBSECTION ", 0) == 0) {
+        std::string name = trim(line.substr(11));
+        if (!prm.count(name)) fail("There is no such subsection to be entered: " + name);
+        if (!path.empty()) fail("nested subsections are not declared by InputDataPoroel");
+        path.push_back(name);
+      } else if (line == "end" || line == "END") {
+        if (path.empty()) fail("There is no subsection to leave here");
+        path.pop_back();
+      } else if (line.rfind("set ", 0) == 0 || line.rfind("SET ", 0) == 0) {
+        size_t eq = line.find('=');
+        if (eq == std::string::npos) fail("invalid format of set expression");
+        std::string key = collapse_ws(line.substr(4, eq - 4));
+        std::string val = trim(line.substr(eq + 1));
+        if (path.empty()) fail("No such entry was declared: " + key);
+        auto& sec = prm[path.back()];
+        auto it = sec.find(key);
+        if (it == sec.end()) fail("No such entry was declared: " + key);
+        if (!check(val, it->second)) fail("The entry value '" + val + "' for the entry named '" + key + "' does not match the given pattern");
+        it->second.value = val;
+      } else {
+        fail("could not be parsed: " + line);
+      }
+    }
+    if (!path.empty()) throw std::runtime_error("Unbalanced 'subsection'/'end' in input");
+  }
+
+  double get_double(const char* s, const char* k) const { return std::strtod(prm.at(s).at(k).value.c_str(), nullptr); }
+  long get_integer(const char* s, const char* k) const { return std::strtol(prm.at(s).at(k).value.c_str(), nullptr, 10); }
+  const std::string& get(const char* s, const char* k) const { return prm.at(s).at(k).value; }
+
+  void assign_parameters() {  // ID:150-210
+    dim = (int)get_integer("Mesh", "Dimensions");
+    domain_size = parse_string_list<double>(get("Mesh", "Domain size"));
+    initial_refinement_level = (int)get_integer("Mesh", "Initial refinement level");
+    max_refinement_level = (int)get_integer("Mesh", "Max refinement level");
+    const double mili_darcy = 9.869233e-16;
+    youngs_modulus = get_double("Properties", "Young modulus");
+    poisson_ratio = get_double("Properties", "Poisson ratio");
+    biot_coef = get_double("Properties", "Biot coefficient");
+    perm = get_double("Properties", "Permeability");
+    perm *= mili_darcy;
+    poro = get_double("Properties", "Porosity");
+    visc = get_double("Properties", "Viscosity");
+    bulk_density = get_double("Properties", "Bulk density");
+    f_comp = get_double("Properties", "Fluid compressibility");
+    r_well = get_double("Properties", "Well radius");
+    flow_rate = get_double("Properties", "Flow rate");
+    p_init = get_double("In situ", "Initial pressure");
+    stress_boundary_labels = parse_string_list<int>(get("In situ", "Stress boundary labels"));
+    stress_boundary_components = parse_string_list<int>(get("In situ", "Stress boundary components"));
+    stress_boundary_values = parse_string_list<double>(get("In situ", "Stress boundary values"));
+    displacement_boundary_labels = parse_string_list<int>(get("In situ", "Displacement boundary labels"));
+    displacement_boundary_components = parse_string_list<int>(get("In situ", "Displacement boundary components"));
+    displacement_boundary_values = parse_string_list<double>(get("In situ", "Displacement boundary values"));
+    time_step = get_double("Solver", "Time step");
+    t_max = get_double("Solver", "Time max");
+    fss_tol = get_double("Solver", "FSS tolerance");
+    pressure_tol = get_double("Solver", "Pressure tolerance");
+    max_fss_iterations = (int)get_integer("Solver", "Max FSS iterations");
+    max_pressure_iterations = (int)get_integer("Solver", "Max pressure iterations");
+    // extensions
+    displacement_degree = (int)get_integer("GPU", "Displacement FE degree");
+    std::vector<int> cpa = parse_string_list<int>(get("GPU", "Cells per axis"));
+    for (int i = 0; i < 3; ++i) cells_per_axis[i] = i < (int)cpa.size() ? cpa[i] : 0;
+    mesh_from_file = (int)get_integer("GPU", "Read mesh file");
+    preconditioner = (int)get_integer("GPU", "Preconditioner");
+    chebyshev_degree = (int)get_integer("GPU", "Chebyshev degree");
+    chebyshev_eig_ratio = get_double("GPU", "Chebyshev eigenvalue ratio");
+    cg_max_iterations = (int)get_integer("GPU", "CG max iterations");
+    refine_every = (int)get_integer("GPU", "Refine every");
+    couple_volumetric_strain = (int)get_integer("GPU", "Couple volumetric strain");
+    write_vtk = (int)get_integer("GPU", "Write VTK");
+    max_time_steps = (int)get_integer("GPU", "Max time steps");
+    if ((int)domain_size.size() < dim)
+      throw std::runtime_error("'Domain size' needs at least 'Dimensions' entries (FSS:423-426)");
+    if (displacement_boundary_labels.size() != displacement_boundary_components.size() ||
+        displacement_boundary_labels.size() != displacement_boundary_values.size())
+      throw std::runtime_error("Displacement boundary lists differ in length (BC:34-35)");
+    if (stress_boundary_labels.size() != stress_boundary_components.size() ||
+        stress_boundary_labels.size() != stress_boundary_values.size())
+      throw std::runtime_error("Stress boundary lists differ in length (BC:52-53)");
+    for (int c : displacement_boundary_components)
+      if (c >= dim) throw std::runtime_error("Displacement boundary component >= dim (BC:37-38)");
+    for (int c : stress_boundary_components)
+      if (c >= dim) throw std::runtime_error("Stress boundary component >= dim (BC:55-57)");
+  }
+};
+
+}  // namespace input_data

@@ -1,0 +1,325 @@
+// problem.hpp — the solver driver the reference lacks a main() for.
+//
+// poro_elastisity::PoroElasticProblem<dim> (lib/include/PoroelasticityFSS.h:49-90) re-written as
+// plain host C++ whose only numerical back end is the CUDA device library behind
+// include/poroel.h.  The loop structure, the order of operator calls, the convergence tests and the
+// log lines are those of PoroElasticProblem::run (FSS:294-415), with the as-is quirks kept:
+//   * mechanics -> flow feedback off unless `Couple volumetric strain = 1` (FSS:399 is commented out);
+//   * the initial volumetric strain is the reference state for all steps (FSS:317, PS:122-124);
+//   * create_mesh() is the default, read_mesh() optional (FSS:297-298).
+// AMR (FSS:333-340) is out of scope: `Refine every` must be 0.
+#pragma once
+#include <cstdio>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/poroel.h"
+#include "dofs.hpp"
+#include "input_data.hpp"
+#include "mesh.hpp"
+#include "partition.hpp"
+
+namespace poro_elastisity {
+
+struct StepReport {
+  double time = 0;
+  int time_step_number = 0, fss_iterations = 0, pressure_iterations = 0;
+  int cg_its_pressure = 0, cg_its_displacement = 0, cg_its_projection = 0;
+  int status = 0;
+  double pressure_error = 0, pressure_linfty = 0;
+};
+
+inline pe_params params_from_input(const input_data::InputDataPoroel& d) {
+  pe_params p{};
+  p.dim = d.dim;
+  p.degree_u = d.displacement_degree;
+  p.degree_p = 1;  // PS:20
+  p.preconditioner = d.preconditioner;
+  p.chebyshev_degree = d.chebyshev_degree;
+  p.cg_max_iterations = d.cg_max_iterations;
+  p.cg_check_interval = 0;
+  p.lame_lambda = d.lame_constant;
+  p.shear_modulus = d.shear_modulus;
+  p.bulk_modulus = d.bulk_modulus;
+  p.biot_coef = d.biot_coef;
+  p.m_modulus = d.m_modulus;
+  p.perm_over_visc = d.perm / d.visc;
+  p.well_radius = d.r_well;
+  p.flow_rate = d.flow_rate;
+  p.cg_rel_tol_pressure = 1e-8;       // PS:175
+  p.cg_abs_tol_displacement = 1e-12;  // DS:298
+  p.cg_rel_tol_projection = 1e-8;     // SP:209
+  p.chebyshev_eig_ratio = d.chebyshev_eig_ratio;
+  return p;
+}
+
+class PoroElasticProblem {
+ public:
+  PoroElasticProblem(const input_data::InputDataPoroel& data_, int device, int rank_, int nranks_, const void* nccl_id, size_t id_bytes)
+      : data(data_), rank(rank_), nranks(nranks_) {
+    dim = data.dim;
+    // FSS:92-124
+    n_stress_components = (dim * dim + dim) / 2;
+    if (dim == 2) { strain_tensor_volumetric_components = {0, 3}; strain_tensor_shear_components = {1}; }
+    else if (dim == 3) { strain_tensor_volumetric_components = {0, 4, 8}; strain_tensor_shear_components = {1, 2, 5}; }
+    else throw std::runtime_error("PoroElasticProblem: dim must be 2 or 3");
+    for (int c : strain_tensor_volumetric_components) strain_rhs_volumetric_entries.push_back(entryIndex(c));
+    int rc = pe_create(&ctx, device, rank, nranks, nccl_id, id_bytes);
+    if (rc != 0) throw std::runtime_error(std::string("pe_create: ") + pe_last_error(nullptr));
+  }
+  ~PoroElasticProblem() { if (ctx) pe_destroy(ctx); }
+  PoroElasticProblem(const PoroElasticProblem&) = delete;
+
+  // TensorIndexer<dim>::entryIndex (TensorIndexer.h:18-52)
+  int entryIndex(int tensor_index) const {
+    static const int m2[4] = {0, 1, 1, 2}, m3[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
+    return dim == 2 ? m2[tensor_index] : m3[tensor_index];
+  }
+
+  void check(int rc, const char* what) {
+    if (rc != 0) throw std::runtime_error(std::string(what) + ": " + pe_last_error(ctx) + " (status " + std::to_string(rc) + ")");
+  }
+
+  // FSS:297-317
+  void initialize(bool verbose) {
+    if (data.refine_every != 0) throw std::runtime_error("adaptive refinement (FSS:333-340) is out of scope: set 'Refine every = 0'");
+    // create_mesh() / read_mesh()
+    if (data.mesh_from_file) global_mesh = mesh::read_msh(data.mesh_file, dim);
+    else if (data.cells_per_axis[0] > 0) global_mesh = mesh::create_subdivided(dim, data.domain_size.data(), data.cells_per_axis);
+    else global_mesh = mesh::create_hyper_rectangle(dim, data.domain_size.data(), data.initial_refinement_level);
+    // setup_dofs(): distribute_dofs for both handlers (PS:73, DS:110)
+    dofs::DofMap dp = dofs::distribute_dofs(global_mesh, 1, 1);
+    dofs::DofMap du = dofs::distribute_dofs(global_mesh, data.displacement_degree, dim);
+    n_global_p = dp.n_dofs;
+    n_global_u = du.n_dofs;
+    // displacement_solver.set_boundary_conditions (FSS:300-306) -> Dirichlet lines (DS:117-135)
+    dofs::Constraints cons = dofs::make_dirichlet(global_mesh, du, data.displacement_boundary_labels,
+                                                  data.displacement_boundary_components, data.displacement_boundary_values);
+    pe_params prm = params_from_input(data);
+    check(pe_set_params(ctx, &prm), "pe_set_params");
+    const mesh::Mesh* lm = &global_mesh;
+    const int32_t *cdp = dp.cell_dofs.data(), *cdu = du.cell_dofs.data();
+    int64_t nlp = dp.n_dofs, nlu = du.n_dofs;
+    std::vector<int32_t> line_dof = cons.line_dof;
+    std::vector<double> line_g = cons.inhomogeneity;
+    if (nranks > 1) {
+      part = partition::make_part(global_mesh, dp, du, rank, nranks);
+      lm = &part.mesh;
+      cdp = part.field[0].cell_dofs.data();
+      cdu = part.field[1].cell_dofs.data();
+      nlp = part.field[0].n_local;
+      nlu = part.field[1].n_local;
+      std::vector<int32_t> g2l(du.n_dofs, -1);
+      for (int64_t i = 0; i < nlu; ++i) g2l[part.field[1].local_to_global[i]] = (int32_t)i;
+      line_dof.clear();
+      line_g.clear();
+      std::vector<std::pair<int32_t, double>> ll;
+      for (size_t i = 0; i < cons.line_dof.size(); ++i)
+        if (g2l[cons.line_dof[i]] >= 0) ll.push_back({g2l[cons.line_dof[i]], cons.inhomogeneity[i]});
+      std::sort(ll.begin(), ll.end());
+      for (auto& e : ll) { line_dof.push_back(e.first); line_g.push_back(e.second); }
+      global_ids[0] = std::vector<int64_t>(part.field[0].local_to_global.begin(), part.field[0].local_to_global.begin() + part.field[0].n_owned);
+      global_ids[1] = std::vector<int64_t>(part.field[1].local_to_global.begin(), part.field[1].local_to_global.begin() + part.field[1].n_owned);
+    } else {
+      global_ids[0].resize(nlp);
+      global_ids[1].resize(nlu);
+      for (int64_t i = 0; i < nlp; ++i) global_ids[0][i] = i;
+      for (int64_t i = 0; i < nlu; ++i) global_ids[1][i] = i;
+    }
+    check(pe_upload_mesh(ctx, dim, lm->n_vertices(), lm->xyz.data(), lm->n_cells(), lm->cell_vertices.data(), lm->n_bfaces(),
+                         lm->bface_cell.data(), lm->bface_local.data(), lm->bface_id.data()), "pe_upload_mesh");
+    check(pe_upload_dofs(ctx, PE_FIELD_PRESSURE, nlp, cdp), "pe_upload_dofs(p)");
+    check(pe_upload_dofs(ctx, PE_FIELD_DISPLACEMENT, nlu, cdu), "pe_upload_dofs(u)");
+    std::vector<int64_t> eptr(line_dof.size() + 1, 0);
+    check(pe_upload_constraints(ctx, PE_FIELD_DISPLACEMENT, (int64_t)line_dof.size(), line_dof.data(), eptr.data(), nullptr, nullptr, line_g.data()),
+          "pe_upload_constraints");
+    std::vector<int32_t> nl(data.stress_boundary_labels.begin(), data.stress_boundary_labels.end()),
+        ncmp(data.stress_boundary_components.begin(), data.stress_boundary_components.end());
+    check(pe_upload_neumann(ctx, (int)nl.size(), nl.data(), ncmp.data(), data.stress_boundary_values.data()), "pe_upload_neumann");
+    if (nranks > 1)
+      for (int f = 0; f < 2; ++f) {
+        auto& F = part.field[f];
+        check(pe_upload_partition(ctx, f, F.n_owned, (int)F.neighbor_rank.size(), F.neighbor_rank.data(), F.send_ptr.data(), F.send_idx.data(),
+                                  F.recv_ptr.data()), "pe_upload_partition");
+      }
+    local_mesh = lm;
+    check(pe_setup(ctx), "pe_setup");
+    if (nranks == 1) { /* keep the global mesh for output */ }
+
+    // Initialize reservoir (FSS:310-317)
+    check(pe_pressure_set_uniform(ctx, data.p_init), "pressure_set_uniform");
+    check(pe_displacement_assemble(ctx), "displacement_assemble");
+    int its = 0;
+    double res = 0;
+    check(pe_displacement_solve(ctx, &its, &res), "displacement_solve");
+    if (verbose && rank == 0) std::printf("initial displacement solve: %d CG iterations, residual %.3e\n", its, res);
+    check(pe_project_assemble_matrix(ctx), "project_assemble_matrix");
+    int pits = 0;
+    get_normal_strain_components(&pits);
+    get_volumetric_strain(/*as_initial=*/true);
+    time = 0;
+    time_step_number = 0;
+  }
+
+  // FSS:153-164
+  void get_normal_strain_components(int* cg_its) {
+    std::vector<int32_t> comps(strain_tensor_volumetric_components.begin(), strain_tensor_volumetric_components.end());
+    check(pe_project_assemble_rhs(ctx, (int)comps.size(), comps.data()), "project_assemble_rhs");
+    for (int comp : strain_tensor_volumetric_components) {
+      int its = 0;
+      check(pe_project_solve(ctx, entryIndex(comp), &its), "project_solve");
+      if (cg_its) *cg_its += its;
+    }
+  }
+  // FSS:167-176
+  void get_shear_strain_components() {
+    std::vector<int32_t> comps(strain_tensor_shear_components.begin(), strain_tensor_shear_components.end());
+    // the reference never assembles the shear right-hand sides (projection_rhs stays zero for them);
+    // here they are assembled so the optional stress output is meaningful.
+    check(pe_project_assemble_rhs(ctx, (int)comps.size(), comps.data()), "project_assemble_rhs(shear)");
+    for (int comp : strain_tensor_shear_components) {
+      int its = 0;
+      check(pe_project_solve(ctx, entryIndex(comp), &its), "project_solve(shear)");
+    }
+  }
+  // FSS:179-186 (+ FSS:317 when as_initial)
+  void get_volumetric_strain(bool as_initial) {
+    std::vector<int32_t> e(strain_rhs_volumetric_entries.begin(), strain_rhs_volumetric_entries.end());
+    check(pe_volumetric_strain_from_projection(ctx, (int)e.size(), e.data(), as_initial ? 1 : 0), "volumetric_strain");
+  }
+
+  // One pass of FSS:328-407
+  StepReport step(bool verbose) {
+    StepReport R;
+    const double time_step = data.time_step;
+    time += time_step;
+    time_step_number++;
+    R.time = time;
+    R.time_step_number = time_step_number;
+    const bool out = verbose && rank == 0;
+    if (out) std::printf("Time: %g\n", time);
+    check(pe_pressure_begin_step(ctx), "begin_step");  // FSS:342
+    double pressure_error = data.pressure_tol * 2;      // FSS:345
+    int fss_iteration = 0;
+    while (fss_iteration < data.max_fss_iterations && pressure_error > data.fss_tol) {
+      fss_iteration++;
+      if (out) std::printf("    Coupling iteration: %d\n", fss_iteration);
+      int pressure_iteration = 0;
+      check(pe_pressure_zero_update(ctx), "zero_update");  // FSS:356
+      while (pressure_iteration < data.max_pressure_iterations) {
+        pressure_iteration++;
+        R.pressure_iterations++;
+        check(pe_pressure_update_volumetric_strain(ctx), "update_volumetric_strain");
+        check(pe_pressure_assemble_residual(ctx, time_step, &pressure_error), "assemble_residual");
+        if (pressure_error < data.pressure_tol) {
+          if (out) std::printf("        pressure converged; iterations: %d\n", pressure_iteration - 1);
+          break;
+        }
+        check(pe_pressure_assemble_jacobian(ctx, time_step), "assemble_jacobian");
+        int its = 0;
+        double res = 0;
+        check(pe_pressure_solve(ctx, &its, &res), "pressure_solve");
+        R.cg_its_pressure += its;
+        check(pe_pressure_add_update(ctx), "add_update");  // FSS:379
+      }
+      check(pe_pressure_linfty(ctx, &R.pressure_linfty), "linfty");
+      if (out) std::printf("Solution limits: %g\t\n", R.pressure_linfty);
+      // Solve displacement system (FSS:395-396)
+      check(pe_displacement_assemble(ctx), "displacement_assemble");
+      int its = 0;
+      double res = 0;
+      check(pe_displacement_solve(ctx, &its, &res), "displacement_solve");
+      R.cg_its_displacement += its;
+      get_normal_strain_components(&R.cg_its_projection);  // FSS:398
+      if (data.couple_volumetric_strain) get_volumetric_strain(false);  // FSS:399 (commented out in the reference)
+      check(pe_pressure_assemble_residual(ctx, time_step, &pressure_error), "assemble_residual");  // FSS:402-405
+      if (out) std::printf("        Error: %g\n", pressure_error);
+    }
+    R.fss_iterations = fss_iteration;
+    R.pressure_error = pressure_error;
+    return R;
+  }
+
+  // FSS:294-415
+  void run(bool verbose) {
+    initialize(verbose);
+    if (verbose && rank == 0) {
+      std::printf("starting time loop\n");
+      std::printf("time max %g\n", data.t_max);
+    }
+    while (time < data.t_max) {
+      StepReport R = step(verbose);
+      (void)R;
+      if (data.write_vtk) {
+        get_shear_strain_components();                      // FSS:409
+        check(pe_effective_stresses(ctx), "stresses");      // FSS:410
+        output_results(time_step_number);                   // FSS:411
+      }
+      if (data.max_time_steps > 0 && time_step_number >= data.max_time_steps) break;
+    }
+  }
+
+  // FSS:227-291 — minimal legacy-VTK writer (Q1 patches of the local mesh; single rank only)
+  void output_results(unsigned int n) {
+    if (nranks != 1 || data.displacement_degree != 1) return;  // Q2 displacement would need interpolation to vertices
+    const mesh::Mesh& m = global_mesh;
+    dofs::DofMap dp = dofs::distribute_dofs(m, 1, 1);
+    std::vector<double> p(n_global_p), u(n_global_u);
+    check(pe_get_vector(ctx, PE_VEC_P, p.data(), n_global_p), "get p");
+    check(pe_get_vector(ctx, PE_VEC_U, u.data(), n_global_u), "get u");
+    std::vector<int32_t> v2d(m.n_vertices(), -1);
+    const int vpc = m.vpc();
+    for (int64_t c = 0; c < m.n_cells(); ++c)
+      for (int v = 0; v < vpc; ++v) v2d[m.cell_vertices[c * vpc + v]] = dp.cell_dofs[c * vpc + v];
+    char name[256];
+    std::snprintf(name, sizeof name, "./solution/solution-%04u.vtk", n);
+    FILE* f = std::fopen(name, "w");
+    if (!f) return;
+    std::fprintf(f, "# vtk DataFile Version 3.0\nporoelasticity fixed-stress\nASCII\nDATASET UNSTRUCTURED_GRID\nPOINTS %lld double\n", (long long)m.n_vertices());
+    for (int64_t v = 0; v < m.n_vertices(); ++v)
+      std::fprintf(f, "%.12g %.12g %.12g\n", m.xyz[v * dim], m.xyz[v * dim + 1], dim == 3 ? m.xyz[v * dim + 2] : 0.0);
+    std::fprintf(f, "CELLS %lld %lld\n", (long long)m.n_cells(), (long long)(m.n_cells() * (vpc + 1)));
+    static const int vtk2[4] = {0, 1, 3, 2}, vtk3[8] = {0, 1, 3, 2, 4, 5, 7, 6};
+    for (int64_t c = 0; c < m.n_cells(); ++c) {
+      std::fprintf(f, "%d", vpc);
+      for (int v = 0; v < vpc; ++v) std::fprintf(f, " %d", m.cell_vertices[c * vpc + (dim == 2 ? vtk2[v] : vtk3[v])]);
+      std::fprintf(f, "\n");
+    }
+    std::fprintf(f, "CELL_TYPES %lld\n", (long long)m.n_cells());
+    for (int64_t c = 0; c < m.n_cells(); ++c) std::fprintf(f, "%d\n", dim == 2 ? 9 : 12);
+    std::fprintf(f, "POINT_DATA %lld\nVECTORS u double\n", (long long)m.n_vertices());
+    for (int64_t v = 0; v < m.n_vertices(); ++v) {
+      int64_t d0 = (int64_t)v2d[v] * dim;  // vertex dofs of both handlers are numbered in the same first-touch order
+      std::fprintf(f, "%.12g %.12g %.12g\n", u[d0], u[d0 + 1], dim == 3 ? u[d0 + 2] : 0.0);
+    }
+    std::fprintf(f, "SCALARS p double 1\nLOOKUP_TABLE default\n");
+    for (int64_t v = 0; v < m.n_vertices(); ++v) std::fprintf(f, "%.12g\n", p[v2d[v]]);
+    static const char* names2[3] = {"xx", "xy", "yy"};
+    static const char* names3[6] = {"xx", "xy", "xz", "yy", "yz", "zz"};
+    std::vector<double> s(n_global_p);
+    for (int pass = 0; pass < 2; ++pass)
+      for (int e = 0; e < n_stress_components; ++e) {
+        check(pe_get_vector(ctx, (pass == 0 ? PE_VEC_STRAIN0 : PE_VEC_STRESS0) + e, s.data(), n_global_p), "get strain/stress");
+        std::fprintf(f, "SCALARS %s_%s double 1\nLOOKUP_TABLE default\n", pass == 0 ? "eps" : "sigma", dim == 2 ? names2[e] : names3[e]);
+        for (int64_t v = 0; v < m.n_vertices(); ++v) std::fprintf(f, "%.12g\n", s[v2d[v]]);
+      }
+    std::fclose(f);
+  }
+
+  pe_ctx* ctx = nullptr;
+  input_data::InputDataPoroel data;
+  int dim = 2, rank = 0, nranks = 1;
+  mesh::Mesh global_mesh;
+  const mesh::Mesh* local_mesh = nullptr;
+  partition::Part part;
+  std::vector<int64_t> global_ids[2];
+  int64_t n_global_p = 0, n_global_u = 0;
+  double time = 0;
+  int time_step_number = 0;
+  std::vector<int> strain_tensor_volumetric_components, strain_rhs_volumetric_entries, strain_tensor_shear_components;
+  int n_stress_components = 0;
+};
+
+}  // namespace poro_elastisity
