@@ -1,0 +1,260 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): assembled matrix entries <= 1e-12 relative, pressure and displacement
+fields <= 1e-8 relative L2 after each time step at the same solver tolerance.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+capi, fss = H.capi, H.fss
+pytestmark = pytest.mark.gpu
+
+MATRIX_TOL = 1e-12
+FIELD_TOL = 1e-8
+
+
+def both(inp_text, mesh_file=None, prm_mod=None):
+    inp = capi.InputData(text=inp_text)
+    mesh = fss.make_mesh(inp, mesh_file=mesh_file)
+    dev = capi.create_device_backend(0)
+    ora = H.create_oracle_backend()
+    prm = inp.params()
+    if prm_mod:
+        prm_mod(prm)
+    for b in (dev, ora):
+        fss.upload_problem(b, inp, mesh, prm)
+    return inp, mesh, dev, ora
+
+
+def max_rel(A, B):
+    D = (A - B)
+    return float(abs(D).max() / abs(B).max()) if B.nnz else 0.0
+
+
+CASES = {
+    "c1_2d_q2_shipped": dict(dim=2, refine=4, degree_u=2),
+    "2d_q1": dict(dim=2, refine=4, degree_u=1),
+    "3d_q1": dict(dim=3, refine=3, degree_u=1),
+    "3d_q2": dict(dim=3, refine=2, degree_u=2),
+    "3d_q1_ragged": dict(dim=3, refine=2, degree_u=1, cells=[5, 3, 4]),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_matrices_match_oracle(name):
+    inp, mesh, dev, ora = both(H.make_input(**CASES[name]))
+    try:
+        for b in (dev, ora):
+            b.pressure_set_uniform(inp.p_init)
+            b.displacement_assemble()
+            b.assemble_jacobian(inp.time_step)
+        for which in (capi.MAT_MASS, capi.MAT_LAPLACE, capi.MAT_JACOBIAN, capi.MAT_ELASTICITY):
+            A, B = dev.get_matrix(which), ora.get_matrix(which)
+            assert A.shape[0] == B.shape[0] and A.nnz == B.nnz, "sparsity pattern differs"
+            assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+            assert max_rel(A, B) <= MATRIX_TOL, (name, which, max_rel(A, B))
+        f_d, f_o = dev.get_vector(capi.VEC_WELL_RHS), ora.get_vector(capi.VEC_WELL_RHS)
+        assert np.abs(f_d - f_o).max() <= 1e-12 * np.abs(f_o).max()
+        b_d, b_o = dev.get_vector(capi.VEC_U_RHS), ora.get_vector(capi.VEC_U_RHS)
+        assert np.abs(b_d - b_o).max() <= 1e-12 * np.abs(b_o).max()
+    finally:
+        dev.close(); ora.close()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("precond", [capi.PRECOND_JACOBI, capi.PRECOND_CHEBYSHEV])
+def test_time_steps_match_oracle(name, precond):
+    def mod(prm):
+        prm.preconditioner = precond
+        prm.chebyshev_degree = 3
+        prm.cg_max_iterations = 5000  # Jacobi-class CG needs more than SSOR's 1000 on the stiffest cases
+    inp, mesh, dev, ora = both(H.make_input(**CASES[name]), prm_mod=mod)
+    try:
+        i_d, i_o = fss.initialize(dev, inp), fss.initialize(ora, inp)
+        assert fss.rel_l2(dev.get_vector(capi.VEC_U), ora.get_vector(capi.VEC_U)) <= FIELD_TOL
+        # T5 patch test: normal displacement prescribed on all faces -> uniform strains of -1e-6
+        ev0 = dev.get_vector(capi.VEC_VOL_STRAIN0)
+        assert np.allclose(ev0, -1e-6 * inp.dim, rtol=1e-5)
+        for step in range(3):
+            r_d, r_o = fss.time_step(dev, inp), fss.time_step(ora, inp)
+            assert r_d["inner_counts"] == r_o["inner_counts"], (step, r_d["residual_history"], r_o["residual_history"])
+            assert r_d["fss_iterations"] == r_o["fss_iterations"] == 1
+            ep = fss.rel_l2(dev.get_vector(capi.VEC_P), ora.get_vector(capi.VEC_P))
+            eu = fss.rel_l2(dev.get_vector(capi.VEC_U), ora.get_vector(capi.VEC_U))
+            assert ep <= FIELD_TOL and eu <= FIELD_TOL, (name, step, ep, eu)
+            assert np.allclose(r_d["residual_history"], r_o["residual_history"], rtol=1e-5)
+            # strains do not feed back (FSS:399) and are solved to 1e-8 relative residual only
+            for e in range(3 if inp.dim == 2 else 6):
+                s_d, s_o = dev.get_vector(capi.VEC_STRAIN0 + e), ora.get_vector(capi.VEC_STRAIN0 + e)
+                assert np.abs(s_d - s_o).max() <= 1e-6 * max(np.abs(s_o).max(), 1e-30)
+    finally:
+        dev.close(); ora.close()
+
+
+def test_gmsh_mesh_with_its_own_boundary_ids():
+    # domain.geo:22-25 -> 0 bottom, 1 right, 2 top, 3 left: rollers on all four sides
+    text = H.make_input(dim=2, refine=2, degree_u=2, dirichlet=([3, 1, 0, 2], [0, 0, 1, 1], [0, -1e-5, 0, -1e-5]))
+    inp, mesh, dev, ora = both(text, mesh_file=H.ROOT / "tests" / "golden" / "square10.msh")
+    try:
+        assert mesh.arrays.n_cells == 100
+        fss.initialize(dev, inp); fss.initialize(ora, inp)
+        for _ in range(2):
+            r_d, r_o = fss.time_step(dev, inp), fss.time_step(ora, inp)
+            assert r_d["inner_counts"] == r_o["inner_counts"]
+        assert fss.rel_l2(dev.get_vector(capi.VEC_P), ora.get_vector(capi.VEC_P)) <= FIELD_TOL
+        assert fss.rel_l2(dev.get_vector(capi.VEC_U), ora.get_vector(capi.VEC_U)) <= FIELD_TOL
+        A, B = dev.get_matrix(capi.MAT_ELASTICITY), ora.get_matrix(capi.MAT_ELASTICITY)
+        assert max_rel(A, B) <= MATRIX_TOL
+    finally:
+        dev.close(); ora.close()
+
+
+@pytest.mark.parametrize("dim,deg", [(2, 1), (2, 2), (3, 1)])
+def test_neumann_load(dim, deg):
+    # undrained load: traction on the top face, rollers on the others (SURVEY §8d "Terzaghi-style")
+    top = 2 * dim - 1
+    labels = [f for f in range(2 * dim) if f != top]
+    text = H.make_input(dim=dim, refine=2, degree_u=deg, dirichlet=(labels, [f // 2 for f in labels], [0.0] * len(labels)),
+                        neumann=([top], [dim - 1], [-1e6]))
+    inp, mesh, dev, ora = both(text)
+    try:
+        fss.initialize(dev, inp); fss.initialize(ora, inp)
+        b_d, b_o = dev.get_vector(capi.VEC_U_RHS), ora.get_vector(capi.VEC_U_RHS)
+        assert np.abs(b_d - b_o).max() <= 1e-12 * np.abs(b_o).max()
+        r_d, r_o = fss.time_step(dev, inp), fss.time_step(ora, inp)
+        assert r_d["inner_counts"] == r_o["inner_counts"]
+        assert fss.rel_l2(dev.get_vector(capi.VEC_U), ora.get_vector(capi.VEC_U)) <= FIELD_TOL
+        assert fss.rel_l2(dev.get_vector(capi.VEC_P), ora.get_vector(capi.VEC_P)) <= FIELD_TOL
+    finally:
+        dev.close(); ora.close()
+
+
+def test_assembly_is_bitwise_reproducible():
+    text = H.make_input(dim=3, refine=3, degree_u=1)
+    vals = []
+    for _ in range(2):
+        inp = capi.InputData(text=text)
+        mesh = fss.make_mesh(inp)
+        dev = capi.create_device_backend(0)
+        fss.upload_problem(dev, inp, mesh)
+        dev.pressure_set_uniform(inp.p_init)
+        dev.displacement_assemble()
+        fss.initialize(dev, inp)
+        rep = fss.time_step(dev, inp)
+        vals.append((dev.get_matrix(capi.MAT_ELASTICITY).data.copy(), dev.get_matrix(capi.MAT_MASS).data.copy(),
+                     dev.get_vector(capi.VEC_U_RHS), dev.get_vector(capi.VEC_P), dev.get_vector(capi.VEC_U), rep["cg_its_displacement"]))
+        dev.close()
+    for a, b in zip(vals[0][:-1], vals[1][:-1]):
+        assert np.array_equal(a, b)  # coloured scatter + ordered reductions: identical bits run to run
+    assert vals[0][-1] == vals[1][-1]
+
+
+def test_spmv_matches_scipy_and_is_linear():
+    inp, mesh, dev, ora = both(H.make_input(dim=3, refine=3, degree_u=1))
+    try:
+        dev.pressure_set_uniform(inp.p_init); dev.displacement_assemble(); dev.assemble_jacobian(inp.time_step)
+        rng = np.random.default_rng(1234)
+        for which in (capi.MAT_ELASTICITY, capi.MAT_JACOBIAN, capi.MAT_MASS):
+            A = dev.get_matrix(which)
+            x, y = rng.uniform(-1, 1, A.shape[0]), rng.uniform(-1, 1, A.shape[0])
+            _, ax = capi.device_spmv(dev, which, x, want_y=True)
+            _, ay = capi.device_spmv(dev, which, y, want_y=True)
+            _, axy = capi.device_spmv(dev, which, x + 2 * y, want_y=True)
+            ref = A @ x
+            assert np.abs(ax - ref).max() <= 1e-13 * np.abs(ref).max()
+            assert np.abs(axy - (ax + 2 * ay)).max() <= 1e-12 * np.abs(axy).max()
+            assert abs(y @ ax - x @ ay) <= 1e-12 * abs(y @ ax)  # symmetry
+    finally:
+        dev.close(); ora.close()
+
+
+def test_no_convergence_is_an_error_code():
+    def mod(prm):
+        prm.cg_max_iterations = 3
+    inp, mesh, dev, ora = both(H.make_input(dim=2, refine=4, degree_u=1), prm_mod=mod)
+    try:
+        dev.pressure_set_uniform(inp.p_init)
+        dev.displacement_assemble()
+        with pytest.raises(capi.BackendError) as e:
+            dev.displacement_solve()
+        assert e.value.status == capi.PE_ERR_NO_CONVERGENCE  # SolverControl::NoConvergence (DS:299)
+        with pytest.raises(capi.BackendError) as e2:
+            ora.pressure_set_uniform(inp.p_init); ora.displacement_assemble(); ora.displacement_solve()
+        assert e2.value.status == capi.PE_ERR_NO_CONVERGENCE
+    finally:
+        dev.close(); ora.close()
+
+
+def test_abi_state_errors():
+    dev = capi.create_device_backend(0)
+    try:
+        with pytest.raises(capi.BackendError) as e:
+            dev.setup()
+        assert e.value.status == capi.PE_ERR_STATE
+        inp = capi.InputData(text=H.make_input(dim=2, refine=2, degree_u=1))
+        prm = inp.params()
+        prm.degree_p = 2
+        with pytest.raises(capi.BackendError) as e:
+            dev.set_params(prm)
+        assert e.value.status == capi.PE_ERR_UNSUPPORTED
+    finally:
+        dev.close()
+
+
+def test_cpp_driver_matches_python_mirror():
+    """The C++ PoroElasticProblem (csrc/host/problem.hpp) and the Python mirror issue the same calls."""
+    text = H.make_input(dim=3, refine=3, degree_u=1)
+    inp = capi.InputData(text=text)
+    prob = capi.Problem(inp, device=0)
+    prob.initialize()
+    reps = [prob.step() for _ in range(2)]
+    p1, u1 = prob.backend.get_vector(capi.VEC_P), prob.backend.get_vector(capi.VEC_U)
+    prob.close()
+    mesh = fss.make_mesh(inp)
+    dev = capi.create_device_backend(0)
+    fss.upload_problem(dev, inp, mesh)
+    fss.initialize(dev, inp)
+    reps2 = [fss.time_step(dev, inp) for _ in range(2)]
+    assert np.array_equal(p1, dev.get_vector(capi.VEC_P)) and np.array_equal(u1, dev.get_vector(capi.VEC_U))
+    assert [r["cg_its_displacement"] for r in reps] == [r["cg_its_displacement"] for r in reps2]
+    assert all(r["fss_iterations"] == 1 for r in reps)
+    dev.close()
+
+
+def test_large_mesh_properties():
+    """3D Q1/Q1 refine 5 (32^3): too slow for the serial oracle in a unit test; size-independent properties instead."""
+    inp = capi.InputData(text=H.make_input(dim=3, refine=5, degree_u=1))
+    mesh = fss.make_mesh(inp)
+    dev = capi.create_device_backend(0)
+    try:
+        _, _, (line_dof, _) = fss.upload_problem(dev, inp, mesh)
+        st = dev.stats()
+        n = 32
+        assert st["n_dofs_p"] == (n + 1) ** 3 and st["n_dofs_u"] == 3 * (n + 1) ** 3
+        assert st["nnz_p"] == (3 * n + 1) ** 3 and st["nnz_u"] == 9 * (3 * n + 1) ** 3  # SURVEY §8 nnz formulas
+        fss.initialize(dev, inp)
+        M, K = dev.get_matrix(capi.MAT_MASS), dev.get_matrix(capi.MAT_LAPLACE)
+        assert M.sum() == pytest.approx(1000.0, rel=1e-12)           # sum M = |Omega|
+        assert abs(K.sum(axis=1)).max() <= 1e-12 * abs(K).max()       # row sums of K vanish
+        assert abs(M - M.T).max() == 0 and abs(K - K.T).max() <= 1e-15 * abs(K).max()
+        A = dev.get_matrix(capi.MAT_ELASTICITY)
+        assert abs(A - A.T).max() <= 1e-14 * abs(A).max()
+        ev0 = dev.get_vector(capi.VEC_VOL_STRAIN0)
+        assert np.allclose(ev0, -3e-6, rtol=1e-5)                     # T5 in 3D
+        rep = fss.time_step(dev, inp)
+        assert rep["fss_iterations"] == 1
+        hist = np.array(rep["residual_history"])
+        ratio = hist[2:] / hist[1:-1]
+        assert np.all(ratio < 0.39) and np.all(ratio > 0.3)          # T7: contraction alpha^2 M_b/K_b = 0.38756
+        # the converged displacement satisfies the assembled system to the CG tolerance
+        u, b = dev.get_vector(capi.VEC_U), dev.get_vector(capi.VEC_U_RHS)
+        free = np.ones(u.size, bool)
+        free[line_dof] = False
+        r = (A @ u - b)[free]
+        assert np.linalg.norm(r) <= 1e-9 * np.linalg.norm(b)
+    finally:
+        dev.close()
