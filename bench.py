@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — fixed-stress time steps per second on the 3D Q1/Q1 ~6M-DoF config (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            # the CUDA path (one process per GPU, torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (oracle) on the host cores
+
+A "step" is one pass of PoroElasticProblem::run's time-loop body (lib/include/PoroelasticityFSS.h:328-407):
+inner pressure iterations, displacement assemble+solve, strain projection, convergence check; AMR, stresses
+and VTK excluded.  Workload at every N: 3D unit-cube hex mesh, refine 7 (128^3 cells; 6,440,067
+displacement + 2,146,689 pressure DoFs), cell-partitioned across the N ranks => strong scaling.
+
+Printed JSON (one line, rank 0): value = steps/s with all state resident in HBM (CUDA events on the library's
+stream, max over ranks); e2e = the same through the C-ABI with HOST buffers (pinned host -> device copy of the
+step's state and device -> host copy of p and u inside the timed region); roofline = the displacement-matrix
+CSR SpMV (dominant kernel) from per-launch CUDA events recorded inside the timed region; cpu_baseline = the CPU
+oracle on a bounded sample (see `sample`).
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "fixed_stress_time_steps_per_second"
+UNIT = "steps/s"
+
+
+def input_text(refine, precond, cheb_degree, eig_ratio, max_its, cells=None):
+    import helpers as H
+    extra = (f"  set Preconditioner = {precond}\n  set Chebyshev degree = {cheb_degree}\n"
+             f"  set Chebyshev eigenvalue ratio = {eig_ratio}\n  set CG max iterations = {max_its}\n")
+    return H.make_input(dim=3, refine=refine, degree_u=1, extra_gpu=extra, cells=cells)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+def cpu_sample(refine, threads, golden, cg_sample_its=(2, 5, 5)):
+    """Bounded CPU sample of the same workload with the oracle (the reference's SSOR-CG algorithm).
+
+    Builds the full-size systems, then times a few iterations of each solver and one call of each assembly
+    operator, and extrapolates one time step with the oracle's own iteration counts recorded offline by
+    tests/golden/make_oracle_counts.py (a full oracle step at 128^3 takes tens of minutes)."""
+    import helpers as H
+    capi, fss = H.capi, H.fss
+    lib = H.load_oracle()
+    thr = lib.po_set_threads(threads)
+    inp = capi.InputData(text=input_text(refine, 1, 4, 30, 1000))
+    mesh = fss.make_mesh(inp)
+    b = H.create_oracle_backend()
+    prm = inp.params()
+    t0 = time.perf_counter()
+    fss.upload_problem(b, inp, mesh, prm)
+    t_setup = time.perf_counter() - t0
+    dt = inp.time_step
+
+    def timed(fn):
+        t = time.perf_counter()
+        try:
+            fn()
+        except capi.BackendError as e:  # the capped CG runs end in NoConvergence by construction
+            if e.status != capi.PE_ERR_NO_CONVERGENCE:
+                raise
+        return time.perf_counter() - t
+
+    its_u, its_p, its_m = cg_sample_its
+    b.pressure_set_uniform(inp.p_init)
+    t_asm_u_first = timed(b.displacement_assemble)      # matrix + rhs (once per run)
+    prm.cg_max_iterations = its_u
+    b.set_params(prm)
+    t_u = timed(b.displacement_solve) / (its_u + 1)     # +1: the initial residual vmult and SSOR apply
+    t_asm_u = timed(b.displacement_assemble)            # rhs only (every FSS iteration)
+    b.project_assemble_matrix()
+    t_proj_rhs = timed(lambda: b.project_assemble_rhs(fss.VOLUMETRIC_COMPONENTS[3]))
+    prm.cg_max_iterations = its_m
+    b.set_params(prm)
+    t_m = timed(lambda: b.project_solve(0)) / (its_m + 1)
+    b.volumetric_strain_from_projection([0, 3, 5], True)
+    b.pressure_begin_step(); b.pressure_zero_update(); b.update_volumetric_strain()
+    t_res = timed(lambda: b.assemble_residual(dt))
+    t_jac = timed(lambda: b.assemble_jacobian(dt))
+    prm.cg_max_iterations = its_p
+    b.set_params(prm)
+    t_p = timed(b.pressure_solve) / (its_p + 1)
+    b.close()
+    g = golden
+    per_step = (g["pressure_iterations"] * (t_res + t_jac) + g["cg_its_pressure"] * t_p + t_asm_u + g["cg_its_displacement"] * t_u +
+                t_proj_rhs + g["cg_its_projection"] * t_m + t_res)
+    detail = {"setup_s": round(t_setup, 2), "s_per_cg_it_u": t_u, "s_per_cg_it_p": t_p, "s_per_cg_it_proj": t_m, "s_residual": t_res,
+              "s_jacobian": t_jac, "s_u_rhs": t_asm_u, "s_u_matrix_and_rhs": t_asm_u_first, "s_proj_rhs": t_proj_rhs, "counts": g, "est_s_per_step": per_step}
+    return 1.0 / per_step, thr, detail
+
+
+def golden_counts(refine):
+    """Oracle iteration counts per time step (mean over the recorded steps)."""
+    p = ROOT / "tests" / "golden" / f"oracle_counts_r{refine}.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        steps = d["steps"]
+        keys = ("pressure_iterations", "cg_its_pressure", "cg_its_displacement", "cg_its_projection")
+        return {k: float(np.mean([s[k] for s in steps])) for k in keys} | {"source": p.name, "extrapolated": False}
+    # no record at this size: scale the SSOR-CG counts of the largest recorded mesh with 2^(levels) (kappa ~ h^-1 at best);
+    # flagged in the output
+    for r in range(refine - 1, 3, -1):
+        q = ROOT / "tests" / "golden" / f"oracle_counts_r{r}.json"
+        if q.exists():
+            g = golden_counts(r)
+            f = 2.0 ** (refine - r)
+            return {"pressure_iterations": g["pressure_iterations"], "cg_its_pressure": g["cg_its_pressure"] * f,
+                    "cg_its_displacement": g["cg_its_displacement"] * f, "cg_its_projection": g["cg_its_projection"],
+                    "source": q.name + f" x{f:g} (extrapolated)", "extrapolated": True}
+    raise RuntimeError("no oracle count record under tests/golden")
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU algorithm (oracle port; deal.II cannot be built here) on the host cores."""
+    if rank != 0:
+        return
+    g = golden_counts(args.refine)
+    vals = []
+    detail = None
+    for _ in range(max(1, min(args.steps, 2))):  # each "step" is one bounded sample; two are enough for a stable number
+        v, thr, detail = cpu_sample(args.refine, 0, g)
+        vals.append(v)
+    v = float(np.median(vals))
+    sample = ("oracle (SSOR-CG, reference settings) at full size: %d/%d/%d CG iterations of the u/p/projection solvers and one call of each "
+              "assembly operator timed, extrapolated to one step with the oracle's recorded iteration counts (%s)" % (2, 5, 5, g["source"]))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "detail": detail}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    n = 2 ** args.refine
+    return {"workload": f"3D unit-cube hex mesh, Q1 displacement / Q1 pressure, refine {args.refine} ({n}^3 cells, {3 * (n + 1) ** 3} u + {(n + 1) ** 3} p DoFs), "
+                        "shipped input.data properties, dt=60, rollers on all faces, well source; BASELINE.json configs[3]",
+            "refine": args.refine, "parallelism": f"cell-partitioned x{args.gpus}", "l2_policy": "inputs larger than L2 (6.3 GB matrix vs 126 MB L2), no flush",
+            "preconditioner": "chebyshev-jacobi" if args.precond == 1 else "jacobi", "chebyshev_degree": args.cheb_degree,
+            "cg_max_iterations": args.max_its}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--refine", type=int, default=7)
+    ap.add_argument("--precond", type=int, default=1)
+    ap.add_argument("--cheb-degree", type=int, default=4)
+    ap.add_argument("--eig-ratio", type=float, default=30.0)
+    ap.add_argument("--max-its", type=int, default=4000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import __graft_entry__ as G
+    G.build()
+    pkg = importlib.import_module("poroelasticity-dealii_b200")
+    capi = pkg.capi
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        box = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    inp = capi.InputData(text=input_text(args.refine, args.precond, args.cheb_degree, args.eig_ratio, args.max_its))
+    prob = capi.Problem(inp, device=local, rank=rank, nranks=world, nccl_id=nccl_id)
+    t0 = time.perf_counter()
+    prob.initialize(verbose=False)
+    t_init = time.perf_counter() - t0
+    be = prob.backend
+    lib = be.lib
+    stream = torch.cuda.ExternalStream(lib.pe_stream(be.ctx), device=torch.device("cuda", local))
+
+    for _ in range(args.warmup):
+        prob.step()
+    # ---- timed region: K steps, state resident in HBM
+    be.reset_stats()
+    lib.pe_set_profiling(be.ctx, 1)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    reports = [prob.step() for _ in range(args.steps)]
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    stats = be.stats()
+    lib.pe_set_profiling(be.ctx, 0)
+
+    # ---- e2e: same steps through the C-ABI with host buffers (H2D of the state, D2H of p and u per step)
+    e2e = None
+    if not args.no_e2e:
+        n_p, n_u = be.n_p, be.n_u
+        host = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k, n in
+                (("p", n_p), ("ev", n_p), ("ev0", n_p), ("u", n_u), ("p_out", n_p), ("u_out", n_u))}
+        ids = {"p": capi.VEC_P, "ev": capi.VEC_VOL_STRAIN, "ev0": capi.VEC_VOL_STRAIN0, "u": capi.VEC_U}
+        for k, which in ids.items():
+            host[k].numpy()[:] = be.get_vector(which)
+        f64 = C.POINTER(C.c_double)
+
+        def ptr(t):
+            return C.cast(t.data_ptr(), f64)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            for k, which in ids.items():
+                be._ck(lib.pe_set_vector(be.ctx, which, ptr(host[k]), host[k].numel()), "set_vector")
+            prob.step()
+            be._ck(lib.pe_get_vector(be.ctx, capi.VEC_P, ptr(host["p_out"]), n_p), "get_vector")
+            be._ck(lib.pe_get_vector(be.ctx, capi.VEC_U, ptr(host["u_out"]), n_u), "get_vector")
+            be._ck(lib.pe_get_vector(be.ctx, capi.VEC_VOL_STRAIN, ptr(host["ev"]), n_p), "get_vector")
+            host["p"].copy_(host["p_out"]); host["u"].copy_(host["u_out"])
+        barrier()
+        t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e = {"value": args.steps / float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": int((3 * n_p + n_u) * 8),
+               "d2h_bytes_per_step": int((2 * n_p + n_u) * 8)}
+
+    if rank == 0:
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        peak = peaks.get("hbm_gbs", 6650.0)
+        spmv_ms = stats["spmv_ms_u"] / max(1, stats["spmv_timed_u"])
+        achieved = stats["spmv_bytes_u"] / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
+        spmv_ms_p = stats["spmv_ms_p"] / max(1, stats["spmv_timed_p"])
+        value = args.steps / (ms_total * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args), "clocks": clocks, "gpu_launches": int(stats["kernel_launches"]),
+            "e2e": e2e,
+            "roofline": {"bound": "hbm", "kernel": "k_spmv<32,*> (CSR SpMV of the displacement matrix, fused dot / Chebyshev epilogues)",
+                         "achieved": achieved, "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
+                         "traffic": None, "algorithmic_bytes_per_launch": stats["spmv_bytes_u"], "avg_launch_ms": spmv_ms,
+                         "launches_timed": int(stats["spmv_timed_u"]),
+                         "pressure_spmv": {"avg_launch_ms": spmv_ms_p, "achieved": (stats["spmv_bytes_p"] / (spmv_ms_p * 1e-3) / 1e9) if spmv_ms_p > 0 else None,
+                                           "launches_timed": int(stats["spmv_timed_p"])},
+                         "spmv_share_of_step": (stats["spmv_ms_u"] + stats["spmv_ms_p"]) / ms_total if ms_total > 0 else None},
+            "iterations_per_step": {"pressure_inner": float(np.mean([r["pressure_iterations"] for r in reports])),
+                                    "cg_pressure": float(np.mean([r["cg_its_pressure"] for r in reports])),
+                                    "cg_displacement": float(np.mean([r["cg_its_displacement"] for r in reports])),
+                                    "cg_projection": float(np.mean([r["cg_its_projection"] for r in reports])),
+                                    "fss": float(np.mean([r["fss_iterations"] for r in reports])),
+                                    "matrix_passes_u": stats["spmv_launches_u"] / args.steps, "matrix_passes_p": stats["spmv_launches_p"] / args.steps},
+            "init_s": t_init, "setup_ms": stats["setup_ms"],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                g = golden_counts(args.refine)
+                v, thr, detail = cpu_sample(args.refine, 0, g)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": thr, "kind": "port",
+                                        "sample": "oracle at full size: 2/5/5 CG iterations of the u/p/projection SSOR-CG solvers and one call of each assembly "
+                                                  f"operator timed, extrapolated to one step with the oracle's recorded iteration counts ({g['source']})",
+                                        "detail": detail}
+            except Exception as exc:  # the baseline must never take the GPU number down with it
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+        print(json.dumps(line), flush=True)
+    prob.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -102,6 +102,9 @@ typedef struct pe_stats {
   double  spmv_bytes_p, spmv_bytes_u;        /* algorithmic bytes per matrix pass          */
   double  eig_max_p, eig_max_u, eig_max_m;   /* power-iteration estimates of lambda_max(D^-1 A) */
   double  setup_ms;                          /* pe_setup wall time                         */
+  double  spmv_ms_p, spmv_ms_u;              /* CUDA-event time summed over the matrix passes timed while
+                                                profiling is on (pe_set_profiling)          */
+  int64_t spmv_timed_p, spmv_timed_u;        /* number of matrix passes in those sums      */
 } pe_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------- */
@@ -158,6 +161,7 @@ int  pe_get_matrix(pe_ctx*, int matrix, int64_t* rowptr, int32_t* col, double* v
 int  pe_get_stats(pe_ctx*, pe_stats*);
 int  pe_reset_stats(pe_ctx*);
 int  pe_synchronize(pe_ctx*);
+int  pe_set_profiling(pe_ctx*, int on); /* bracket every matrix pass with CUDA events on the launch stream */
 void* pe_stream(pe_ctx*);   /* cudaStream_t the kernels are launched on (for event timing) */
 
 #ifdef __cplusplus

@@ -166,6 +166,8 @@ struct Pattern {
   }
 };
 
+int g_threads = 1;  // po_set_threads: 1 = faithful serial loops; >1 = OpenMP where the algorithm allows it
+
 Pattern make_pattern(int64_t n_dofs, int64_t n_cells, int n_loc, const int32_t* cell_dofs) {
   // dof -> cells adjacency
   vector<int64_t> cnt(n_dofs + 1, 0);
@@ -180,20 +182,21 @@ Pattern make_pattern(int64_t n_dofs, int64_t n_cells, int n_loc, const int32_t* 
   Pattern P;
   P.n = n_dofs;
   P.rowptr.assign(n_dofs + 1, 0);
-  vector<vector<int32_t>> rows;  // built in chunks to bound memory
-  vector<int32_t> tmp;
-  // pass 1: count
+  // pass 1: count (rows are independent: OpenMP when po_set_threads(>1) was called)
+#pragma omp parallel for num_threads(g_threads) schedule(static, 4096) if (g_threads > 1)
   for (int64_t r = 0; r < n_dofs; ++r) {
-    tmp.clear();
+    vector<int32_t> tmp;
     for (int64_t a = cnt[r]; a < cnt[r + 1]; ++a)
       for (int k = 0; k < n_loc; ++k) tmp.push_back(cell_dofs[(int64_t)adj[a] * n_loc + k]);
     std::sort(tmp.begin(), tmp.end());
-    P.rowptr[r + 1] = P.rowptr[r] + (int64_t)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+    P.rowptr[r + 1] = (int64_t)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
   }
+  for (int64_t r = 0; r < n_dofs; ++r) P.rowptr[r + 1] += P.rowptr[r];
   P.col.resize(P.rowptr[n_dofs]);
   P.right_of_diag.resize(n_dofs);
+#pragma omp parallel for num_threads(g_threads) schedule(static, 4096) if (g_threads > 1)
   for (int64_t r = 0; r < n_dofs; ++r) {
-    tmp.clear();
+    vector<int32_t> tmp;
     for (int64_t a = cnt[r]; a < cnt[r + 1]; ++a)
       for (int k = 0; k < n_loc; ++k) tmp.push_back(cell_dofs[(int64_t)adj[a] * n_loc + k]);
     std::sort(tmp.begin(), tmp.end());
@@ -210,8 +213,6 @@ Pattern make_pattern(int64_t n_dofs, int64_t n_cells, int n_loc, const int32_t* 
   }
   return P;
 }
-
-int g_threads = 1;
 
 // SparseMatrix::vmult
 void vmult(const Pattern& P, const Vec& val, const Vec& x, Vec& y) {
@@ -413,14 +414,43 @@ inline double well_value(const Ctx& C, const double* x) {
   return 0;
 }
 
+// Cell schedule: one list in natural order when serial (faithful to the reference's loops); with
+// po_set_threads(>1) a greedy vertex colouring so that cells of one list never share a dof and an
+// OpenMP loop over a list is race free.
+vector<vector<int64_t>> cell_schedule(const Ctx& C) {
+  vector<vector<int64_t>> lists;
+  if (g_threads <= 1) {
+    lists.emplace_back(C.n_cells);
+    for (int64_t c = 0; c < C.n_cells; ++c) lists[0][c] = c;
+    return lists;
+  }
+  const int vpc = 1 << C.dim;
+  vector<uint64_t> vmask(C.n_vertices, 0);
+  for (int64_t c = 0; c < C.n_cells; ++c) {
+    uint64_t used = 0;
+    for (int v = 0; v < vpc; ++v) used |= vmask[C.cell_vertices[c * vpc + v]];
+    int col = 0;
+    while (col < 63 && ((used >> col) & 1)) ++col;
+    if ((int)lists.size() <= col) lists.resize(col + 1);
+    lists[col].push_back(c);
+    for (int v = 0; v < vpc; ++v) vmask[C.cell_vertices[c * vpc + v]] |= (uint64_t)1 << col;
+  }
+  return lists;
+}
+
 void assemble_mass_laplace(Ctx& C) {  // PS:96-101
   const int dim = C.dim, ns = C.nloc_p;
   C.M.assign(C.Pp.nnz(), 0);
   C.K.assign(C.Pp.nnz(), 0);
   C.frhs.assign(C.np, 0);
+  for (const auto& list : cell_schedule(C)) {
+#pragma omp parallel num_threads(g_threads) if (g_threads > 1)
+  {
   CellGeom G;
   vector<double> gr((size_t)ns * dim), cm((size_t)ns * ns), ck((size_t)ns * ns), cf(ns);
-  for (int64_t c = 0; c < C.n_cells; ++c) {
+#pragma omp for schedule(static)
+  for (int64_t li = 0; li < (int64_t)list.size(); ++li) {
+    const int64_t c = list[li];
     cell_geometry(C, c, C.geo_q2, C.q2, G);
     std::fill(cm.begin(), cm.end(), 0);
     std::fill(ck.begin(), ck.end(), 0);
@@ -449,6 +479,8 @@ void assemble_mass_laplace(Ctx& C) {  // PS:96-101
       }
     }
   }
+  }  // omp parallel
+  }  // schedule
 }
 
 // symmetric 2-tensor helpers; storage index e(i,j) for i<=j: TensorIndexer (TI:25-30)
@@ -464,18 +496,22 @@ void displacement_assemble(Ctx& C) {
   const bool build = C.rebuild_system_matrix;
   if (build) C.A.assign(C.Pu.nnz(), 0);
   C.b.assign(C.nu, 0);
-  CellGeom G;
   const Quad& Q = C.qu;
-  vector<double> eps((size_t)nl * dim * dim), sig((size_t)nl * dim * dim), cm((size_t)nl * nl), cr(nl), gr(dim);
-  vector<double> pq(Q.n);
   // boundary faces per cell (for Neumann), built lazily
   vector<vector<int>> cell_bf;
   if (!C.nm_label.empty()) {
     cell_bf.resize(C.n_cells);
     for (int64_t f = 0; f < C.n_bfaces; ++f) cell_bf[C.bface_cell[f]].push_back((int)f);
   }
-  vector<double> usup = unit_support(dim, C.prm.degree_u);
-  for (int64_t c = 0; c < C.n_cells; ++c) {
+  for (const auto& list : cell_schedule(C)) {
+#pragma omp parallel num_threads(g_threads) if (g_threads > 1)
+  {
+  CellGeom G;
+  vector<double> eps((size_t)nl * dim * dim), sig((size_t)nl * dim * dim), cm((size_t)nl * nl), cr(nl), gr(dim);
+  vector<double> pq(Q.n);
+#pragma omp for schedule(static)
+  for (int64_t li = 0; li < (int64_t)list.size(); ++li) {
+    const int64_t c = list[li];
     const int32_t* cd = &C.cd_u[c * nl];
     const int32_t* cdp = &C.cd_p[c * nsp];
     bool need_matrix = build;
@@ -586,6 +622,8 @@ void displacement_assemble(Ctx& C) {
       C.b[cd[i]] += r;
     }
   }
+  }  // omp parallel
+  }  // schedule
   C.rebuild_system_matrix = false;
 }
 
@@ -597,9 +635,14 @@ void projection_rhs(Ctx& C, int n_comp, const int32_t* comps) {
     entries[c] = sym_entry(dim, comps[c] / dim, comps[c] % dim);
     C.proj_rhs[entries[c]].assign(C.np, 0);
   }
+  for (const auto& list : cell_schedule(C)) {
+#pragma omp parallel num_threads(g_threads) if (g_threads > 1)
+  {
   CellGeom G;
   vector<double> cr((size_t)n_comp * nsp), gr(dim);
-  for (int64_t cell = 0; cell < C.n_cells; ++cell) {
+#pragma omp for schedule(static)
+  for (int64_t li = 0; li < (int64_t)list.size(); ++li) {
+    const int64_t cell = list[li];
     cell_geometry(C, cell, C.geo_q2, C.q2, G);
     std::fill(cr.begin(), cr.end(), 0);
     const int32_t* cd = &C.cd_u[cell * nl];
@@ -624,6 +667,8 @@ void projection_rhs(Ctx& C, int n_comp, const int32_t* comps) {
     for (int c = 0; c < n_comp; ++c)
       for (int i = 0; i < nsp; ++i) C.proj_rhs[entries[c]][cdp[i]] += cr[(size_t)c * nsp + i];
   }
+  }  // omp parallel
+  }  // schedule
 }
 
 int fail(Ctx* c, int code, const std::string& m) {

@@ -51,6 +51,7 @@ class PeStats(C.Structure):
         ("spmv_launches_p", C.c_int64), ("spmv_launches_u", C.c_int64), ("kernel_launches", C.c_int64),
         ("spmv_bytes_p", C.c_double), ("spmv_bytes_u", C.c_double),
         ("eig_max_p", C.c_double), ("eig_max_u", C.c_double), ("eig_max_m", C.c_double), ("setup_ms", C.c_double),
+        ("spmv_ms_p", C.c_double), ("spmv_ms_u", C.c_double), ("spmv_timed_p", C.c_int64), ("spmv_timed_u", C.c_int64),
     ]
 
     def as_dict(self):
@@ -116,7 +117,7 @@ DEVICE_SYMBOLS = [
     "pe_pressure_solve", "pe_pressure_add_update", "pe_pressure_linfty", "pe_displacement_assemble", "pe_displacement_solve",
     "pe_project_assemble_matrix", "pe_project_assemble_rhs", "pe_project_solve", "pe_volumetric_strain_from_projection",
     "pe_effective_stresses", "pe_spmv", "pe_get_vector", "pe_set_vector", "pe_get_matrix_size", "pe_get_matrix", "pe_get_stats",
-    "pe_reset_stats", "pe_synchronize", "pe_stream",
+    "pe_reset_stats", "pe_synchronize", "pe_stream", "pe_set_profiling",
 ]
 HOST_SYMBOLS = [
     "peh_last_error", "peh_input_create", "peh_input_destroy", "peh_input_read_file", "peh_input_read_string", "peh_input_view_get",
@@ -164,6 +165,21 @@ def _declare_operator_api(lib, prefix):
     g("destroy").restype = None
 
 
+def _preload_nccl():
+    """libporoel.so needs `libnccl.so.2`.  PyTorch bundles a newer NCCL under the same soname; whichever is
+    loaded first wins for the whole process, so load torch's copy first (if there is one) to keep a later
+    `import torch` working.  Without the wheel the system library is used."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    if spec and spec.submodule_search_locations:
+        cand = Path(list(spec.submodule_search_locations)[0]) / "lib" / "libnccl.so.2"
+        if cand.exists():
+            C.CDLL(str(cand), mode=C.RTLD_GLOBAL)
+
+
 def load_device():
     """dlopen libporoel.so; raises (loudly) when the CUDA extension has not been built."""
     global _dev
@@ -173,7 +189,8 @@ def load_device():
     if not path.exists():
         raise RuntimeError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(the product has no CPU fallback)")
-    lib = C.CDLL(str(path), mode=C.RTLD_GLOBAL)
+    _preload_nccl()
+    lib = C.CDLL(str(path))
     _declare_operator_api(lib, "pe_")
     P = C.c_void_p
     lib.pe_create.argtypes = [C.POINTER(P), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
@@ -181,6 +198,7 @@ def load_device():
     lib.pe_upload_partition.argtypes = [P, C.c_int, C.c_int64, C.c_int, i32p, i64p, i32p, i64p]
     lib.pe_spmv.argtypes = [P, C.c_int, f64p, f64p, C.c_int, C.POINTER(C.c_float)]
     lib.pe_synchronize.argtypes = [P]
+    lib.pe_set_profiling.argtypes = [P, C.c_int]
     lib.pe_stream.argtypes = [P]
     lib.pe_stream.restype = C.c_void_p
     _dev = lib

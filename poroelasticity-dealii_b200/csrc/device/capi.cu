@@ -136,6 +136,7 @@ void pe_destroy(pe_ctx* c) {
   if (c->h_state) cudaFreeHost(c->h_state);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
   for (auto& e : c->ev_poll) if (e) cudaEventDestroy(e);
+  for (auto& e : c->prof_ev) if (e) cudaEventDestroy(e);
   cudaStream_t s = c->stream;
   delete c;
   if (s) cudaStreamDestroy(s);
@@ -555,9 +556,21 @@ int pe_get_matrix(pe_ctx* c, int matrix, int64_t* rowptr, int32_t* col, double* 
   if (rowptr) for (size_t i = 0; i < rp.size(); ++i) rowptr[i] = rp[i];
   PE_LEAVE(c)
 }
+int pe_set_profiling(pe_ctx* c, int on) {
+  PE_ENTER(c)
+  if (on && c->prof_ev.empty()) {
+    c->prof_ev.resize(2 * PE_PROF_PAIRS);
+    c->prof_field.assign(PE_PROF_PAIRS, 0);
+    for (auto& e : c->prof_ev) PE_CUDA(cudaEventCreate(&e));
+  }
+  if (!on) pe_prof_flush(c);
+  c->profiling = on != 0;
+  PE_LEAVE(c)
+}
 int pe_get_stats(pe_ctx* c, pe_stats* s) {
   PE_ENTER(c)
   require(s != nullptr, PE_ERR_BAD_INPUT, "null output");
+  pe_prof_flush(c);
   *s = c->st;
   PE_LEAVE(c)
 }
@@ -568,6 +581,9 @@ int pe_reset_stats(pe_ctx* c) {
   c->st.cg_solves_pressure = c->st.cg_solves_displacement = c->st.cg_solves_projection = 0;
   c->st.spmv_launches_p = c->st.spmv_launches_u = 0;
   c->st.kernel_launches = 0;
+  pe_prof_flush(c);
+  c->st.spmv_ms_p = c->st.spmv_ms_u = 0;
+  c->st.spmv_timed_p = c->st.spmv_timed_u = 0;
   (void)k;
   PE_LEAVE(c)
 }

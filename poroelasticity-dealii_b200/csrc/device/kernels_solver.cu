@@ -404,18 +404,41 @@ void launch_spmv(pe_ctx* c, Field& F, SpmvArgs& a) {
   a.red = red_args(c);
   const int lpr = lanes_per_row(F);
   const int grid = spmv_grid(c, a.n, lpr);
+  if (c->profiling) pe_prof_begin(c, &F == &c->fu ? 1 : 0);
   switch (lpr) {
     case 32: k_spmv<32, EPI><<<grid, SPMV_T, 0, c->stream>>>(a); break;
     case 16: k_spmv<16, EPI><<<grid, SPMV_T, 0, c->stream>>>(a); break;
     case 8: k_spmv<8, EPI><<<grid, SPMV_T, 0, c->stream>>>(a); break;
     default: k_spmv<4, EPI><<<grid, SPMV_T, 0, c->stream>>>(a); break;
   }
+  if (c->profiling) pe_prof_end(c);
   c->st.kernel_launches++;
 }
 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
+void pe_prof_begin(pe_ctx* c, int field) {
+  if (c->prof_used == PE_PROF_PAIRS) pe_prof_flush(c);
+  c->prof_field[c->prof_used] = field;
+  cudaEventRecord(c->prof_ev[2 * c->prof_used], c->stream);
+}
+void pe_prof_end(pe_ctx* c) {
+  cudaEventRecord(c->prof_ev[2 * c->prof_used + 1], c->stream);
+  c->prof_used++;
+}
+void pe_prof_flush(pe_ctx* c) {
+  if (!c->prof_used) return;
+  cudaEventSynchronize(c->prof_ev[2 * c->prof_used - 1]);
+  for (int i = 0; i < c->prof_used; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]);
+    if (c->prof_field[i]) { c->st.spmv_ms_u += ms; c->st.spmv_timed_u++; }
+    else { c->st.spmv_ms_p += ms; c->st.spmv_timed_p++; }
+  }
+  c->prof_used = 0;
+}
+
 void pe_allreduce_sum(pe_ctx* c, double* dev, int count) {
   if (c->nranks > 1) PE_NCCL(ncclAllReduce(dev, dev, count, ncclDouble, ncclSum, c->comm, c->stream));
 }

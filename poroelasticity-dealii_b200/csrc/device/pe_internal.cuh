@@ -177,7 +177,17 @@ struct pe_ctx {
   cudaEvent_t ev_poll[2] = {nullptr, nullptr};
 
   pe_stats st{};
+
+  // optional per-launch timing of the matrix passes (roofline evidence): event pairs on `stream`
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_ev;        // 2 * PROF_PAIRS events
+  std::vector<int> prof_field;             // field of each recorded pair
+  int prof_used = 0;
 };
+static constexpr int PE_PROF_PAIRS = 2048;
+void pe_prof_begin(pe_ctx* c, int field);
+void pe_prof_end(pe_ctx* c);
+void pe_prof_flush(pe_ctx* c);
 
 // ---- kernels_pattern.cu
 void pe_build_pattern(pe_ctx* c, Field& F);

@@ -2,11 +2,14 @@
 import ctypes as C
 import importlib
 import subprocess
+import sys
 from pathlib import Path
 
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
 pkg = importlib.import_module("poroelasticity-dealii_b200")
 capi = pkg.capi
 fss = pkg.fss

@@ -1,0 +1,60 @@
+"""The C-ABI libraries load and export every symbol the headers declare; without a GPU the product fails loudly."""
+import ctypes as C
+import re
+import subprocess
+
+import pytest
+
+import helpers as H
+
+capi = H.capi
+
+
+def header_functions(name):
+    text = (H.ROOT / "include" / name).read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pe[h]?_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_device_library_exports_every_declared_symbol():
+    lib = capi.load_device()
+    declared = header_functions("poroel.h")
+    assert set(declared) == set(capi.DEVICE_SYMBOLS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.pe_version() == 100
+
+
+def test_host_library_exports_every_declared_symbol():
+    lib = capi.load_host()
+    declared = [s for s in header_functions("poroel_host.h") if s.startswith("peh_") and not s.endswith(("_view", "_report"))]
+    assert set(declared) == set(capi.HOST_SYMBOLS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
+def test_device_library_is_sm100a_only_and_has_no_oracle_dependency():
+    lib = H.ROOT / "poroelasticity-dealii_b200" / "lib" / "libporoel.so"
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", str(lib)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+    needed = subprocess.run(["readelf", "-d", str(lib)], capture_output=True, text=True).stdout
+    assert "oracle" not in needed
+    host = subprocess.run(["readelf", "-d", str(lib.with_name("libporoel_host.so"))], capture_output=True, text=True).stdout
+    assert "libporoel.so" in host and "oracle" not in host
+
+
+def test_struct_layouts_match_the_header():
+    # sizes computed from the C declarations (8-byte aligned PODs)
+    assert C.sizeof(capi.PeParams) == 8 * 4 + 12 * 8
+    assert C.sizeof(capi.PeStats) == 14 * 8 + 6 * 8 + 4 * 8
+
+
+def test_product_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.BackendError) as e:
+        capi.create_device_backend(0)
+    assert e.value.status == capi.PE_ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
