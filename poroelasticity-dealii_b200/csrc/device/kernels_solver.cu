@@ -78,36 +78,89 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], RedArgs R, int slot
   }
 }
 
+// Streaming loads of the matrix (read once per pass: bypass L1) and cached gathers of the vector.  They are
+// `volatile` on purpose: ptxas otherwise sinks every dependent gather right behind its column load and
+// recycles one register for all of them, which serialises the loads (memory-level parallelism of ~1 per
+// warp).  Volatile asm keeps program order, so all column/value loads of a row pair are in flight before
+// the first gather waits.
 __device__ __forceinline__ double ld_stream(const double* p) {
   double v;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ int ld_stream(const int* p) {
   int v;
-  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  asm volatile("ld.global.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_gather(const double* p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
 
-// sum_j val[j] * x[col[j]] of one row, LPR lanes cooperating; result valid in every lane of the group
+// One row segment [start, end) handled by the LPR lanes of a group: the first four strided chunks live in
+// registers (issue(): 4 column + 4 value loads, nothing dependent), finish() gathers x and accumulates;
+// rows longer than 4*LPR continue in a plain loop.
+template <int LPR>
+struct RowChunks {
+  int c[4];
+  double v[4];
+  int start, end, sub;
+  __device__ __forceinline__ void issue_cols(const int32_t* __restrict__ col, int start_, int end_, int sub_) {
+    start = start_; end = end_; sub = sub_;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = start + sub + k * LPR;
+      c[k] = 0;
+      if (j < end) c[k] = ld_stream(col + j);
+    }
+  }
+  __device__ __forceinline__ void issue_vals(const double* __restrict__ val) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = start + sub + k * LPR;
+      v[k] = 0.0;
+      if (j < end) v[k] = ld_stream(val + j);
+    }
+  }
+  __device__ __forceinline__ double finish(const int32_t* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x) {
+    double xv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = start + sub + k * LPR;
+      xv[k] = 0.0;
+      if (j < end) xv[k] = ld_gather(x + c[k]);
+    }
+    double s0 = v[0] * xv[0] + v[2] * xv[2], s1 = v[1] * xv[1] + v[3] * xv[3];
+    for (int j = start + sub + 4 * LPR; j < end; j += LPR) s0 += ld_stream(val + j) * ld_gather(x + ld_stream(col + j));
+    return s0 + s1;
+  }
+};
+
+template <int LPR>
+__device__ __forceinline__ double group_reduce(double s) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+template <int LPR>
+__device__ __forceinline__ double row_sum(const int32_t* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
+                                          int start, int end, int sub) {
+  RowChunks<LPR> R;
+  R.issue_cols(col, start, end, sub);
+  R.issue_vals(val);
+  return group_reduce<LPR>(R.finish(col, val, x));
+}
+
+// row pointer pair of the old one-row-per-group kernels
 template <int LPR>
 __device__ __forceinline__ double row_dot(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
                                           const double* __restrict__ x, int64_t row, int sub, bool valid) {
   int start = 0, end = 0;
   if (valid) { start = rowptr[row]; end = rowptr[row + 1]; }
-  double s0 = 0.0, s1 = 0.0;
-  int j = start + sub;
-  for (; j + LPR < end; j += 2 * LPR) {
-    const int c0 = ld_stream(col + j), c1 = ld_stream(col + j + LPR);
-    const double v0 = ld_stream(val + j), v1 = ld_stream(val + j + LPR);
-    s0 += v0 * x[c0];
-    s1 += v1 * x[c1];
-  }
-  if (j < end) s0 += ld_stream(val + j) * x[ld_stream(col + j)];
-  double s = s0 + s1;
-#pragma unroll
-  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  return s;
+  return row_sum<LPR>(col, val, x, start, end, sub);
 }
 
 // epilogue kinds of the fused SpMV
@@ -132,23 +185,46 @@ struct SpmvArgs {
   int slot;
 };
 
+// CSR SpMV with warp-blocked rows.  A warp owns 32 CONSECUTIVE rows: their row pointers arrive with one
+// coalesced load and are handed out by shuffles (no dependent rowptr -> col -> x chain per row); the
+// 32/LPR lane groups sweep the rows LPR rounds, two rounds in flight; each lane ends up holding the sum of
+// "its" row, so the result store and every fused epilogue (dot, residual, Chebyshev update) are coalesced
+// 32-row accesses instead of single-lane traffic.
 template <int LPR, int EPI>
 __global__ void __launch_bounds__(SPMV_T) k_spmv(SpmvArgs a) {
   if (a.state && a.state->done) return;
-  constexpr int RPB = SPMV_T / LPR;
-  const int sub = threadIdx.x % LPR;
+  constexpr int G = 32 / LPR;  // rows in flight per round
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, grp = lane / LPR;
+  const int64_t n_blocks = (a.n + 31) >> 5;
   double acc[1] = {0.0};
-  // n_pad is a multiple of RPB, so the loop condition is uniform across the CTA (shuffles stay converged)
-  const int64_t n_pad = ((a.n + RPB - 1) / RPB) * RPB;
-  for (int64_t row = (int64_t)blockIdx.x * RPB + threadIdx.x / LPR; row < n_pad; row += (int64_t)gridDim.x * RPB) {
-    const bool valid = row < a.n;
-    const double s = row_dot<LPR>(a.rowptr, a.col, a.val, a.x, row, sub, valid);
-    if (valid && sub == 0) {
-      if (EPI == EPI_PLAIN) a.y[row] = s;
-      if (EPI == EPI_DOT) { a.y[row] = s; acc[0] += s * a.x[row]; }
-      if (EPI == EPI_RESID) { const double g = s - a.b[row]; a.y[row] = g; acc[0] += g * g; }
+  for (int64_t rb = (int64_t)blockIdx.x * (SPMV_T / 32) + warp; rb < n_blocks; rb += (int64_t)gridDim.x * (SPMV_T / 32)) {
+    const int64_t row = (rb << 5) + lane;
+    const int64_t rlo = row < a.n ? row : a.n, rhi = row + 1 < a.n ? row + 1 : a.n;
+    const int ptr_lo = a.rowptr[rlo], ptr_hi = a.rowptr[rhi];  // rows past the end are empty
+    double mine = 0.0;
+    for (int t = 0; t < LPR; t += 2) {  // two rounds (2*G rows) in flight
+      const int ra = t * G + grp, rb_ = (t + 1) * G + grp;
+      const int sa = __shfl_sync(0xffffffffu, ptr_lo, ra), ea = __shfl_sync(0xffffffffu, ptr_hi, ra);
+      const int sb = __shfl_sync(0xffffffffu, ptr_lo, rb_), eb = __shfl_sync(0xffffffffu, ptr_hi, rb_);
+      RowChunks<LPR> A, B;
+      A.issue_cols(a.col, sa, ea, sub);
+      B.issue_cols(a.col, sb, eb, sub);
+      A.issue_vals(a.val);
+      B.issue_vals(a.val);
+      __syncwarp();  // scheduling fence: keeps the 16 streaming loads above ahead of the first dependent gather
+      const double s_a = group_reduce<LPR>(A.finish(a.col, a.val, a.x));
+      const double s_b = group_reduce<LPR>(B.finish(a.col, a.val, a.x));
+      const double va = __shfl_sync(0xffffffffu, s_a, ((lane - t * G) & (G - 1)) * LPR);
+      const double vb = __shfl_sync(0xffffffffu, s_b, ((lane - (t + 1) * G) & (G - 1)) * LPR);
+      if (lane / G == t) mine = va;
+      if (lane / G == t + 1) mine = vb;
+    }
+    if (row < a.n) {
+      if (EPI == EPI_PLAIN) a.y[row] = mine;
+      if (EPI == EPI_DOT) { a.y[row] = mine; acc[0] += mine * a.x[row]; }
+      if (EPI == EPI_RESID) { const double g = mine - a.b[row]; a.y[row] = g; acc[0] += g * g; }
       if (EPI == EPI_CHEB) {
-        const double rn = a.r[row] - s;
+        const double rn = a.r[row] - mine;
         a.r[row] = rn;
         const double dn = a.c1 * a.x[row] + a.c2 * a.invdiag[row] * rn;
         a.d_out[row] = dn;
@@ -383,15 +459,17 @@ inline int vec_grid(pe_ctx* c, int64_t n) {
 }
 
 inline int lanes_per_row(const Field& F) {
+  // four strided chunks per lane cover a row: LPR ~ avg_row_length / 4
   const double avg = F.n_owned ? (double)F.nnz / (double)F.n_owned : 1.0;
-  if (avg > 48) return 32;
-  if (avg > 20) return 16;
-  if (avg > 10) return 8;
+  if (avg > 64) return 32;
+  if (avg > 32) return 16;
+  if (avg > 12) return 8;
   return 4;
 }
 
 inline int spmv_grid(pe_ctx* c, int64_t n, int lpr) {
-  const int rpb = SPMV_T / lpr;
+  (void)lpr;
+  const int rpb = SPMV_T;  // 32 rows per warp, SPMV_T/32 warps
   int64_t want = (n + rpb - 1) / rpb;
   return (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min<int64_t>(PE_MAX_RED_BLOCKS, (int64_t)c->sm_count * 8)));
 }
