@@ -1,0 +1,80 @@
+"""Cell-partitioned multi-GPU path (NCCL halo exchange + allreduce) against the single-GPU run and the oracle.
+Needs >= 2 CUDA devices (gpurun --gpus 2); skipped otherwise."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+capi, fss = H.capi, H.fss
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _worker(rank, world, nccl_id, text, q):
+    sys.path.insert(0, str(H.ROOT / "tests"))
+    try:
+        inp = capi.InputData(text=text)
+        prob = capi.Problem(inp, device=rank, rank=rank, nranks=world, nccl_id=nccl_id)
+        prob.initialize()
+        reps = [prob.step() for _ in range(2)]
+        be = prob.backend
+        out = dict(rank=rank, reps=reps, gp=prob.global_ids(capi.FIELD_PRESSURE), gu=prob.global_ids(capi.FIELD_DISPLACEMENT),
+                   p=be.get_vector(capi.VEC_P), u=be.get_vector(capi.VEC_U), ev0=be.get_vector(capi.VEC_VOL_STRAIN0), stats=be.stats())
+        q.put(out)
+        prob.close()
+    except Exception as e:  # surface the failure in the parent
+        q.put(dict(rank=rank, error=repr(e)))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("case", ["3d_q1_morton", "3d_q1_ragged", "2d_q2"])
+def test_partitioned_run_matches_single_gpu_and_oracle(world, case):
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    kw = {"3d_q1_morton": dict(dim=3, refine=3, degree_u=1), "3d_q1_ragged": dict(dim=3, refine=2, degree_u=1, cells=[7, 5, 6]),
+          "2d_q2": dict(dim=2, refine=4, degree_u=2)}[case]
+    text = H.make_input(extra_gpu="  set CG max iterations = 5000\n", **kw)
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    nccl_id = capi.nccl_unique_id()
+    procs = [ctx.Process(target=_worker, args=(r, world, nccl_id, text, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for r in res:
+        assert "error" not in r, r
+    res.sort(key=lambda r: r["rank"])
+    n_p = sum(len(r["gp"]) for r in res)
+    n_u = sum(len(r["gu"]) for r in res)
+    p, u, ev0 = np.zeros(n_p), np.zeros(n_u), np.zeros(n_p)
+    for r in res:
+        p[r["gp"]], u[r["gu"]], ev0[r["gp"]] = r["p"], r["u"], r["ev0"]
+    # single-GPU run and oracle on the same input
+    inp = capi.InputData(text=text)
+    mesh = fss.make_mesh(inp)
+    outs = {}
+    for name, b in (("gpu1", capi.create_device_backend(0)), ("oracle", H.create_oracle_backend())):
+        fss.upload_problem(b, inp, mesh)
+        fss.initialize(b, inp)
+        reps = [fss.time_step(b, inp) for _ in range(2)]
+        outs[name] = (b.get_vector(capi.VEC_P), b.get_vector(capi.VEC_U), reps)
+        b.close()
+    assert len(outs["gpu1"][0]) == n_p and len(outs["gpu1"][1]) == n_u
+    for name in ("gpu1", "oracle"):
+        assert fss.rel_l2(p, outs[name][0]) <= 1e-8, (name, fss.rel_l2(p, outs[name][0]))
+        assert fss.rel_l2(u, outs[name][1]) <= 1e-8, (name, fss.rel_l2(u, outs[name][1]))
+    # every rank reports the same (global) iteration counts, and the inner-loop counts are the oracle's
+    for r in res[1:]:
+        assert [s["cg_its_displacement"] for s in r["reps"]] == [s["cg_its_displacement"] for s in res[0]["reps"]]
+    assert [s["pressure_iterations"] for s in res[0]["reps"]] == [s["pressure_iterations"] for s in outs["oracle"][2]]
+    assert sum(r["stats"]["n_dofs_u"] for r in res) == n_u
