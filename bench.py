@@ -191,7 +191,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--refine", type=int, default=7)
-    ap.add_argument("--precond", type=int, default=1)
+    ap.add_argument("--precond", type=int, default=0)
     ap.add_argument("--cheb-degree", type=int, default=4)
     ap.add_argument("--eig-ratio", type=float, default=30.0)
     ap.add_argument("--max-its", type=int, default=4000)
