@@ -132,6 +132,7 @@ void pe_destroy(pe_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  pe_comm_release(c);
   if (c->comm) ncclCommDestroy(c->comm);
   if (c->h_state) cudaFreeHost(c->h_state);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
@@ -303,8 +304,7 @@ int pe_setup(pe_ctx* c) {
     c->proj_rhs[e].alloc_zero((size_t)npl, s);
     c->stresses[e].alloc_zero((size_t)npl, s);
   }
-  const size_t nw = (size_t)std::max(npl, nul);
-  for (DBuf<double>* v : {&c->w_g, &c->w_h, &c->w_d, &c->w_z, &c->w_d2, &c->w_r}) v->alloc_zero(nw, s);
+  pe_comm_setup(c, (size_t)std::max(npl, nul));
   c->M.alloc((size_t)c->fp.nnz);
   c->K.alloc((size_t)c->fp.nnz);
   c->J.alloc_zero((size_t)c->fp.nnz, s);
@@ -390,7 +390,7 @@ int pe_pressure_solve(pe_ctx* c, int* its, double* res) {
   c->st.cg_solves_pressure++;
   if (its) *its = r.its;
   if (res) *res = r.res;
-  if (r.status != PE_OK) throw PeError(r.status, "pressure CG did not converge (SolverControl::NoConvergence, PS:175)");
+  if (r.status != PE_OK) throw PeError(r.status, r.status == PE_ERR_NCCL ? "pressure CG: peer communication timed out" : "pressure CG did not converge (SolverControl::NoConvergence, PS:175)");
   PE_LEAVE(c)
 }
 int pe_pressure_add_update(pe_ctx* c) {
@@ -430,7 +430,7 @@ int pe_displacement_solve(pe_ctx* c, int* its, double* res) {
   c->st.cg_solves_displacement++;
   if (its) *its = r.its;
   if (res) *res = r.res;
-  if (r.status != PE_OK) throw PeError(r.status, "displacement CG did not converge (SolverControl::NoConvergence, DS:299)");
+  if (r.status != PE_OK) throw PeError(r.status, r.status == PE_ERR_NCCL ? "displacement CG: peer communication timed out" : "displacement CG did not converge (SolverControl::NoConvergence, DS:299)");
   PE_LEAVE(c)
 }
 

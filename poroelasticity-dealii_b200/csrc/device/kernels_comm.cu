@@ -1,0 +1,259 @@
+// kernels_comm.cu — K12: ghost-dof halo exchange and the global reductions of CG.
+//
+// The reference is serial (Vector<double>, SparseMatrix<double>: lib/include/PoroElasticPressureSolver.h:36-44);
+// this is the communication of the new cell-partitioned build.  Two transports:
+//   * NCCL (grouped ncclSend/ncclRecv, ncclAllReduce) — setup and the handful of exchanges per time step
+//     outside the CG loop (p, t1, u before cell kernels, the initial guess of a solve);
+//   * peer memory over NVLink/NVSwitch — everything inside the CG loop.  A CG iteration at 8 GPUs is ~0.2 ms
+//     of SpMV and needs one halo exchange and two reductions; NCCL's launch+protocol latency per call
+//     (tens of microseconds) would eat the strong-scaling target.  Here the SENDER's kernel stores the halo
+//     values straight into the ghost segment of the receiver's vector (cudaIpc-mapped), fences at system
+//     scope and bumps an epoch flag in the receiver's control block; reductions go through per-sender
+//     mailboxes, every rank sums the mailboxes in rank order (bitwise identical result on all ranks).
+// All waits are bounded: a peer that never arrives flags CgState and the solve returns PE_ERR_NCCL.
+#include <cstdlib>
+#include <cstring>
+
+#include "pe_internal.cuh"
+
+namespace {
+
+constexpr int T = 256;
+constexpr long long SPIN_TIMEOUT_CYCLES = 20000000000LL;  // ~10 s at 2 GHz
+
+__global__ void k_pack(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ v, double* __restrict__ buf) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) buf[i] = v[idx[i]];
+}
+
+__device__ __forceinline__ int ld_flag(const int* p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_flag(int* p, int v) { asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ double ld_mail(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
+// spin until *flag has reached `epoch` (wrap-safe); false on timeout
+__device__ __forceinline__ bool wait_flag(const int* flag, int epoch) {
+  const long long t0 = clock64();
+  while ((int)(ld_flag(flag) - epoch) < 0) {
+    if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) return false;
+  }
+  return true;
+}
+
+// Sender side of a halo exchange: v_off = offset (in doubles) of the vector inside the work area of every region.
+__global__ void __launch_bounds__(T)
+k_halo_send(int64_t n_send, const int32_t* __restrict__ send_idx, const int32_t* __restrict__ send_dest, const int32_t* __restrict__ send_nb,
+            const int32_t* __restrict__ neigh_rank, int n_neigh, char* const* __restrict__ peer, size_t ctrl_bytes, size_t v_off,
+            const double* __restrict__ v, int field, int me, int epoch, unsigned* __restrict__ ticket, const CgState* __restrict__ state) {
+  if (state && state->done) return;
+  __shared__ bool s_last;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_send; i += (int64_t)gridDim.x * blockDim.x) {
+    double* dst = reinterpret_cast<double*>(peer[neigh_rank[send_nb[i]]] + ctrl_bytes) + v_off;
+    dst[send_dest[i]] = v[send_idx[i]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {  // every block's stores are fenced: publish
+    __threadfence_system();
+    for (int k = threadIdx.x; k < n_neigh; k += blockDim.x) {
+      P2PControl* ctl = reinterpret_cast<P2PControl*>(peer[neigh_rank[k]]);
+      st_flag(&ctl->halo_flag[field][me], epoch);
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
+// Receiver side: returns once every neighbour's halo of this epoch has landed in my ghost segment.
+__global__ void k_halo_wait(const P2PControl* __restrict__ ctl, const int32_t* __restrict__ neigh_rank, int n_neigh, int field, int epoch,
+                            CgState* __restrict__ state) {
+  if (state && state->done) return;
+  bool ok = true;
+  for (int k = threadIdx.x; k < n_neigh; k += blockDim.x) ok = wait_flag(&ctl->halo_flag[field][neigh_rank[k]], epoch) && ok;
+  __threadfence_system();
+  if (!ok && state) { state->pad = 1; state->done = -1; }
+}
+
+// Allreduce(sum) of `count` doubles in place: post to every rank's mailbox, wait for everyone, sum in rank order.
+__global__ void k_allreduce_p2p(double* __restrict__ vals, int count, char* const* __restrict__ peer, int nranks, int me, int epoch,
+                                CgState* __restrict__ state) {
+  if (state && state->done) return;
+  const int r = threadIdx.x;
+  const int par = epoch & 1;
+  if (r < nranks) {
+    P2PControl* ctl = reinterpret_cast<P2PControl*>(peer[r]);
+    for (int k = 0; k < count; ++k) ctl->red_val[par][me][k] = vals[k];
+    __threadfence_system();
+    st_flag(&ctl->red_flag[me], epoch);
+  }
+  const P2PControl* mine = reinterpret_cast<const P2PControl*>(peer[me]);
+  bool ok = true;
+  if (r < nranks) ok = wait_flag(&mine->red_flag[r], epoch);
+  ok = __all_sync(0xffffffffu, ok);
+  __threadfence_system();
+  if (!ok) {
+    if (r == 0 && state) { state->pad = 1; state->done = -1; }
+    return;
+  }
+  if (r < count) {
+    double s = 0.0;
+    for (int q = 0; q < nranks; ++q) s += ld_mail(&mine->red_val[par][q][r]);
+    vals[r] = s;
+  }
+}
+
+bool in_work_area(const pe_ctx* c, const double* v, size_t* off) {
+  const char* w0 = c->p2p.region + c->p2p.ctrl_bytes;
+  const char* p = reinterpret_cast<const char*>(v);
+  if (!c->p2p.region || p < w0 || p >= c->p2p.region + c->p2p.region_bytes) return false;
+  *off = (size_t)(p - w0) / sizeof(double);
+  return true;
+}
+
+}  // namespace
+
+void pe_pack_launch(pe_ctx* c, int64_t n, const int32_t* idx, const double* v, double* buf) {
+  if (!n) return;
+  k_pack<<<pe_div_up(n, T), T, 0, c->stream>>>(n, idx, v, buf);
+  c->st.kernel_launches++;
+}
+
+void pe_allreduce_sum(pe_ctx* c, double* dev, int count, bool in_solve) {
+  if (c->nranks <= 1) return;
+  if (c->p2p.on && count <= 4) {
+    const int epoch = (int)(++c->p2p.red_epoch);
+    k_allreduce_p2p<<<1, 32, 0, c->stream>>>(dev, count, c->p2p.d_peer.p, c->nranks, c->rank, epoch, in_solve ? c->cg_state.p : nullptr);
+    c->st.kernel_launches++;
+    return;
+  }
+  PE_NCCL(ncclAllReduce(dev, dev, count, ncclDouble, ncclSum, c->comm_nccl(), c->stream));
+}
+
+// ghost values of v (entries [n_owned, n_local)) <- owners
+void pe_halo_exchange(pe_ctx* c, Field& F, double* v, bool in_solve) {
+  if (c->nranks <= 1 || F.halo.n_neigh == 0) return;
+  Halo& H = F.halo;
+  const int64_t ns = H.n_send();
+  size_t v_off = 0;
+  const int fi = &F == &c->fu ? 1 : 0;
+  if (c->p2p.on && in_work_area(c, v, &v_off)) {
+    P2PField& P = c->p2p.f[fi];
+    const int epoch = (int)(++P.epoch);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ns + T - 1) / T, 4 * c->sm_count));
+    k_halo_send<<<grid, T, 0, c->stream>>>(ns, H.send_idx.p, P.send_dest.p, P.send_nb.p, P.neigh_rank.p, H.n_neigh, c->p2p.d_peer.p,
+                                           c->p2p.ctrl_bytes, v_off, v, fi, c->rank, epoch, c->p2p.ticket.p, in_solve ? c->cg_state.p : nullptr);
+    k_halo_wait<<<1, 32, 0, c->stream>>>(reinterpret_cast<const P2PControl*>(c->p2p.region), P.neigh_rank.p, H.n_neigh, fi, epoch, in_solve ? c->cg_state.p : nullptr);
+    c->st.kernel_launches += 2;
+    return;
+  }
+  pe_pack_launch(c, ns, H.send_idx.p, v, H.send_buf.p);
+  PE_NCCL(ncclGroupStart());
+  for (int k = 0; k < H.n_neigh; ++k) {
+    const int64_t s0 = H.send_ptr[k], s1 = H.send_ptr[k + 1], r0 = H.recv_ptr[k], r1 = H.recv_ptr[k + 1];
+    if (s1 > s0) PE_NCCL(ncclSend(H.send_buf.p + s0, (size_t)(s1 - s0), ncclDouble, H.rank[k], c->comm_nccl(), c->stream));
+    if (r1 > r0) PE_NCCL(ncclRecv(v + F.n_owned + r0, (size_t)(r1 - r0), ncclDouble, H.rank[k], c->comm_nccl(), c->stream));
+  }
+  PE_NCCL(ncclGroupEnd());
+}
+
+void pe_comm_release(pe_ctx* c) {
+  P2P& M = c->p2p;
+  for (int r = 0; r < (int)M.peer.size(); ++r)
+    if (M.peer[r] && r != c->rank) cudaIpcCloseMemHandle(M.peer[r]);
+  M.peer.clear();
+  if (M.region) cudaFree(M.region);
+  M.region = nullptr;
+  M.on = false;
+}
+
+void pe_comm_setup(pe_ctx* c, size_t n_work) {
+  pe_comm_release(c);
+  P2P& M = c->p2p;
+  cudaStream_t s = c->stream;
+  M.ctrl_bytes = (sizeof(P2PControl) + 255) / 256 * 256;
+  // every rank must use the same vector stride so that offsets mean the same thing in every region
+  long long stride = (long long)((n_work + 31) / 32 * 32);
+  if (c->nranks > 1) {
+    DBuf<long long> d;
+    d.upload(&stride, 1, s);
+    PE_NCCL(ncclAllReduce(d.p, d.p, 1, ncclInt64, ncclMax, c->comm_nccl(), s));
+    PE_CUDA(cudaMemcpyAsync(&stride, d.p, sizeof stride, cudaMemcpyDeviceToHost, s));
+    PE_CUDA(cudaStreamSynchronize(s));
+  }
+  M.region_bytes = M.ctrl_bytes + (size_t)6 * stride * sizeof(double);
+  PE_CUDA(cudaMalloc((void**)&M.region, M.region_bytes));
+  PE_CUDA(cudaMemsetAsync(M.region, 0, M.region_bytes, s));
+  double* w0 = reinterpret_cast<double*>(M.region + M.ctrl_bytes);
+  pe_ctx::WPtr* ws[6] = {&c->w_g, &c->w_h, &c->w_d, &c->w_z, &c->w_d2, &c->w_r};
+  for (int k = 0; k < 6; ++k) ws[k]->p = w0 + (size_t)k * stride;
+  M.peer.assign(c->nranks, nullptr);
+  M.peer[c->rank] = M.region;
+  M.on = false;
+  if (c->nranks > 1) {
+    const char* env = std::getenv("PE_COMM");
+    const bool want = !(env && std::strcmp(env, "nccl") == 0) && c->nranks <= PE_P2P_MAX_RANKS;
+    if (want) {
+      // exchange the IPC handles of all regions through NCCL
+      cudaIpcMemHandle_t mine;
+      PE_CUDA(cudaIpcGetMemHandle(&mine, M.region));
+      DBuf<char> all;
+      all.alloc((size_t)c->nranks * sizeof mine);
+      PE_CUDA(cudaMemcpyAsync(all.p + (size_t)c->rank * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice, s));
+      PE_NCCL(ncclAllGather(all.p + (size_t)c->rank * sizeof mine, all.p, sizeof mine, ncclChar, c->comm_nccl(), s));
+      std::vector<cudaIpcMemHandle_t> h(c->nranks);
+      PE_CUDA(cudaMemcpyAsync(h.data(), all.p, all.n, cudaMemcpyDeviceToHost, s));
+      PE_CUDA(cudaStreamSynchronize(s));
+      for (int r = 0; r < c->nranks; ++r)
+        if (r != c->rank) PE_CUDA(cudaIpcOpenMemHandle((void**)&M.peer[r], h[r], cudaIpcMemLazyEnablePeerAccess));
+      M.d_peer.upload(M.peer, s);
+      M.ticket.alloc_zero(1, s);
+      // landing offsets: neighbour k must be told where its values go inside MY vector (n_owned + recv_ptr[k]);
+      // I need the same number from it.
+      for (int fi = 0; fi < 2; ++fi) {
+        Field& F = fi ? c->fu : c->fp;
+        Halo& H = F.halo;
+        P2PField& P = M.f[fi];
+        P.epoch = 0;
+        const int nn = H.n_neigh;
+        std::vector<long long> mine_off(std::max(nn, 1)), theirs(std::max(nn, 1));
+        for (int k = 0; k < nn; ++k) mine_off[k] = (long long)F.n_owned + H.recv_ptr[k];
+        DBuf<long long> d_out, d_in;
+        d_out.upload(mine_off, s);
+        d_in.alloc(mine_off.size());
+        PE_NCCL(ncclGroupStart());
+        for (int k = 0; k < nn; ++k) {
+          PE_NCCL(ncclSend(d_out.p + k, 1, ncclInt64, H.rank[k], c->comm_nccl(), s));
+          PE_NCCL(ncclRecv(d_in.p + k, 1, ncclInt64, H.rank[k], c->comm_nccl(), s));
+        }
+        PE_NCCL(ncclGroupEnd());
+        PE_CUDA(cudaMemcpyAsync(theirs.data(), d_in.p, theirs.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
+        PE_CUDA(cudaStreamSynchronize(s));
+        std::vector<int32_t> dest((size_t)H.n_send()), nb((size_t)H.n_send()), nr(H.rank.begin(), H.rank.end());
+        for (int k = 0; k < nn; ++k)
+          for (int64_t i = H.send_ptr[k]; i < H.send_ptr[k + 1]; ++i) {
+            dest[i] = (int32_t)(theirs[k] + (i - H.send_ptr[k]));
+            nb[i] = k;
+          }
+        P.send_dest.upload(dest, s);
+        P.send_nb.upload(nb, s);
+        P.neigh_rank.upload(nr, s);
+      }
+      M.red_epoch = 0;
+      // nobody may start storing into a region before every rank has zeroed its own
+      DBuf<int> bar;
+      bar.alloc_zero(1, s);
+      PE_NCCL(ncclAllReduce(bar.p, bar.p, 1, ncclInt, ncclSum, c->comm_nccl(), s));
+      PE_CUDA(cudaStreamSynchronize(s));
+      M.on = true;
+    }
+  }
+  PE_CUDA(cudaStreamSynchronize(s));
+}

@@ -344,6 +344,7 @@ __global__ void k_cg_init_state(CgState* state, const double* __restrict__ red, 
   state->max_it = max_it;
   state->gh = 0.0;
   state->done = 0;
+  state->pad = 0;
   if (res <= state->tol) state->done = 1;
   else if (max_it <= 0 || isnan(res)) state->done = -1;
 }
@@ -400,10 +401,6 @@ __global__ void k_scale_by(int64_t n, const double* __restrict__ s, double* __re
 __global__ void k_distribute(int64_t n_lines, const int32_t* __restrict__ line_dof, const double* __restrict__ g, double* __restrict__ v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_lines) v[line_dof[i]] = g[i];
-}
-__global__ void k_pack(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ v, double* __restrict__ buf) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) buf[i] = v[idx[i]];
 }
 __global__ void k_invdiag(int64_t n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
                           double* __restrict__ invdiag) {
@@ -515,28 +512,6 @@ void pe_prof_flush(pe_ctx* c) {
     else { c->st.spmv_ms_p += ms; c->st.spmv_timed_p++; }
   }
   c->prof_used = 0;
-}
-
-void pe_allreduce_sum(pe_ctx* c, double* dev, int count) {
-  if (c->nranks > 1) PE_NCCL(ncclAllReduce(dev, dev, count, ncclDouble, ncclSum, c->comm, c->stream));
-}
-
-// K12: ghost values of v (entries [n_owned, n_local)) <- owners
-void pe_halo_exchange(pe_ctx* c, Field& F, double* v) {
-  if (c->nranks <= 1 || F.halo.n_neigh == 0) return;
-  Halo& H = F.halo;
-  const int64_t ns = H.n_send();
-  if (ns) {
-    k_pack<<<pe_div_up(ns, VEC_T), VEC_T, 0, c->stream>>>(ns, H.send_idx.p, v, H.send_buf.p);
-    c->st.kernel_launches++;
-  }
-  PE_NCCL(ncclGroupStart());
-  for (int k = 0; k < H.n_neigh; ++k) {
-    const int64_t s0 = H.send_ptr[k], s1 = H.send_ptr[k + 1], r0 = H.recv_ptr[k], r1 = H.recv_ptr[k + 1];
-    if (s1 > s0) PE_NCCL(ncclSend(H.send_buf.p + s0, (size_t)(s1 - s0), ncclDouble, H.rank[k], c->comm, c->stream));
-    if (r1 > r0) PE_NCCL(ncclRecv(v + F.n_owned + r0, (size_t)(r1 - r0), ncclDouble, H.rank[k], c->comm, c->stream));
-  }
-  PE_NCCL(ncclGroupEnd());
 }
 
 void pe_vec_axpy(pe_ctx* c, int64_t n, double a, const double* x, double* y) {
@@ -701,7 +676,7 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
         a.c1 = rho_new * rho;
         a.c2 = 2.0 * rho_new / delta;
         a.state = st;
-        pe_halo_exchange(c, F, din);
+        pe_halo_exchange(c, F, din, true);
         launch_spmv<EPI_CHEB>(c, F, a);
         (*spmv_counter)++;
         rho = rho_new;
@@ -710,7 +685,7 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
       k_dot<<<vg, VEC_T, 0, c->stream>>>(n, st, g, z, R, 2);
       c->st.kernel_launches++;
     }
-    pe_allreduce_sum(c, red + 2, 1);
+    pe_allreduce_sum(c, red + 2, 1, true);
   };
 
   // g = A x - b, ||g||^2 -> red[0]; ||b||^2 -> red[3]
@@ -752,13 +727,13 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
       a.y = h;
       a.state = st;
       a.slot = 0;
-      pe_halo_exchange(c, F, d);
+      pe_halo_exchange(c, F, d, true);
       launch_spmv<EPI_DOT>(c, F, a);  // h = A d, red[0] = d.h
       (*spmv_counter)++;
-      pe_allreduce_sum(c, red, 1);
+      pe_allreduce_sum(c, red, 1, true);
       if (!cheb) k_cg_update<true><<<vg, VEC_T, 0, c->stream>>>(n, st, red, gh_cur, x, g, d, h, invdiag, z, R);
       else k_cg_update<false><<<vg, VEC_T, 0, c->stream>>>(n, st, red, gh_cur, x, g, d, h, invdiag, z, R);
-      pe_allreduce_sum(c, red + 1, cheb ? 1 : 2);
+      pe_allreduce_sum(c, red + 1, cheb ? 1 : 2, true);
       k_cg_check<<<1, 1, 0, c->stream>>>(st, red);
       c->st.kernel_launches += 2;
       if (cheb) apply_precond_and_dot();
@@ -790,6 +765,6 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
   CgResult out;
   out.its = last.it;
   out.res = last.res;
-  out.status = last.done == 1 ? PE_OK : (std::isnan(last.res) ? PE_ERR_NAN : PE_ERR_NO_CONVERGENCE);
+  out.status = last.done == 1 ? PE_OK : (last.pad ? PE_ERR_NCCL : (std::isnan(last.res) ? PE_ERR_NAN : PE_ERR_NO_CONVERGENCE));
   return out;
 }

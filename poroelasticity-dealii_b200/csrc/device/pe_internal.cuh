@@ -122,10 +122,39 @@ struct Reducer {
   DBuf<double> out;        // PE_RED_SLOTS (+ scratch)
 };
 
+// Peer-memory communication over NVLink (kernels_comm.cu): every rank exports one region
+// [control block | six CG work vectors] with cudaIpc; halo values are stored by the SENDER straight into the
+// ghost segment of the receiver's vector and reductions are exchanged through per-sender mailboxes, both
+// published with a system-scope fence + an epoch flag the receiver polls.  NCCL stays for setup and for
+// the few exchanges outside the CG loop.
+static constexpr int PE_P2P_MAX_RANKS = 16;
+struct P2PControl {                                   // lives at the start of every rank's region
+  int halo_flag[2][PE_P2P_MAX_RANKS];                 // [field][sender rank] = epoch of the last halo it stored here
+  int red_flag[PE_P2P_MAX_RANKS];                     // [sender rank] = epoch of its last mailbox post
+  double red_val[2][PE_P2P_MAX_RANKS][4];             // [epoch parity][sender rank][slot]
+};
+struct P2PField {
+  DBuf<int32_t> send_dest;   // per send entry: index in the receiver's vector (ghost segment)
+  DBuf<int32_t> send_nb;     // per send entry: neighbour slot
+  DBuf<int32_t> neigh_rank;  // neighbour ranks (device copy)
+  unsigned epoch = 0;        // halo exchanges posted so far
+};
+struct P2P {
+  bool on = false;
+  char* region = nullptr;            // my region (cudaMalloc)
+  size_t region_bytes = 0, ctrl_bytes = 0;
+  std::vector<char*> peer;           // region of every rank as mapped here (peer[rank] == region)
+  DBuf<char*> d_peer;                // device copy
+  DBuf<unsigned> ticket;             // last-block counter of k_halo_send
+  P2PField f[2];
+  unsigned red_epoch = 0;
+};
+
 struct pe_ctx {
   int device = 0, rank = 0, nranks = 1;
   cudaStream_t stream = nullptr;
   ncclComm_t comm = nullptr;
+  ncclComm_t comm_nccl() const { return comm; }
   std::string err;
   pe_params prm{};
   bool have_params = false, have_mesh = false, setup_done = false;
@@ -167,8 +196,10 @@ struct pe_ctx {
   DBuf<double> u, b, b_const;
   std::vector<DBuf<double>> strains, proj_rhs, stresses;
   int n_stress = 0;
-  // CG work vectors sized for the larger field
-  DBuf<double> w_g, w_h, w_d, w_z, w_d2, w_r;
+  // CG work vectors sized for the larger field; they live in `comm.region` (IPC-exported when nranks > 1)
+  struct WPtr { double* p = nullptr; };
+  WPtr w_g, w_h, w_d, w_z, w_d2, w_r;
+  P2P p2p;
 
   Reducer red;
   DBuf<CgState> cg_state;
@@ -203,7 +234,7 @@ void pe_assemble_projection_rhs(pe_ctx* c, int n_comp, const int32_t* comps, con
 
 // ---- kernels_solver.cu
 struct CgResult { int its; double res; int status; };
-void pe_halo_exchange(pe_ctx* c, Field& F, double* v);
+void pe_halo_exchange(pe_ctx* c, Field& F, double* v, bool in_solve = false);  // in_solve: honour CgState::done
 void pe_extract_invdiag(pe_ctx* c, Field& F, const double* val, double* invdiag);
 double pe_estimate_eig_max(pe_ctx* c, Field& F, const double* val, const double* invdiag);
 CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdiag, double eig_max, double* x, const double* b,
@@ -217,6 +248,10 @@ void pe_vec_axpby_vals(pe_ctx* c, int64_t n, double a, const double* x, double b
 void pe_distribute(pe_ctx* c, Field& F, double* v);  // constrained dofs <- inhomogeneity
 double pe_linfty(pe_ctx* c, Field& F, const double* v);
 void pe_stress_kernel(pe_ctx* c);
-void pe_allreduce_sum(pe_ctx* c, double* dev, int count);
+void pe_allreduce_sum(pe_ctx* c, double* dev, int count, bool in_solve = false);
+// ---- kernels_comm.cu
+void pe_comm_setup(pe_ctx* c, size_t n_work);  // allocates the region (+ IPC exchange when nranks > 1)
+void pe_comm_release(pe_ctx* c);
+void pe_pack_launch(pe_ctx* c, int64_t n, const int32_t* idx, const double* v, double* buf);
 
 static inline int pe_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
