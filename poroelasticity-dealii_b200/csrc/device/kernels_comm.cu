@@ -19,32 +19,10 @@
 namespace {
 
 constexpr int T = 256;
-constexpr long long SPIN_TIMEOUT_CYCLES = 20000000000LL;  // ~10 s at 2 GHz
 
 __global__ void k_pack(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ v, double* __restrict__ buf) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) buf[i] = v[idx[i]];
-}
-
-__device__ __forceinline__ int ld_flag(const int* p) {
-  int v;
-  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void st_flag(int* p, int v) { asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ double ld_mail(const double* p) {
-  double v;
-  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
-
-// spin until *flag has reached `epoch` (wrap-safe); false on timeout
-__device__ __forceinline__ bool wait_flag(const int* flag, int epoch) {
-  const long long t0 = clock64();
-  while ((int)(ld_flag(flag) - epoch) < 0) {
-    if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) return false;
-  }
-  return true;
 }
 
 // Sender side of a halo exchange: v_off = offset (in doubles) of the vector inside the work area of every region.
@@ -66,7 +44,7 @@ k_halo_send(int64_t n_send, const int32_t* __restrict__ send_idx, const int32_t*
     __threadfence_system();
     for (int k = threadIdx.x; k < n_neigh; k += blockDim.x) {
       P2PControl* ctl = reinterpret_cast<P2PControl*>(peer[neigh_rank[k]]);
-      st_flag(&ctl->halo_flag[field][me], epoch);
+      pe_st_flag(&ctl->halo_flag[field][me], epoch);
     }
     if (threadIdx.x == 0) *ticket = 0u;
   }
@@ -77,7 +55,7 @@ __global__ void k_halo_wait(const P2PControl* __restrict__ ctl, const int32_t* _
                             CgState* __restrict__ state) {
   if (state && state->done) return;
   bool ok = true;
-  for (int k = threadIdx.x; k < n_neigh; k += blockDim.x) ok = wait_flag(&ctl->halo_flag[field][neigh_rank[k]], epoch) && ok;
+  for (int k = threadIdx.x; k < n_neigh; k += blockDim.x) ok = pe_wait_flag(&ctl->halo_flag[field][neigh_rank[k]], epoch) && ok;
   __threadfence_system();
   if (!ok && state) { state->pad = 1; state->done = -1; }
 }
@@ -92,11 +70,11 @@ __global__ void k_allreduce_p2p(double* __restrict__ vals, int count, char* cons
     P2PControl* ctl = reinterpret_cast<P2PControl*>(peer[r]);
     for (int k = 0; k < count; ++k) ctl->red_val[par][me][k] = vals[k];
     __threadfence_system();
-    st_flag(&ctl->red_flag[me], epoch);
+    pe_st_flag(&ctl->red_flag[me], epoch);
   }
   const P2PControl* mine = reinterpret_cast<const P2PControl*>(peer[me]);
   bool ok = true;
-  if (r < nranks) ok = wait_flag(&mine->red_flag[r], epoch);
+  if (r < nranks) ok = pe_wait_flag(&mine->red_flag[r], epoch);
   ok = __all_sync(0xffffffffu, ok);
   __threadfence_system();
   if (!ok) {
@@ -105,7 +83,7 @@ __global__ void k_allreduce_p2p(double* __restrict__ vals, int count, char* cons
   }
   if (r < count) {
     double s = 0.0;
-    for (int q = 0; q < nranks; ++q) s += ld_mail(&mine->red_val[par][q][r]);
+    for (int q = 0; q < nranks; ++q) s += pe_ld_mail(&mine->red_val[par][q][r]);
     vals[r] = s;
   }
 }
@@ -138,7 +116,8 @@ void pe_allreduce_sum(pe_ctx* c, double* dev, int count, bool in_solve) {
 }
 
 // ghost values of v (entries [n_owned, n_local)) <- owners
-void pe_halo_exchange(pe_ctx* c, Field& F, double* v, bool in_solve) {
+void pe_halo_exchange(pe_ctx* c, Field& F, double* v, bool in_solve, int* fused_epoch) {
+  if (fused_epoch) *fused_epoch = 0;
   if (c->nranks <= 1 || F.halo.n_neigh == 0) return;
   Halo& H = F.halo;
   const int64_t ns = H.n_send();
@@ -150,8 +129,13 @@ void pe_halo_exchange(pe_ctx* c, Field& F, double* v, bool in_solve) {
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((ns + T - 1) / T, 4 * c->sm_count));
     k_halo_send<<<grid, T, 0, c->stream>>>(ns, H.send_idx.p, P.send_dest.p, P.send_nb.p, P.neigh_rank.p, H.n_neigh, c->p2p.d_peer.p,
                                            c->p2p.ctrl_bytes, v_off, v, fi, c->rank, epoch, c->p2p.ticket.p, in_solve ? c->cg_state.p : nullptr);
+    c->st.kernel_launches++;
+    if (fused_epoch) {
+      *fused_epoch = epoch;
+      return;
+    }
     k_halo_wait<<<1, 32, 0, c->stream>>>(reinterpret_cast<const P2PControl*>(c->p2p.region), P.neigh_rank.p, H.n_neigh, fi, epoch, in_solve ? c->cg_state.p : nullptr);
-    c->st.kernel_launches += 2;
+    c->st.kernel_launches++;
     return;
   }
   pe_pack_launch(c, ns, H.send_idx.p, v, H.send_buf.p);

@@ -16,6 +16,7 @@
 // polls a pinned copy every few iterations, one poll behind the launches, so the GPU never idles.
 #include <cmath>
 #include <deque>
+#include <type_traits>
 
 #include "pe_internal.cuh"
 
@@ -28,7 +29,41 @@ struct RedArgs {
   double* partials;
   unsigned* counter;
   double* out;
+  // fused peer-memory allreduce: when `peer` is set the last block also posts the totals to every rank's mailbox
+  char* const* peer;
+  int nranks, me, epoch;
 };
+
+// Where a consumer kernel finds a reduced scalar: the local slot (1 rank / NCCL already reduced it in place) or
+// the per-sender mailboxes of the peer-memory protocol (summed in rank order => identical bits on every rank).
+struct RedIn {
+  const double* local;
+  const P2PControl* ctl;
+  int nranks, epoch;
+};
+
+// block-cooperative; call from uniform control flow.  *ok is cleared on a peer timeout.
+__device__ __forceinline__ double red_fetch(const RedIn& r, int slot, bool* ok) {
+  if (r.ctl == nullptr) return r.local[slot];
+  __shared__ double s_val[PE_RED_SLOTS];
+  __shared__ int s_ok;
+  if (threadIdx.x < 32) {
+    bool good = true;
+    if ((int)threadIdx.x < r.nranks) good = pe_wait_flag(&r.ctl->red_flag[threadIdx.x], r.epoch);
+    good = __all_sync(0xffffffffu, good);
+    __threadfence_system();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      if (good)
+        for (int q = 0; q < r.nranks; ++q) s += pe_ld_mail(&r.ctl->red_val[r.epoch & 1][q][slot]);
+      s_val[slot] = s;
+      s_ok = good ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  if (!s_ok) *ok = false;
+  return s_val[slot];
+}
 
 // Block-reduce NV values; the last block of the grid adds the per-block partials in a fixed order
 // and stores the totals to out[slot0..slot0+NV).  Requires gridDim.x <= PE_MAX_RED_BLOCKS.
@@ -71,7 +106,17 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], RedArgs R, int slot
       if (w == 0) {
         double y = lane < nw ? s_part[k][lane] : 0.0;
         for (int o = 16; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
-        if (lane == 0) R.out[slot0 + k] = y;
+        if (lane == 0) { R.out[slot0 + k] = y; s_part[k][0] = y; }
+      }
+    }
+    if (R.peer) {  // fused allreduce: totals -> every rank's mailbox, then fence, then the epoch flag
+      __syncthreads();
+      if ((int)threadIdx.x < R.nranks) {
+        P2PControl* ctl = reinterpret_cast<P2PControl*>(R.peer[threadIdx.x]);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) ctl->red_val[R.epoch & 1][R.me][slot0 + k] = s_part[k][0];
+        __threadfence_system();
+        pe_st_flag(&ctl->red_flag[R.me], R.epoch);
       }
     }
     if (threadIdx.x == 0) *R.counter = 0u;
@@ -183,6 +228,10 @@ struct SpmvArgs {
   const CgState* state;   // early exit when state->done != 0 (may be null)
   RedArgs red;
   int slot;
+  // fused halo wait (peer-memory protocol): block until every neighbour's values of `halo_epoch` have landed
+  const P2PControl* ctl;
+  const int32_t* neigh_rank;
+  int n_neigh, field, halo_epoch;
 };
 
 // CSR SpMV with warp-blocked rows.  A warp owns 32 CONSECUTIVE rows: their row pointers arrive with one
@@ -193,6 +242,13 @@ struct SpmvArgs {
 template <int LPR, int EPI>
 __global__ void __launch_bounds__(SPMV_T) k_spmv(SpmvArgs a) {
   if (a.state && a.state->done) return;
+  if (a.ctl) {
+    bool ok = true;
+    if ((int)threadIdx.x < a.n_neigh) ok = pe_wait_flag(&a.ctl->halo_flag[a.field][a.neigh_rank[threadIdx.x]], a.halo_epoch);
+    if (!ok && a.state) { CgState* st = const_cast<CgState*>(a.state); st->pad = 1; st->done = -1; }
+    __threadfence_system();
+    __syncthreads();
+  }
   constexpr int G = 32 / LPR;  // rows in flight per round
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, grp = lane / LPR;
   const int64_t n_blocks = (a.n + 31) >> 5;
@@ -282,14 +338,31 @@ __global__ void k_residual_t1(int64_t n, const double* __restrict__ ev, const do
   t1[i] = x1 + x2;
 }
 
+// SolverControl::check for iteration `it` with ||g||^2 = res2; one thread records it.  Returns true when the
+// solve is over (every thread of every block computes the same answer from the same reduced value).
+__device__ __forceinline__ bool cg_check(CgState* state, double res2, int it, bool comm_ok) {
+  const double res = sqrt(res2);
+  const bool converged = res <= state->tol;
+  const bool failed = !comm_ok || it >= state->max_it || isnan(res);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    state->it = it;
+    state->res = res;
+    if (!comm_ok) state->pad = 1;
+    if (converged) state->done = 1; else if (failed) state->done = -1;
+  }
+  return converged || failed;
+}
+
 // CG update (after h = A d): alpha = gh/dh; g += alpha h; x += alpha d; res2 = g.g; [Jacobi] z = D^-1 g, gz = g.z
 template <bool JACOBI>
 __global__ void __launch_bounds__(VEC_T)
-k_cg_update(int64_t n, const CgState* __restrict__ state, const double* __restrict__ red_in, const double* __restrict__ gh_cur,
-            double* __restrict__ x, double* __restrict__ g, const double* __restrict__ d, const double* __restrict__ h,
-            const double* __restrict__ invdiag, double* __restrict__ z, RedArgs red) {
+k_cg_update(int64_t n, const CgState* __restrict__ state, RedIn dh_in, const double* __restrict__ gh_cur, double* __restrict__ x,
+            double* __restrict__ g, const double* __restrict__ d, const double* __restrict__ h, const double* __restrict__ invdiag,
+            double* __restrict__ z, RedArgs red) {
   if (state->done) return;
-  const double alpha = *gh_cur / red_in[0];
+  bool ok = true;
+  const double dh = red_fetch(dh_in, 0, &ok);
+  const double alpha = *gh_cur / dh;  // a peer timeout yields dh = 0: the next check flags the failure
   double acc[2] = {0.0, 0.0};
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double gi = g[i] + alpha * h[i];
@@ -305,34 +378,32 @@ k_cg_update(int64_t n, const CgState* __restrict__ state, const double* __restri
   grid_reduce<2>(acc, red, 1);
 }
 
-// single thread: iteration bookkeeping after the update kernel (SolverControl::check)
-__global__ void k_cg_check(CgState* state, const double* __restrict__ red) {
-  if (state->done) return;
-  state->it += 1;
-  const double res = sqrt(red[1]);
-  state->res = res;
-  if (res <= state->tol) state->done = 1;
-  else if (state->it >= state->max_it || isnan(res)) state->done = -1;
-}
-
-// d = beta d - z with beta = gz_new / gh_old.  gh lives in a two-entry ring indexed by iteration parity
-// (the host knows the parity when it enqueues), so no thread reads a value another one is writing.
+// [check of iteration `it` when do_check] then d = beta d - z with beta = gz_new / gh_old.  gh lives in a two-entry
+// ring indexed by iteration parity (the host knows the parity when it enqueues), so no thread reads a value
+// another one is writing.
 __global__ void __launch_bounds__(VEC_T)
-k_cg_direction(int64_t n, const CgState* __restrict__ state, const double* __restrict__ red, const double* __restrict__ gh_cur,
+k_cg_direction(int64_t n, CgState* __restrict__ state, RedIn r_in, int it, bool do_check, const double* __restrict__ gh_cur,
                double* __restrict__ gh_next, double* __restrict__ d, const double* __restrict__ z) {
   if (state->done) return;
-  const double gz = red[2];
+  bool ok = true;
+  if (do_check) {
+    const double res2 = red_fetch(r_in, 1, &ok);
+    if (cg_check(state, res2, it, ok)) return;
+  }
+  const double gz = red_fetch(r_in, 2, &ok);
   const double beta = gz / *gh_cur;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = beta * d[i] - z[i];
   if (blockIdx.x == 0 && threadIdx.x == 0) *gh_next = gz;
 }
 
 // start of a solve: z = P^-1 g was computed; d = -z ; gh = g.z (in red[2])
-__global__ void k_cg_start(int64_t n, const CgState* __restrict__ state, const double* __restrict__ red, double* __restrict__ gh0,
-                           double* __restrict__ d, const double* __restrict__ z) {
+__global__ void k_cg_start(int64_t n, const CgState* __restrict__ state, RedIn r_in, double* __restrict__ gh0, double* __restrict__ d,
+                           const double* __restrict__ z) {
   if (state->done) return;
+  bool ok = true;
+  const double gz = red_fetch(r_in, 2, &ok);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = -z[i];
-  if (blockIdx.x == 0 && threadIdx.x == 0) *gh0 = red[2];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *gh0 = gz;
 }
 __global__ void k_cg_init_state(CgState* state, const double* __restrict__ red, double tol, int tol_relative, int max_it) {
   // red[0] = ||g0||^2, red[3] = ||b||^2 (when relative)
@@ -374,9 +445,14 @@ k_dot(int64_t n, const CgState* __restrict__ state, const double* __restrict__ a
 
 // Chebyshev start: r = g ; d = (1/theta) D^-1 r ; z = d
 __global__ void __launch_bounds__(VEC_T)
-k_cheb_first(int64_t n, const CgState* __restrict__ state, const double* __restrict__ g, const double* __restrict__ invdiag, double inv_theta,
-             double* __restrict__ r, double* __restrict__ d, double* __restrict__ z) {
+k_cheb_first(int64_t n, CgState* __restrict__ state, RedIn r_in, int it, bool do_check, const double* __restrict__ g,
+             const double* __restrict__ invdiag, double inv_theta, double* __restrict__ r, double* __restrict__ d, double* __restrict__ z) {
   if (state && state->done) return;
+  if (do_check) {
+    bool ok = true;
+    const double res2 = red_fetch(r_in, 1, &ok);
+    if (cg_check(state, res2, it, ok)) return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double gi = g[i];
     const double di = inv_theta * invdiag[i] * gi;
@@ -448,7 +524,7 @@ __global__ void k_stress(int64_t n, int dim, double lambda, double mu, const dou
   }
 }
 
-inline RedArgs red_args(pe_ctx* c) { return RedArgs{c->red.partials.p, c->red.counter.p, c->red.out.p}; }
+inline RedArgs red_args(pe_ctx* c) { return RedArgs{c->red.partials.p, c->red.counter.p, c->red.out.p, nullptr, 1, 0, 0}; }
 
 inline int vec_grid(pe_ctx* c, int64_t n) {
   int64_t want = (n + VEC_T - 1) / VEC_T;
@@ -476,7 +552,7 @@ void launch_spmv(pe_ctx* c, Field& F, SpmvArgs& a) {
   a.rowptr = F.rowptr.p;
   a.col = F.col.p;
   a.n = F.n_owned;
-  a.red = red_args(c);
+  if (a.red.partials == nullptr) a.red = red_args(c);
   const int lpr = lanes_per_row(F);
   const int grid = spmv_grid(c, a.n, lpr);
   if (c->profiling) pe_prof_begin(c, &F == &c->fu ? 1 : 0);
@@ -638,28 +714,76 @@ double pe_estimate_eig_max(pe_ctx* c, Field& F, const double* val, const double*
 }
 
 // Preconditioned CG.  x is n_local (ghost slots are scratch), b is read on owned rows.
+//
+// Communication modes inside the loop:
+//   1 rank ............ none;
+//   NCCL (PE_COMM=nccl) grouped send/recv before each SpMV, ncclAllReduce in place after each reducing kernel;
+//   peer memory ....... k_halo_send stores d into the neighbours' ghost segments, the SpMV itself waits for
+//                       the flags; the last block of every reducing kernel posts its totals to all mailboxes and
+//                       the consuming kernel sums them in its prologue (no collective launches at all).
 CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdiag, double eig_max, double* x, const double* b, double tol,
                      bool tol_relative_to_b, int64_t* spmv_counter) {
   const int64_t n = F.n_owned;
   double *g = c->w_g.p, *h = c->w_h.p, *d = c->w_d.p, *z = c->w_z.p, *d2 = c->w_d2.p, *r = c->w_r.p;
   CgState* st = c->cg_state.p;
-  RedArgs R = red_args(c);
+  const RedArgs R0 = red_args(c);
   double* red = c->red.out.p;
   double* ghbuf = red + PE_RED_SLOTS + 2;  // two-entry ring for g.h
   const int vg = std::min(vec_grid(c, n), PE_MAX_RED_BLOCKS);
   const bool cheb = c->prm.preconditioner == PE_PRECOND_CHEBYSHEV && c->prm.chebyshev_degree > 1;
   const int kdeg = c->prm.chebyshev_degree;
+  const bool multi = c->nranks > 1;
+  const bool fused = multi && c->p2p.on;
+  const P2PControl* ctl = fused ? reinterpret_cast<const P2PControl*>(c->p2p.region) : nullptr;
+  const int fi = &F == &c->fu ? 1 : 0;
   // Chebyshev interval [lmax/ratio, lmax] on D^-1 A
   const double lmax = eig_max, lmin = eig_max / c->prm.chebyshev_eig_ratio;
   const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
 
-  // z = P^-1 g (P = Jacobi or Chebyshev polynomial), gz -> red[2]
-  auto apply_precond_and_dot = [&]() {
+  // a reducing kernel about to be launched: in fused mode it posts under a fresh epoch
+  auto producer = [&](int* epoch) {
+    RedArgs R = R0;
+    *epoch = 0;
+    if (fused) {
+      *epoch = (int)(++c->p2p.red_epoch);
+      R.peer = c->p2p.d_peer.p;
+      R.nranks = c->nranks;
+      R.me = c->rank;
+      R.epoch = *epoch;
+    }
+    return R;
+  };
+  auto consumer = [&](int epoch) { return RedIn{red, fused ? ctl : nullptr, c->nranks, epoch}; };
+  // in-place collective for the NCCL mode (the fused mode needs none, one rank neither)
+  auto nccl_sum = [&](double* p, int count) {
+    if (multi && !fused) pe_allreduce_sum(c, p, count, true);
+  };
+  // SpMV on a vector that lives in the work area: ship its halo first, let the kernel wait for the flags
+  auto spmv_in_solve = [&](SpmvArgs& a, double* xvec, auto epi_tag) {
+    int halo_epoch = 0;
+    pe_halo_exchange(c, F, xvec, true, fused ? &halo_epoch : nullptr);
+    if (halo_epoch) {
+      a.ctl = ctl;
+      a.neigh_rank = c->p2p.f[fi].neigh_rank.p;
+      a.n_neigh = F.halo.n_neigh;
+      a.field = fi;
+      a.halo_epoch = halo_epoch;
+    }
+    launch_spmv<decltype(epi_tag)::value>(c, F, a);
+    (*spmv_counter)++;
+  };
+
+  // z = P^-1 g (P = Jacobi or Chebyshev polynomial) and g.z -> slot 2; `check_in`/`it` fold SolverControl::check of
+  // the iteration that just updated g into the first kernel (Chebyshev only; Jacobi folds it into k_cg_direction).
+  // Returns the epoch under which g.z was posted.
+  auto apply_precond_and_dot = [&](bool do_check, RedIn check_in, int it) {
+    int e = 0;
     if (!cheb) {
+      RedArgs R = producer(&e);
       k_jacobi_dot<<<vg, VEC_T, 0, c->stream>>>(n, st, g, invdiag, z, R);
       c->st.kernel_launches++;
     } else {
-      k_cheb_first<<<vg, VEC_T, 0, c->stream>>>(n, st, g, invdiag, 1.0 / theta, r, d2, z);
+      k_cheb_first<<<vg, VEC_T, 0, c->stream>>>(n, st, check_in, it, do_check, g, invdiag, 1.0 / theta, r, d2, z);
       c->st.kernel_launches++;
       double rho = 1.0 / sigma;
       double* din = d2;
@@ -676,19 +800,19 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
         a.c1 = rho_new * rho;
         a.c2 = 2.0 * rho_new / delta;
         a.state = st;
-        pe_halo_exchange(c, F, din, true);
-        launch_spmv<EPI_CHEB>(c, F, a);
-        (*spmv_counter)++;
+        spmv_in_solve(a, din, std::integral_constant<int, EPI_CHEB>{});
         rho = rho_new;
         std::swap(din, dout);
       }
+      RedArgs R = producer(&e);
       k_dot<<<vg, VEC_T, 0, c->stream>>>(n, st, g, z, R, 2);
       c->st.kernel_launches++;
     }
-    pe_allreduce_sum(c, red + 2, 1, true);
+    nccl_sum(red + 2, 1);
+    return e;
   };
 
-  // g = A x - b, ||g||^2 -> red[0]; ||b||^2 -> red[3]
+  // g = A x - b, ||g||^2 -> red[0]; ||b||^2 -> red[3]   (cold path: plain collectives, CgState not yet valid)
   pe_halo_exchange(c, F, x);
   {
     SpmvArgs a{};
@@ -702,14 +826,16 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
     (*spmv_counter)++;
   }
   if (tol_relative_to_b) {
-    k_dot<<<vg, VEC_T, 0, c->stream>>>(n, nullptr, b, b, R, 3);
+    k_dot<<<vg, VEC_T, 0, c->stream>>>(n, nullptr, b, b, R0, 3);
     c->st.kernel_launches++;
   }
   pe_allreduce_sum(c, red, PE_RED_SLOTS);
   k_cg_init_state<<<1, 1, 0, c->stream>>>(st, red, tol, tol_relative_to_b ? 1 : 0, c->prm.cg_max_iterations);
-  apply_precond_and_dot();
-  k_cg_start<<<vg, VEC_T, 0, c->stream>>>(n, st, red, ghbuf, d, z);
-  c->st.kernel_launches += 2;
+  {
+    const int e = apply_precond_and_dot(false, consumer(0), 0);
+    k_cg_start<<<vg, VEC_T, 0, c->stream>>>(n, st, consumer(e), ghbuf, d, z);
+    c->st.kernel_launches += 2;
+  }
 
   const int max_it = c->prm.cg_max_iterations;
   const int interval = c->prm.cg_check_interval > 0 ? c->prm.cg_check_interval : 8;
@@ -719,25 +845,30 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
   auto launch_chunk = [&]() {
     const int chunk = std::min(interval, max_it - launched);
     for (int k = 0; k < chunk; ++k) {
-      double* gh_cur = ghbuf + ((launched + k) & 1);
-      double* gh_nxt = ghbuf + ((launched + k + 1) & 1);
+      const int it = launched + k + 1;
+      double* gh_cur = ghbuf + ((it - 1) & 1);
+      double* gh_nxt = ghbuf + (it & 1);
+      int e_dh = 0, e_upd = 0;
       SpmvArgs a{};
       a.val = val;
       a.x = d;
       a.y = h;
       a.state = st;
       a.slot = 0;
-      pe_halo_exchange(c, F, d, true);
-      launch_spmv<EPI_DOT>(c, F, a);  // h = A d, red[0] = d.h
-      (*spmv_counter)++;
-      pe_allreduce_sum(c, red, 1, true);
-      if (!cheb) k_cg_update<true><<<vg, VEC_T, 0, c->stream>>>(n, st, red, gh_cur, x, g, d, h, invdiag, z, R);
-      else k_cg_update<false><<<vg, VEC_T, 0, c->stream>>>(n, st, red, gh_cur, x, g, d, h, invdiag, z, R);
-      pe_allreduce_sum(c, red + 1, cheb ? 1 : 2, true);
-      k_cg_check<<<1, 1, 0, c->stream>>>(st, red);
-      c->st.kernel_launches += 2;
-      if (cheb) apply_precond_and_dot();
-      k_cg_direction<<<vg, VEC_T, 0, c->stream>>>(n, st, red, gh_cur, gh_nxt, d, z);
+      a.red = producer(&e_dh);
+      spmv_in_solve(a, d, std::integral_constant<int, EPI_DOT>{});  // h = A d, slot 0 = d.h
+      nccl_sum(red, 1);
+      RedArgs Ru = producer(&e_upd);
+      if (!cheb) k_cg_update<true><<<vg, VEC_T, 0, c->stream>>>(n, st, consumer(e_dh), gh_cur, x, g, d, h, invdiag, z, Ru);
+      else k_cg_update<false><<<vg, VEC_T, 0, c->stream>>>(n, st, consumer(e_dh), gh_cur, x, g, d, h, invdiag, z, Ru);
+      c->st.kernel_launches++;
+      nccl_sum(red + 1, cheb ? 1 : 2);
+      if (!cheb) {
+        k_cg_direction<<<vg, VEC_T, 0, c->stream>>>(n, st, consumer(e_upd), it, true, gh_cur, gh_nxt, d, z);
+      } else {
+        const int e_gz = apply_precond_and_dot(true, consumer(e_upd), it);
+        k_cg_direction<<<vg, VEC_T, 0, c->stream>>>(n, st, consumer(e_gz), it, false, gh_cur, gh_nxt, d, z);
+      }
       c->st.kernel_launches++;
     }
     launched += chunk;

@@ -234,7 +234,9 @@ void pe_assemble_projection_rhs(pe_ctx* c, int n_comp, const int32_t* comps, con
 
 // ---- kernels_solver.cu
 struct CgResult { int its; double res; int status; };
-void pe_halo_exchange(pe_ctx* c, Field& F, double* v, bool in_solve = false);  // in_solve: honour CgState::done
+// in_solve: honour CgState::done.  fused_epoch != null: peer-memory sends skip the separate wait kernel and return the
+// epoch the consumer has to wait for itself (0 when nothing has to be waited for).
+void pe_halo_exchange(pe_ctx* c, Field& F, double* v, bool in_solve = false, int* fused_epoch = nullptr);
 void pe_extract_invdiag(pe_ctx* c, Field& F, const double* val, double* invdiag);
 double pe_estimate_eig_max(pe_ctx* c, Field& F, const double* val, const double* invdiag);
 CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdiag, double eig_max, double* x, const double* b,
@@ -253,5 +255,28 @@ void pe_allreduce_sum(pe_ctx* c, double* dev, int count, bool in_solve = false);
 void pe_comm_setup(pe_ctx* c, size_t n_work);  // allocates the region (+ IPC exchange when nranks > 1)
 void pe_comm_release(pe_ctx* c);
 void pe_pack_launch(pe_ctx* c, int64_t n, const int32_t* idx, const double* v, double* buf);
+
+#ifdef __CUDACC__
+// ---- device-side primitives of the peer-memory protocol (used by kernels_comm.cu and kernels_solver.cu)
+__device__ __forceinline__ int pe_ld_flag(const int* p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void pe_st_flag(int* p, int v) { asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ double pe_ld_mail(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+// spin until *flag has reached `epoch` (wrap-safe compare); false after ~10 s
+__device__ __forceinline__ bool pe_wait_flag(const int* flag, int epoch) {
+  const long long t0 = clock64();
+  while ((int)(pe_ld_flag(flag) - epoch) < 0) {
+    if (clock64() - t0 > 20000000000LL) return false;
+  }
+  return true;
+}
+#endif
 
 static inline int pe_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
