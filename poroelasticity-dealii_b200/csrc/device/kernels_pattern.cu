@@ -157,6 +157,14 @@ __global__ void row_pattern(const int32_t* __restrict__ cell_dofs, int nloc, int
   if (!WRITE && lane == 0) rowlen[row] = base;
 }
 
+// first row that references a ghost column (col >= n_owned)
+__global__ void first_ghost_row(int64_t n_owned, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int* __restrict__ first) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_owned) return;
+  // columns ascend: the last entry of the row is its largest column
+  if (rowptr[r + 1] > rowptr[r] && col[rowptr[r + 1] - 1] >= n_owned) atomicMin(first, (int)r);
+}
+
 }  // namespace
 
 int64_t pe_exclusive_scan_i32(pe_ctx* c, int32_t* data, int64_t n) {
@@ -222,4 +230,16 @@ void pe_build_pattern(pe_ctx* c, Field& F) {
   PE_CUDA(cudaGetLastError());
   if (h_over) throw PeError(PE_ERR_UNSUPPORTED, "row-pattern shared-memory capacity exceeded");
   c->st.kernel_launches += 4;
+  // rows before the first one with a ghost column can be multiplied before the halo has arrived
+  F.n_interior = F.n_owned;
+  if (F.n_local > F.n_owned) {
+    DBuf<int> first;
+    int init = (int)F.n_owned;
+    first.upload(&init, 1, c->stream);
+    first_ghost_row<<<pe_div_up(F.n_owned, T), T, 0, c->stream>>>(F.n_owned, F.rowptr.p, F.col.p, first.p);
+    PE_CUDA(cudaMemcpyAsync(&init, first.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PE_CUDA(cudaStreamSynchronize(c->stream));
+    F.n_interior = (int64_t)(init / 32) * 32;  // whole 32-row warp blocks
+    c->st.kernel_launches++;
+  }
 }

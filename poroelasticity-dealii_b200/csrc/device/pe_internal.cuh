@@ -104,6 +104,7 @@ struct Field {
   // CSR pattern of the owned rows, columns ascending (local ids)
   DBuf<int32_t> rowptr, col;
   int64_t nnz = 0;
+  int64_t n_interior = 0;  // rows [0, n_interior) reference no ghost column (32-row aligned); == n_owned on one rank
   Halo halo;
 };
 
@@ -210,7 +211,7 @@ struct pe_ctx {
   pe_stats st{};
 
   // optional per-launch timing of the matrix passes (roofline evidence): event pairs on `stream`
-  bool profiling = false;
+  bool profiling = false, prof_hold = false;
   std::vector<cudaEvent_t> prof_ev;        // 2 * PROF_PAIRS events
   std::vector<int> prof_field;             // field of each recorded pair
   int prof_used = 0;

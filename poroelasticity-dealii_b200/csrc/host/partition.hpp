@@ -6,8 +6,10 @@
 // (octants/boxes for Morton-ordered 2^L grids, slabs for lexicographic ones).  A dof is owned by
 // the rank of the first cell that touches it (== the cell that numbered it, first-touch).  A rank
 // keeps every cell that touches one of its owned dofs (its own cells plus one ghost layer), so
-// owned matrix rows assemble without communication.  Local dof order: [owned ascending | ghosts
-// grouped by owner rank, ascending], which makes every receive land contiguously.
+// owned matrix rows assemble without communication.  Local dof order: [owned interior | owned boundary |
+// ghosts grouped by owner rank], each group ascending in the global id.  "Interior" dofs share no cell
+// with a ghost dof, so their matrix rows need no halo value: the device runs those rows while the halo
+// exchange is still in flight.  Ghosts grouped by owner make every receive land contiguously.
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -72,6 +74,16 @@ inline void build_field(const mesh::Mesh& m, const dofs::DofMap& d, const std::v
     std::sort(all.begin(), all.end());
     all.erase(std::unique(all.begin(), all.end()), all.end());
     for (int32_t g : all) (owner[g] == rank ? owned : ghost).push_back(g);
+  }
+  {  // interior-first order of the owned dofs
+    std::vector<uint8_t> boundary(d.n_dofs, 0);
+    for (int64_t c : local_cells) {
+      bool has_ghost = false;
+      for (int k = 0; k < d.n_loc; ++k) has_ghost |= owner[d.cell_dofs[c * d.n_loc + k]] != rank;
+      if (has_ghost)
+        for (int k = 0; k < d.n_loc; ++k) boundary[d.cell_dofs[c * d.n_loc + k]] = 1;
+    }
+    std::stable_sort(owned.begin(), owned.end(), [&](int32_t a, int32_t b) { return boundary[a] != boundary[b] ? boundary[a] < boundary[b] : a < b; });
   }
   std::stable_sort(ghost.begin(), ghost.end(), [&](int32_t a, int32_t b) { return owner[a] != owner[b] ? owner[a] < owner[b] : a < b; });
   F.n_owned = (int64_t)owned.size();

@@ -57,7 +57,17 @@ def test_partition_invariants(nranks):
             owner = np.empty(d.n_dofs, int)
             for r, o in enumerate(owned):
                 owner[o] = r
-                assert np.all(np.diff(o) > 0)
+            for r, p in enumerate(parts):  # owned = [interior ascending | boundary ascending]; interior rows touch no ghost
+                F = p.field[f]
+                o = owned[r]
+                touches_ghost = np.zeros(F["n_local"], bool)
+                cd = F["cell_dofs"]
+                ghost_cells = (cd >= F["n_owned"]).any(axis=1)
+                touches_ghost[np.unique(cd[ghost_cells])] = True
+                tb = touches_ghost[: F["n_owned"]]
+                n_int = int((~tb).sum())
+                assert not tb[:n_int].any() and tb[n_int:].all(), name
+                assert np.all(np.diff(o[:n_int]) > 0) and np.all(np.diff(o[n_int:]) > 0)
             for r, p in enumerate(parts):
                 F = p.field[f]
                 # local cell dofs map back to the global numbering
