@@ -15,6 +15,7 @@
 // to arrive sums them in a fixed order.  Loop control lives on the device (CgState); the host only
 // polls a pinned copy every few iterations, one poll behind the launches, so the GPU never idles.
 #include <cmath>
+#include <cstdlib>
 #include <deque>
 #include <type_traits>
 
@@ -770,7 +771,10 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
     constexpr int EPI = decltype(epi_tag)::value;
     int halo_epoch = 0;
     pe_halo_exchange(c, F, xvec, true, fused ? &halo_epoch : nullptr);
-    const bool split = halo_epoch && F.n_interior >= 4096;
+    // measured on 8 B200s at 128^3: the extra launch and the short boundary kernel cost more than the hidden halo
+    // latency saves (157 vs 147 ms per step), so the split is opt-in
+    static const bool want_split = std::getenv("PE_SPLIT_SPMV") != nullptr;
+    const bool split = want_split && halo_epoch && F.n_interior >= 4096;
     if (split && c->profiling) {  // one timed "matrix pass" = interior + boundary launch
       pe_prof_begin(c, fi);
       c->prof_hold = true;
