@@ -105,6 +105,8 @@ typedef struct pe_stats {
   double  spmv_ms_p, spmv_ms_u;              /* CUDA-event time summed over the matrix passes timed while
                                                 profiling is on (pe_set_profiling)          */
   int64_t spmv_timed_p, spmv_timed_u;        /* number of matrix passes in those sums      */
+  double  pcg_ms_p, pcg_ms_u;                /* CUDA-event time of the persistent CG kernel launches (profiling on) */
+  int64_t pcg_iterations_p, pcg_iterations_u;/* CG iterations executed inside those launches */
 } pe_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------- */

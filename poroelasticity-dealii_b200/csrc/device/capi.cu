@@ -110,6 +110,9 @@ int pe_create(pe_ctx** out, int device, int rank, int nranks, const void* nccl_i
     c->red.counter.alloc_zero(1, c->stream);
     c->red.out.alloc_zero(PE_RED_SLOTS + 8, c->stream);
     c->cg_state.alloc_zero(1, c->stream);
+    c->pcg_tickets.alloc_zero(4, c->stream);
+    c->pcg_flags.alloc_zero(2, c->stream);
+    c->pcg_timing.alloc_zero(2, c->stream);
     PE_CUDA(cudaMallocHost((void**)&c->h_state, 2 * sizeof(CgState)));
     PE_CUDA(cudaMallocHost((void**)&c->h_scalars, (PE_RED_SLOTS + 8) * sizeof(double)));
     PE_CUDA(cudaEventCreateWithFlags(&c->ev_poll[0], cudaEventDisableTiming));
@@ -584,6 +587,8 @@ int pe_reset_stats(pe_ctx* c) {
   pe_prof_flush(c);
   c->st.spmv_ms_p = c->st.spmv_ms_u = 0;
   c->st.spmv_timed_p = c->st.spmv_timed_u = 0;
+  c->st.pcg_ms_p = c->st.pcg_ms_u = 0;
+  c->st.pcg_iterations_p = c->st.pcg_iterations_u = 0;
   (void)k;
   PE_LEAVE(c)
 }

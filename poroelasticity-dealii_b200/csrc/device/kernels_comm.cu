@@ -181,6 +181,7 @@ void pe_comm_setup(pe_ctx* c, size_t n_work) {
   M.peer.assign(c->nranks, nullptr);
   M.peer[c->rank] = M.region;
   M.on = false;
+  M.d_peer.upload(M.peer, s);  // one rank: the persistent CG kernel posts to its own mailbox
   if (c->nranks > 1) {
     const char* env = std::getenv("PE_COMM");
     const bool want = !(env && std::strcmp(env, "nccl") == 0) && c->nranks <= PE_P2P_MAX_RANKS;

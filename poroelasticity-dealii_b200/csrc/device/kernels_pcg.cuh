@@ -1,0 +1,271 @@
+// kernels_pcg.cuh — persistent Jacobi-CG kernel; included inside the anonymous namespace of kernels_solver.cu
+// (it reuses warp_block_rows<LPR>, the peer-memory primitives and the launch constants defined there).
+//
+// Every iteration of dealii::SolverCG's loop (h = A d, alpha, g += alpha h, x += alpha d, check, z = D^-1 g, beta,
+// d = beta d - z; call sites PS:176-179, DS:300-305, SP:210-214) runs inside ONE cooperative launch.  One CTA set
+// stays resident (grid = SMs x occupancy); the three phases of an iteration are separated by on-device
+// synchronisation only:
+//   * the two dot-product reductions double as grid barriers: every CTA deposits its partial, the last one to
+//     arrive (atomic ticket) sums them in a fixed order and POSTS the total to the mailbox of every rank
+//     (peer memory over NVLink; with one rank the mailbox is local) — all CTAs of all ranks then read the same
+//     mailboxes and add them in rank order, so alpha, beta and the stopping decision are bitwise identical
+//     everywhere and no host or NCCL round trip exists inside the loop;
+//   * one explicit grid barrier after the direction update.
+// Halo: the CTAs first store the boundary entries of d straight into the neighbours' ghost segments, then
+// multiply the interior rows (which reference no ghost column), and only then wait for the neighbours' flags
+// before the boundary rows — communication and rank skew hide behind the interior SpMV.
+// Cross-phase visibility follows the PTX memory model: writers fence before they arrive at a barrier / post a
+// flag, readers fence after they observe it (the gpu-scope fence also drops stale L1 lines of this SM).
+
+struct PcgArgs {
+  const int32_t* rowptr;
+  const int32_t* col;
+  const double* val;
+  const double* invdiag;
+  double* x;
+  double* g;
+  double* h;
+  double* d;
+  double* z;
+  int64_t n, n_interior;
+  CgState* state;
+  double* gh;            // in: g.h of the start state; out: current value (for a follow-up launch)
+  double* partials;      // PE_RED_SLOTS * PE_MAX_RED_BLOCKS
+  unsigned* tickets;     // [0] reductions, [1] barrier, [2] halo
+  int* bar_flag;         // grid barrier epoch
+  int* abort;            // raised by any wait that times out
+  unsigned long long* timing;  // [0] ns in the SpMV(+dot) phase as seen by CTA 0, [1] number of phases
+  // peers
+  char* const* peer;
+  int nranks, me, red_epoch0;
+  // halo of d
+  int n_neigh, field, halo_epoch0;
+  const int32_t* neigh_rank;
+  int64_t n_send;
+  const int32_t* send_idx;
+  const int32_t* send_dest;
+  const int32_t* send_nb;
+  size_t ctrl_bytes, d_off;
+  int max_iterations;    // iterations to run in this launch at most
+};
+
+// Bounded wait used by every spin of the persistent kernel.  A timeout (a peer or CTA that never arrives) raises a
+// device-wide abort flag that all other waits poll, so the whole grid leaves its loops within one iteration.
+__device__ __forceinline__ bool pcg_wait(const int* flag, int epoch, int* abort) {
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while ((int)(pe_ld_flag(flag) - epoch) < 0) {
+    if ((++spins & 1023u) == 0) {
+      if (pe_ld_flag(abort)) return false;
+      if (clock64() - t0 > 20000000000LL) {
+        atomicExch(abort, 1);
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
+// sum over the CTA; valid in lane 0 of warp 0 (and every lane of warp 0)
+__device__ __forceinline__ double block_sum(double v, double* s_buf) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) s_buf[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (w == 0) {
+    t = lane < nw ? s_buf[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  return t;
+}
+
+// all CTAs: contribute NV partials; the last CTA posts the totals to every rank's mailbox under `epoch`
+template <int NV>
+__device__ __forceinline__ void pcg_reduce_post(const PcgArgs& a, double (&v)[NV], int slot0, int epoch, double* s_buf, bool* s_last) {
+  __threadfence();  // this thread's vector writes of the phase become visible before its CTA arrives
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double t = block_sum(v[k], s_buf);
+    if (threadIdx.x == 0) a.partials[(size_t)(slot0 + k) * PE_MAX_RED_BLOCKS + blockIdx.x] = t;
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    *s_last = (atomicAdd(&a.tickets[0], 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (*s_last) {
+    __threadfence();
+    double tot[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double p = 0.0;
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) p += ((volatile double*)a.partials)[(size_t)(slot0 + k) * PE_MAX_RED_BLOCKS + i];
+      tot[k] = block_sum(p, s_buf);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      a.tickets[0] = 0u;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) s_buf[k] = tot[k];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < a.nranks) {
+      P2PControl* ctl = reinterpret_cast<P2PControl*>(a.peer[threadIdx.x]);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) ctl->red_val[epoch & 1][a.me][slot0 + k] = s_buf[k];
+      __threadfence_system();
+      pe_st_flag(&ctl->red_flag[a.me], epoch);
+    }
+  }
+}
+
+// all CTAs: wait until every rank has posted `epoch`, return the rank-ordered sums of NV slots
+template <int NV>
+__device__ __forceinline__ bool pcg_fetch(const PcgArgs& a, int slot0, int epoch, double (&out)[NV], double* s_buf, int* s_ok) {
+  const P2PControl* mine = reinterpret_cast<const P2PControl*>(a.peer[a.me]);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    bool good = true;
+    if ((int)threadIdx.x < a.nranks) good = pcg_wait(&mine->red_flag[threadIdx.x], epoch, a.abort);
+    good = __all_sync(0xffffffffu, good);
+    __threadfence_system();
+    if ((int)threadIdx.x < NV) {
+      double sum = 0.0;
+      if (good)
+        for (int q = 0; q < a.nranks; ++q) sum += pe_ld_mail(&mine->red_val[epoch & 1][q][slot0 + threadIdx.x]);
+      s_buf[threadIdx.x] = sum;
+    }
+    if (threadIdx.x == 0) *s_ok = good ? 1 : 0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) out[k] = s_buf[k];
+  const bool ok = *s_ok != 0;
+  __threadfence();  // acquire: what the posting CTAs wrote before their fences is visible here
+  return ok;
+}
+
+__device__ __forceinline__ void pcg_grid_barrier(const PcgArgs& a, int epoch) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&a.tickets[1], 1u) == gridDim.x - 1) {
+      a.tickets[1] = 0u;
+      __threadfence();
+      pe_st_flag(a.bar_flag, epoch);
+    } else {
+      pcg_wait(a.bar_flag, epoch, a.abort);
+    }
+  }
+  __syncthreads();
+  __threadfence();
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(SPMV_T) k_pcg(PcgArgs a) {
+  __shared__ double s_buf[32];
+  __shared__ bool s_last;
+  __shared__ int s_ok;
+  CgState* st = a.state;
+  if (st->done) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsize = (int64_t)gridDim.x * blockDim.x;
+  const int64_t gwarp = (int64_t)blockIdx.x * (SPMV_T / 32) + warp, nwarps = (int64_t)gridDim.x * (SPMV_T / 32);
+  const int64_t nb_all = (a.n + 31) >> 5, nb_int = a.n_neigh ? (a.n_interior >> 5) : nb_all;
+  const int it0 = st->it;
+  const double tol = st->tol;
+  const int max_it = st->max_it;
+  double gh = *a.gh;
+  const P2PControl* my_ctl = reinterpret_cast<const P2PControl*>(a.peer[a.me]);
+  int bar_epoch = pe_ld_flag(a.bar_flag);  // the same value in every CTA: the flag only moves inside barriers
+  unsigned long long t_spmv = 0, n_spmv = 0;
+  __syncthreads();
+
+  for (int k = 1; k <= a.max_iterations; ++k) {
+    const int it = it0 + k;
+    const int e_dh = a.red_epoch0 + 2 * k - 1, e_upd = a.red_epoch0 + 2 * k;
+    unsigned long long t0 = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    // ---- halo of d: store my boundary entries into the neighbours' ghost segments, then publish
+    if (a.n_neigh) {
+      for (int64_t i = gtid; i < a.n_send; i += gsize) {
+        double* dst = reinterpret_cast<double*>(a.peer[a.neigh_rank[a.send_nb[i]]] + a.ctrl_bytes) + a.d_off;
+        dst[a.send_dest[i]] = a.d[a.send_idx[i]];
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) s_last = (atomicAdd(&a.tickets[2], 1u) == gridDim.x - 1);
+      __syncthreads();
+      if (s_last) {
+        __threadfence_system();
+        if ((int)threadIdx.x < a.n_neigh)
+          pe_st_flag(&reinterpret_cast<P2PControl*>(a.peer[a.neigh_rank[threadIdx.x]])->halo_flag[a.field][a.me], a.halo_epoch0 + k);
+        if (threadIdx.x == 0) a.tickets[2] = 0u;
+      }
+    }
+    // ---- h = A d on the interior rows, d.h
+    double acc1[1] = {0.0};
+    for (int64_t rb = gwarp; rb < nb_int; rb += nwarps) {
+      const double mine = warp_block_rows<LPR>(a.rowptr, a.col, a.val, a.d, a.n, rb, lane);
+      const int64_t row = (rb << 5) + lane;
+      if (row < a.n) { a.h[row] = mine; acc1[0] += mine * a.d[row]; }
+    }
+    bool ok = true;
+    if (a.n_neigh) {  // the boundary rows need the neighbours' values
+      if ((int)threadIdx.x < a.n_neigh) ok = pcg_wait(&my_ctl->halo_flag[a.field][a.neigh_rank[threadIdx.x]], a.halo_epoch0 + k, a.abort);
+      ok = __syncthreads_and(ok ? 1 : 0) != 0;
+      __threadfence_system();
+      for (int64_t rb = nb_int + gwarp; rb < nb_all; rb += nwarps) {
+        const double mine = warp_block_rows<LPR>(a.rowptr, a.col, a.val, a.d, a.n, rb, lane);
+        const int64_t row = (rb << 5) + lane;
+        if (row < a.n) { a.h[row] = mine; acc1[0] += mine * a.d[row]; }
+      }
+    }
+    pcg_reduce_post<1>(a, acc1, 0, e_dh, s_buf, &s_last);
+    // ---- alpha; g += alpha h; x += alpha d; z = D^-1 g; ||g||^2, g.z
+    double dh[1];
+    ok = pcg_fetch<1>(a, 0, e_dh, dh, s_buf, &s_ok) && ok;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      t_spmv += t1 - t0;
+      n_spmv += 1;
+    }
+    const double alpha = gh / dh[0];
+    double acc2[2] = {0.0, 0.0};
+    for (int64_t i = gtid; i < a.n; i += gsize) {
+      const double gi = a.g[i] + alpha * a.h[i];
+      a.g[i] = gi;
+      a.x[i] += alpha * a.d[i];
+      const double zi = gi * a.invdiag[i];
+      a.z[i] = zi;
+      acc2[0] += gi * gi;
+      acc2[1] += gi * zi;
+    }
+    pcg_reduce_post<2>(a, acc2, 1, e_upd, s_buf, &s_last);
+    // ---- SolverControl::check, beta, d = beta d - z
+    double rz[2];
+    ok = pcg_fetch<2>(a, 1, e_upd, rz, s_buf, &s_ok) && ok;
+    const double res = sqrt(rz[0]);
+    const bool converged = ok && res <= tol;
+    const bool failed = !ok || it >= max_it || isnan(res);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      st->it = it;
+      st->res = res;
+      if (!ok) st->pad = 1;
+      if (converged) st->done = 1; else if (failed) st->done = -1;
+    }
+    if (converged || failed) break;
+    const double beta = rz[1] / gh;
+    gh = rz[1];
+    for (int64_t i = gtid; i < a.n; i += gsize) a.d[i] = beta * a.d[i] - a.z[i];
+    pcg_grid_barrier(a, ++bar_epoch);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *a.gh = gh;
+    atomicAdd(&a.timing[0], t_spmv);
+    atomicAdd(&a.timing[1], n_spmv);
+  }
+}

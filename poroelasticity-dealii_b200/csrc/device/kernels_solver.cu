@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <deque>
+#include <string>
 #include <type_traits>
 
 #include "pe_internal.cuh"
@@ -215,6 +216,36 @@ __device__ __forceinline__ double row_dot(const int32_t* __restrict__ rowptr, co
   return row_sum<LPR>(col, val, x, start, end, sub);
 }
 
+// Sums of the 32 consecutive rows of row block `rb` (one warp): lane L returns (A x)[32 rb + L].
+template <int LPR>
+__device__ __forceinline__ double warp_block_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                  const double* __restrict__ val, const double* __restrict__ x, int64_t n, int64_t rb, int lane) {
+  constexpr int G = 32 / LPR;  // rows in flight per round
+  const int sub = lane % LPR, grp = lane / LPR;
+  const int64_t row = (rb << 5) + lane;
+  const int64_t rlo = row < n ? row : n, rhi = row + 1 < n ? row + 1 : n;
+  const int ptr_lo = rowptr[rlo], ptr_hi = rowptr[rhi];  // rows past the end are empty
+  double mine = 0.0;
+  for (int t = 0; t < LPR; t += 2) {  // two rounds (2*G rows) in flight
+    const int ra = t * G + grp, rb_ = (t + 1) * G + grp;
+    const int sa = __shfl_sync(0xffffffffu, ptr_lo, ra), ea = __shfl_sync(0xffffffffu, ptr_hi, ra);
+    const int sb = __shfl_sync(0xffffffffu, ptr_lo, rb_), eb = __shfl_sync(0xffffffffu, ptr_hi, rb_);
+    RowChunks<LPR> A, B;
+    A.issue_cols(col, sa, ea, sub);
+    B.issue_cols(col, sb, eb, sub);
+    A.issue_vals(val);
+    B.issue_vals(val);
+    __syncwarp();  // scheduling fence: keeps the 16 streaming loads above ahead of the first dependent gather
+    const double s_a = group_reduce<LPR>(A.finish(col, val, x));
+    const double s_b = group_reduce<LPR>(B.finish(col, val, x));
+    const double va = __shfl_sync(0xffffffffu, s_a, ((lane - t * G) & (G - 1)) * LPR);
+    const double vb = __shfl_sync(0xffffffffu, s_b, ((lane - (t + 1) * G) & (G - 1)) * LPR);
+    if (lane / G == t) mine = va;
+    if (lane / G == t + 1) mine = vb;
+  }
+  return mine;
+}
+
 // epilogue kinds of the fused SpMV
 enum { EPI_PLAIN = 0, EPI_DOT = 1, EPI_RESID = 2, EPI_CHEB = 3 };
 
@@ -257,32 +288,12 @@ __global__ void __launch_bounds__(SPMV_T) k_spmv(SpmvArgs a) {
     __threadfence_system();
     __syncthreads();
   }
-  constexpr int G = 32 / LPR;  // rows in flight per round
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, grp = lane / LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n_blocks = (a.n + 31) >> 5;
   double acc[1] = {0.0};
   for (int64_t rb = (a.row0 >> 5) + (int64_t)blockIdx.x * (SPMV_T / 32) + warp; rb < n_blocks; rb += (int64_t)gridDim.x * (SPMV_T / 32)) {
     const int64_t row = (rb << 5) + lane;
-    const int64_t rlo = row < a.n ? row : a.n, rhi = row + 1 < a.n ? row + 1 : a.n;
-    const int ptr_lo = a.rowptr[rlo], ptr_hi = a.rowptr[rhi];  // rows past the end are empty
-    double mine = 0.0;
-    for (int t = 0; t < LPR; t += 2) {  // two rounds (2*G rows) in flight
-      const int ra = t * G + grp, rb_ = (t + 1) * G + grp;
-      const int sa = __shfl_sync(0xffffffffu, ptr_lo, ra), ea = __shfl_sync(0xffffffffu, ptr_hi, ra);
-      const int sb = __shfl_sync(0xffffffffu, ptr_lo, rb_), eb = __shfl_sync(0xffffffffu, ptr_hi, rb_);
-      RowChunks<LPR> A, B;
-      A.issue_cols(a.col, sa, ea, sub);
-      B.issue_cols(a.col, sb, eb, sub);
-      A.issue_vals(a.val);
-      B.issue_vals(a.val);
-      __syncwarp();  // scheduling fence: keeps the 16 streaming loads above ahead of the first dependent gather
-      const double s_a = group_reduce<LPR>(A.finish(a.col, a.val, a.x));
-      const double s_b = group_reduce<LPR>(B.finish(a.col, a.val, a.x));
-      const double va = __shfl_sync(0xffffffffu, s_a, ((lane - t * G) & (G - 1)) * LPR);
-      const double vb = __shfl_sync(0xffffffffu, s_b, ((lane - (t + 1) * G) & (G - 1)) * LPR);
-      if (lane / G == t) mine = va;
-      if (lane / G == t + 1) mine = vb;
-    }
+    const double mine = warp_block_rows<LPR>(a.rowptr, a.col, a.val, a.x, a.n, rb, lane);
     if (row < a.n) {
       if (EPI == EPI_PLAIN) a.y[row] = mine;
       if (EPI == EPI_DOT) { a.y[row] = mine; acc[0] += mine * a.x[row]; }
@@ -571,6 +582,20 @@ void launch_spmv(pe_ctx* c, Field& F, SpmvArgs& a) {
     default: k_spmv<4, EPI><<<grid, SPMV_T, 0, c->stream>>>(a); break;
   }
   if (c->profiling && !c->prof_hold) pe_prof_end(c);
+  c->st.kernel_launches++;
+}
+
+#include "kernels_pcg.cuh"
+
+template <int LPR>
+void launch_pcg_t(pe_ctx* c, PcgArgs& a, int& grid_cache) {
+  if (grid_cache == 0) {
+    int per_sm = 0;
+    PE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<LPR>, SPMV_T, 0));
+    grid_cache = std::max(1, std::min(per_sm * c->sm_count, PE_MAX_RED_BLOCKS));
+  }
+  void* params[] = {&a};
+  PE_CUDA(cudaLaunchCooperativeKernel((const void*)k_pcg<LPR>, dim3(grid_cache), dim3(SPMV_T), params, 0, c->stream));
   c->st.kernel_launches++;
 }
 
@@ -870,6 +895,85 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
   }
 
   const int max_it = c->prm.cg_max_iterations;
+  static const bool pcg_disabled = std::getenv("PE_PCG") && std::string(std::getenv("PE_PCG")) == "0";
+  if (!cheb && !pcg_disabled && (!multi || fused)) {
+    // ---- the whole CG loop in one persistent cooperative launch (kernels_pcg.cuh)
+    P2PField& PF = c->p2p.f[fi];
+    PcgArgs pa{};
+    pa.rowptr = F.rowptr.p;
+    pa.col = F.col.p;
+    pa.val = val;
+    pa.invdiag = invdiag;
+    pa.x = x;
+    pa.g = g;
+    pa.h = h;
+    pa.d = d;
+    pa.z = z;
+    pa.n = n;
+    pa.n_interior = F.n_interior;
+    pa.state = st;
+    pa.gh = ghbuf;
+    pa.partials = c->red.partials.p;
+    pa.tickets = c->pcg_tickets.p;
+    pa.bar_flag = c->pcg_flags.p;
+    pa.abort = c->pcg_flags.p + 1;
+    pa.timing = c->pcg_timing.p;
+    pa.peer = c->p2p.d_peer.p;
+    pa.nranks = c->nranks;
+    pa.me = c->rank;
+    pa.red_epoch0 = (int)c->p2p.red_epoch;
+    pa.n_neigh = multi ? F.halo.n_neigh : 0;
+    pa.field = fi;
+    pa.halo_epoch0 = (int)PF.epoch;
+    pa.neigh_rank = PF.neigh_rank.p;
+    pa.n_send = multi ? F.halo.n_send() : 0;
+    pa.send_idx = F.halo.send_idx.p;
+    pa.send_dest = PF.send_dest.p;
+    pa.send_nb = PF.send_nb.p;
+    pa.ctrl_bytes = c->p2p.ctrl_bytes;
+    pa.d_off = (size_t)(d - reinterpret_cast<double*>(c->p2p.region + c->p2p.ctrl_bytes));
+    pa.max_iterations = max_it;
+    PE_CUDA(cudaMemsetAsync(c->pcg_timing.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    PE_CUDA(cudaMemsetAsync(c->pcg_flags.p + 1, 0, sizeof(int), c->stream));  // abort flag
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profiling) {
+      PE_CUDA(cudaEventCreate(&e0));
+      PE_CUDA(cudaEventCreate(&e1));
+      PE_CUDA(cudaEventRecord(e0, c->stream));
+    }
+    switch (lanes_per_row(F)) {
+      case 32: launch_pcg_t<32>(c, pa, c->pcg_grid[fi]); break;
+      case 16: launch_pcg_t<16>(c, pa, c->pcg_grid[fi]); break;
+      case 8: launch_pcg_t<8>(c, pa, c->pcg_grid[fi]); break;
+      default: launch_pcg_t<4>(c, pa, c->pcg_grid[fi]); break;
+    }
+    if (c->profiling) PE_CUDA(cudaEventRecord(e1, c->stream));
+    unsigned long long h_timing[2] = {0, 0};
+    PE_CUDA(cudaMemcpyAsync(&c->h_state[0], st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    PE_CUDA(cudaMemcpyAsync(h_timing, c->pcg_timing.p, sizeof h_timing, cudaMemcpyDeviceToHost, c->stream));
+    PE_CUDA(cudaStreamSynchronize(c->stream));
+    PE_CUDA(cudaGetLastError());
+    const CgState last = c->h_state[0];
+    const int its = last.it;
+    c->p2p.red_epoch += 2u * (unsigned)its;  // every rank executed the same number of posts
+    if (multi) PF.epoch += (unsigned)its;
+    *spmv_counter += its;
+    if (c->profiling) {
+      float ms = 0.f;
+      PE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      (fi ? c->st.pcg_ms_u : c->st.pcg_ms_p) += ms;
+      (fi ? c->st.pcg_iterations_u : c->st.pcg_iterations_p) += its;
+      (fi ? c->st.spmv_ms_u : c->st.spmv_ms_p) += (double)h_timing[0] * 1e-6;  // in-kernel %globaltimer, SpMV+dot phase of CTA 0
+      (fi ? c->st.spmv_timed_u : c->st.spmv_timed_p) += (int64_t)h_timing[1];
+    }
+    CgResult out;
+    out.its = its;
+    out.res = last.res;
+    out.status = last.done == 1 ? PE_OK : (last.pad ? PE_ERR_NCCL : (std::isnan(last.res) ? PE_ERR_NAN : PE_ERR_NO_CONVERGENCE));
+    return out;
+  }
   const int interval = c->prm.cg_check_interval > 0 ? c->prm.cg_check_interval : 8;
   int launched = 0;
   std::deque<int> inflight;  // pinned poll slots whose copy is enqueued but not yet consumed

@@ -203,6 +203,11 @@ struct pe_ctx {
   P2P p2p;
 
   Reducer red;
+  // persistent CG kernel scratch: tickets[3], flags {barrier epoch, abort}, timing {ns, count}
+  DBuf<unsigned> pcg_tickets;
+  DBuf<int> pcg_flags;
+  DBuf<unsigned long long> pcg_timing;
+  int pcg_grid[2] = {0, 0};  // cooperative grid size per field (0 = not queried yet)
   DBuf<CgState> cg_state;
   CgState* h_state = nullptr;  // pinned
   double* h_scalars = nullptr; // pinned, PE_RED_SLOTS
