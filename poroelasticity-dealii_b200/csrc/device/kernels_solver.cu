@@ -563,7 +563,8 @@ inline int spmv_grid(pe_ctx* c, int64_t n, int lpr) {
   (void)lpr;
   const int rpb = SPMV_T;  // 32 rows per warp, SPMV_T/32 warps
   int64_t want = (n + rpb - 1) / rpb;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min<int64_t>(PE_MAX_RED_BLOCKS, (int64_t)c->sm_count * 8)));
+  static const int mult = std::getenv("PE_SPMV_GRID_MULT") ? std::atoi(std::getenv("PE_SPMV_GRID_MULT")) : 8;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min<int64_t>(PE_MAX_RED_BLOCKS, (int64_t)c->sm_count * mult)));
 }
 
 template <int EPI>

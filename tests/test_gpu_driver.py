@@ -1,0 +1,39 @@
+"""The C++ driver executable (the main() the reference never shipped) on the reference's shipped input."""
+import re
+import subprocess
+
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+BIN = H.ROOT / "poroelasticity-dealii_b200" / "bin" / "fss-poroel"
+
+
+def test_fss_poroel_runs_the_shipped_case(tmp_path):
+    # input.data as shipped (2D, refine 4, Q2/Q1, dt 60, t_max 1e3 => 17 steps) + AMR off (out of scope)
+    text = H.SHIPPED_INPUT + "\nsubsection GPU\n  set Refine every = 0\n  set CG max iterations = 5000\nend\n"
+    f = tmp_path / "input.data"
+    f.write_text(text)
+    out = subprocess.run([str(BIN), str(f)], capture_output=True, text=True, timeout=300, cwd=tmp_path)
+    assert out.returncode == 0, out.stderr[-2000:]
+    s = out.stdout
+    assert "# Listing of Parameters" in s and "set Initial refinement level" in s   # prm.print_parameters (ID:82)
+    assert "starting time loop" in s and "time max 1000" in s                       # FSS:325-326
+    times = [float(x) for x in re.findall(r"^Time: (\S+)", s, flags=re.M)]
+    assert times == [60.0 * k for k in range(1, 18)]                                # while (time < t_max), FSS:327
+    assert len(re.findall(r"Coupling iteration: 1$", s, flags=re.M)) == 17          # one FSS iteration per step (FSS:399 off)
+    assert "Coupling iteration: 2" not in s
+    conv = [int(x) for x in re.findall(r"pressure converged; iterations: (\d+)", s)]
+    assert len(conv) == 17 and conv[0] == 5                                          # oracle: 6 residual evaluations in step 1
+    errs = [float(x) for x in re.findall(r"Error: (\S+)", s)]
+    assert len(errs) == 17 and all(e < 1e-8 for e in errs)
+
+
+def test_fss_poroel_reports_errors(tmp_path):
+    f = tmp_path / "bad.data"
+    f.write_text("subsection Mesh\n  set Dimensions = 7\nend\n")
+    out = subprocess.run([str(BIN), str(f)], capture_output=True, text=True, timeout=60, cwd=tmp_path)
+    assert out.returncode == 1 and "Exception on processing" in out.stderr and "does not match" in out.stderr
+    out = subprocess.run([str(BIN)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "specify the file name" in out.stdout              # PCL:7-10
