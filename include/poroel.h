@@ -107,6 +107,8 @@ typedef struct pe_stats {
   int64_t spmv_timed_p, spmv_timed_u;        /* number of matrix passes in those sums      */
   double  pcg_ms_p, pcg_ms_u;                /* CUDA-event time of the persistent CG kernel launches (profiling on) */
   int64_t pcg_iterations_p, pcg_iterations_u;/* CG iterations executed inside those launches */
+  int64_t bsr_block_size;                    /* block size of the block-CSR copy of the displacement matrix (0 = plain CSR);
+                                                spmv_bytes_u then counts 8 B per value + 4 B per BLOCK column index */
 } pe_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------- */

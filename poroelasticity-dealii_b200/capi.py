@@ -53,6 +53,7 @@ class PeStats(C.Structure):
         ("eig_max_p", C.c_double), ("eig_max_u", C.c_double), ("eig_max_m", C.c_double), ("setup_ms", C.c_double),
         ("spmv_ms_p", C.c_double), ("spmv_ms_u", C.c_double), ("spmv_timed_p", C.c_int64), ("spmv_timed_u", C.c_int64),
         ("pcg_ms_p", C.c_double), ("pcg_ms_u", C.c_double), ("pcg_iterations_p", C.c_int64), ("pcg_iterations_u", C.c_int64),
+        ("bsr_block_size", C.c_int64),
     ]
 
     def as_dict(self):

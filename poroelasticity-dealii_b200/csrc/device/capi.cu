@@ -1,7 +1,9 @@
 // capi.cu — extern "C" entry points of libporoel.so (include/poroel.h).
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 
 #include "pe_internal.cuh"
 
@@ -416,6 +418,18 @@ int pe_displacement_assemble(pe_ctx* c) {
   if (!c->matrix_u_built) {  // rebuild_system_matrix (DS:137, DS:280-290)
     pe_assemble_elasticity(c);
     pe_extract_invdiag(c, c->fu, c->A.p, c->invdiag_A.p);
+    {
+      const char* fmt = std::getenv("PE_FORMAT");
+      const bool want_bsr = !(fmt && std::string(fmt) == "csr");
+      if (want_bsr && pe_build_bsr(c, c->fu, c->A.p)) {
+        const Field::Bsr& S = c->fu.bsr;
+        c->st.spmv_bytes_u = (double)S.nnzb * (S.B * S.B * 8.0 + 4.0) + (double)S.n_brows * 4.0 + (double)c->fu.n_owned * 16.0;
+        c->st.bsr_block_size = S.B;
+      } else {
+        c->fu.bsr.B = 0;
+        c->st.bsr_block_size = 0;
+      }
+    }
     c->eig_A = 1.1 * pe_estimate_eig_max(c, c->fu, c->A.p, c->invdiag_A.p);
     c->st.eig_max_u = c->eig_A;
     c->matrix_u_built = true;

@@ -165,7 +165,67 @@ __global__ void first_ghost_row(int64_t n_owned, const int32_t* __restrict__ row
   if (rowptr[r + 1] > rowptr[r] && col[rowptr[r + 1] - 1] >= n_owned) atomicMin(first, (int)r);
 }
 
+// CSR -> block CSR, one warp per block row.  `bad` is raised when a row triple does not share one block pattern.
+template <int B>
+__global__ void csr_to_bsr(int64_t n_brows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+                           int32_t* __restrict__ bptr, int32_t* __restrict__ bcol, double* __restrict__ bval, int* __restrict__ bad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t I = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (I >= n_brows) return;
+  const int r0 = rowptr[I * B];
+  const int len = rowptr[I * B + 1] - r0;
+  if (len % B != 0 || r0 % (B * B) != 0) { if (lane == 0) atomicExch(bad, 1); return; }
+  const int nb = len / B, base = r0 / (B * B);
+  if (lane == 0) {
+    bptr[I] = base;
+    if (I == n_brows - 1) bptr[n_brows] = base + nb;
+  }
+  for (int j = lane; j < nb; j += 32) {
+    const int c0 = col[r0 + j * B];
+    if (c0 % B != 0) atomicExch(bad, 1);
+    if (bval == nullptr) continue;
+    bcol[base + j] = c0 / B;
+    for (int r = 0; r < B; ++r) {
+      const int rs = rowptr[I * B + r];
+      if (rowptr[I * B + r + 1] - rs != len) { atomicExch(bad, 1); continue; }
+      for (int cc = 0; cc < B; ++cc) {
+        if (col[rs + j * B + cc] != c0 + cc) atomicExch(bad, 1);
+        bval[(size_t)base * B * B + (size_t)(r * B + cc) * nb + j] = val[rs + j * B + cc];
+      }
+    }
+  }
+}
+
 }  // namespace
+
+bool pe_build_bsr(pe_ctx* c, Field& F, const double* csr_val) {
+  const int B = F.ncomp;
+  F.bsr.B = 0;
+  if (B < 2 || B > 3 || F.n_owned % B != 0 || F.n_local % B != 0 || F.nnz % (B * B) != 0) return false;
+  Field::Bsr& S = F.bsr;
+  S.n_brows = F.n_owned / B;
+  S.nnzb = F.nnz / (B * B);
+  S.bptr.alloc((size_t)S.n_brows + 1);
+  S.bcol.alloc((size_t)S.nnzb);
+  S.bval.alloc((size_t)F.nnz);
+  DBuf<int> bad;
+  bad.alloc_zero(1, c->stream);
+  const int warps = 8;
+  const int grid = pe_div_up(S.n_brows, warps);
+  if (B == 2) csr_to_bsr<2><<<grid, warps * 32, 0, c->stream>>>(S.n_brows, F.rowptr.p, F.col.p, csr_val, S.bptr.p, S.bcol.p, S.bval.p, bad.p);
+  else csr_to_bsr<3><<<grid, warps * 32, 0, c->stream>>>(S.n_brows, F.rowptr.p, F.col.p, csr_val, S.bptr.p, S.bcol.p, S.bval.p, bad.p);
+  int h_bad = 0;
+  PE_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  PE_CUDA(cudaStreamSynchronize(c->stream));
+  PE_CUDA(cudaGetLastError());
+  c->st.kernel_launches++;
+  if (h_bad) {
+    S.bptr.release(); S.bcol.release(); S.bval.release();
+    return false;
+  }
+  S.B = B;
+  return true;
+}
 
 int64_t pe_exclusive_scan_i32(pe_ctx* c, int32_t* data, int64_t n) {
   // scans data[0..n) in place and writes the total to data[n]

@@ -310,6 +310,133 @@ __global__ void __launch_bounds__(SPMV_T) k_spmv(SpmvArgs a) {
   if (EPI == EPI_DOT || EPI == EPI_RESID) grid_reduce<1>(acc, a.red, a.slot);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Block-CSR SpMV for the vector-valued (displacement) matrix: B x B blocks, one column index per block
+// (8 + 4/B^2 bytes per scalar nonzero instead of 12) and one B-wide gather of x per block instead of B^2
+// scalar gathers.  Same warp-blocked scheme as k_spmv: a warp owns 32 consecutive block rows, all 32 lanes
+// take one block each of the current block row (27 blocks for interior Q1 nodes in 3D), two block rows in
+// flight; values are stored component-major inside a block row so every one of the B^2 value loads of a
+// warp is a contiguous segment.
+struct BsrArgs {
+  const int32_t* bptr;
+  const int32_t* bcol;
+  const double* bval;
+  int64_t n_brows;
+};
+
+template <int B>
+struct BlockRow {
+  int c, nb, j;
+  bool p;
+  double v[B * B];
+  size_t vbase;
+  __device__ __forceinline__ void issue(const BsrArgs& m, int base, int nb_, int lane) {
+    nb = nb_;
+    j = lane;
+    p = j < nb;
+    vbase = (size_t)base * B * B;
+    c = 0;
+    if (p) c = ld_stream(m.bcol + base + j);
+  }
+  __device__ __forceinline__ void issue_vals(const BsrArgs& m) {
+#pragma unroll
+    for (int k = 0; k < B * B; ++k) {
+      v[k] = 0.0;
+      if (p) v[k] = ld_stream(m.bval + vbase + (size_t)k * nb + j);
+    }
+  }
+  // partial sums of the B rows of this block row over the blocks this lane owns
+  __device__ __forceinline__ void finish(const BsrArgs& m, const double* __restrict__ x, int base, double (&s)[B]) {
+    double xv[B];
+#pragma unroll
+    for (int cc = 0; cc < B; ++cc) {
+      xv[cc] = 0.0;
+      if (p) xv[cc] = ld_gather(x + (size_t)c * B + cc);
+    }
+#pragma unroll
+    for (int r = 0; r < B; ++r) {
+      double t = 0.0;
+#pragma unroll
+      for (int cc = 0; cc < B; ++cc) t += v[r * B + cc] * xv[cc];
+      s[r] = t;
+    }
+    for (int jj = j + 32; jj < nb; jj += 32) {  // block rows with more than 32 blocks (Q2, unstructured)
+      const int c2 = ld_stream(m.bcol + base + jj);
+      double x2[B];
+#pragma unroll
+      for (int cc = 0; cc < B; ++cc) x2[cc] = ld_gather(x + (size_t)c2 * B + cc);
+#pragma unroll
+      for (int r = 0; r < B; ++r)
+#pragma unroll
+        for (int cc = 0; cc < B; ++cc) s[r] += ld_stream(m.bval + vbase + (size_t)(r * B + cc) * nb + jj) * x2[cc];
+    }
+  }
+};
+
+template <int B, int EPI>
+__global__ void __launch_bounds__(SPMV_T) k_spmv_bsr(SpmvArgs a, BsrArgs m) {
+  if (a.state && a.state->done) return;
+  if (a.ctl) {
+    bool ok = true;
+    if ((int)threadIdx.x < a.n_neigh) ok = pe_wait_flag(&a.ctl->halo_flag[a.field][a.neigh_rank[threadIdx.x]], a.halo_epoch);
+    if (!ok && a.state) { CgState* st = const_cast<CgState*>(a.state); st->pad = 1; st->done = -1; }
+    __threadfence_system();
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n_wb = (m.n_brows + 31) >> 5;
+  double acc[1] = {0.0};
+  for (int64_t wb = (int64_t)blockIdx.x * (SPMV_T / 32) + warp; wb < n_wb; wb += (int64_t)gridDim.x * (SPMV_T / 32)) {
+    const int64_t brow = (wb << 5) + lane;
+    const int64_t blo = brow < m.n_brows ? brow : m.n_brows, bhi = brow + 1 < m.n_brows ? brow + 1 : m.n_brows;
+    const int ptr_lo = m.bptr[blo], ptr_hi = m.bptr[bhi];
+    double mine[B];
+#pragma unroll
+    for (int r = 0; r < B; ++r) mine[r] = 0.0;
+    for (int t = 0; t < 32; t += 2) {
+      const int sa = __shfl_sync(0xffffffffu, ptr_lo, t), ea = __shfl_sync(0xffffffffu, ptr_hi, t);
+      const int sb = __shfl_sync(0xffffffffu, ptr_lo, t + 1), eb = __shfl_sync(0xffffffffu, ptr_hi, t + 1);
+      BlockRow<B> RA, RB;
+      RA.issue(m, sa, ea - sa, lane);
+      RB.issue(m, sb, eb - sb, lane);
+      RA.issue_vals(m);
+      RB.issue_vals(m);
+      __syncwarp();  // scheduling fence, see k_spmv
+      double s_a[B], s_b[B];
+      RA.finish(m, a.x, sa, s_a);
+      RB.finish(m, a.x, sb, s_b);
+#pragma unroll
+      for (int r = 0; r < B; ++r) {
+        double va = s_a[r], vb = s_b[r];
+        for (int o = 16; o > 0; o >>= 1) {
+          va += __shfl_xor_sync(0xffffffffu, va, o);
+          vb += __shfl_xor_sync(0xffffffffu, vb, o);
+        }
+        if (lane == t) mine[r] = va;
+        if (lane == t + 1) mine[r] = vb;
+      }
+    }
+    if (brow < m.n_brows) {
+#pragma unroll
+      for (int r = 0; r < B; ++r) {
+        const int64_t row = brow * B + r;
+        if (EPI == EPI_PLAIN) a.y[row] = mine[r];
+        if (EPI == EPI_DOT) { a.y[row] = mine[r]; acc[0] += mine[r] * a.x[row]; }
+        if (EPI == EPI_RESID) { const double g = mine[r] - a.b[row]; a.y[row] = g; acc[0] += g * g; }
+        if (EPI == EPI_CHEB) {
+          const double rn = a.r[row] - mine[r];
+          a.r[row] = rn;
+          const double dn = a.c1 * a.x[row] + a.c2 * a.invdiag[row] * rn;
+          a.d_out[row] = dn;
+          a.z[row] += dn;
+        }
+      }
+    }
+  }
+  if (EPI == EPI_DOT || EPI == EPI_RESID) grid_reduce<1>(acc, a.red, a.slot);
+}
+
 // pressure residual (PS:113-155): r = -( M t1 + kappa K p + f ), ||r||^2 -> slot
 template <int LPR>
 __global__ void __launch_bounds__(SPMV_T)
@@ -576,6 +703,15 @@ void launch_spmv(pe_ctx* c, Field& F, SpmvArgs& a) {
   const int lpr = lanes_per_row(F);
   const int grid = spmv_grid(c, a.n - a.row0, lpr);
   if (c->profiling && !c->prof_hold) pe_prof_begin(c, &F == &c->fu ? 1 : 0);
+  if (F.bsr.B && a.val == c->A.p && a.row0 == 0 && a.n == F.n_owned) {  // the displacement matrix has a block-CSR copy
+    BsrArgs m{F.bsr.bptr.p, F.bsr.bcol.p, F.bsr.bval.p, F.bsr.n_brows};
+    const int bgrid = spmv_grid(c, F.bsr.n_brows, 32);
+    if (F.bsr.B == 3) k_spmv_bsr<3, EPI><<<bgrid, SPMV_T, 0, c->stream>>>(a, m);
+    else k_spmv_bsr<2, EPI><<<bgrid, SPMV_T, 0, c->stream>>>(a, m);
+    if (c->profiling && !c->prof_hold) pe_prof_end(c);
+    c->st.kernel_launches++;
+    return;
+  }
   switch (lpr) {
     case 32: k_spmv<32, EPI><<<grid, SPMV_T, 0, c->stream>>>(a); break;
     case 16: k_spmv<16, EPI><<<grid, SPMV_T, 0, c->stream>>>(a); break;
@@ -901,7 +1037,8 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
   // (<= ~0.25 ms: 8-GPU blocks of the 128^3 problem, all pressure solves) and loses ~5-10 % on multi-ms passes.
   static const bool pcg_disabled = std::getenv("PE_PCG") && std::string(std::getenv("PE_PCG")) == "0";
   static const long long pcg_max_nnz = std::getenv("PE_PCG_MAX_NNZ") ? std::atoll(std::getenv("PE_PCG_MAX_NNZ")) : 100000000LL;
-  if (!cheb && !pcg_disabled && (!multi || fused) && F.nnz <= pcg_max_nnz) {
+  const bool has_bsr = F.bsr.B && val == c->A.p;  // the persistent kernel is CSR-only
+  if (!cheb && !pcg_disabled && !has_bsr && (!multi || fused) && F.nnz <= pcg_max_nnz) {
     // ---- the whole CG loop in one persistent cooperative launch (kernels_pcg.cuh)
     P2PField& PF = c->p2p.f[fi];
     PcgArgs pa{};

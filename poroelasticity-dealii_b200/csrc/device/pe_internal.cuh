@@ -106,6 +106,15 @@ struct Field {
   int64_t nnz = 0;
   int64_t n_interior = 0;  // rows [0, n_interior) reference no ghost column (32-row aligned); == n_owned on one rank
   Halo halo;
+  // Block-CSR copy of the vector-valued matrix (dim x dim blocks: all components of two nodes couple, DS:143-145).
+  // bval is component-major inside a block row: value k of block j of block row I sits at 9*bptr[I] + k*nb_I + j,
+  // so the lanes of a warp (one block each) read consecutive addresses for every k.
+  struct Bsr {
+    int B = 0;             // block size (0 = not built)
+    int64_t n_brows = 0, nnzb = 0;
+    DBuf<int32_t> bptr, bcol;
+    DBuf<double> bval;
+  } bsr;
 };
 
 // device-resident scalar state of one CG solve
@@ -228,6 +237,7 @@ void pe_prof_flush(pe_ctx* c);
 
 // ---- kernels_pattern.cu
 void pe_build_pattern(pe_ctx* c, Field& F);
+bool pe_build_bsr(pe_ctx* c, Field& F, const double* csr_val);  // false when the matrix has no block structure
 int64_t pe_exclusive_scan_i32(pe_ctx* c, int32_t* data, int64_t n);  // in place, n+1 entries written (last = total)
 
 // ---- kernels_assembly.cu
