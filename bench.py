@@ -304,15 +304,25 @@ def main():
         achieved = stats["spmv_bytes_u"] / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
         spmv_ms_p = stats["spmv_ms_p"] / max(1, stats["spmv_timed_p"])
         value = args.steps / (ms_total * 1e-3)
+        bsr = int(stats["bsr_block_size"])
+        fmt = f"block-CSR {bsr}x{bsr}" if bsr else "CSR"
+        if stats["pcg_iterations_u"] > 0:
+            kernel_name = (f"k_pcg (persistent Jacobi-CG kernel; its SpMV+dot phase on the {fmt} displacement matrix, "
+                           "incl. the in-kernel halo send/wait and the grid/peer reduction that ends the phase)")
+            timing_source = "in-kernel %globaltimer of CTA 0 around every SpMV phase of the timed region (a persistent kernel has no per-pass launches to bracket with CUDA events)"
+        else:
+            kernel_name = (f"k_spmv_bsr<{bsr},*>" if bsr else "k_spmv<32,*>") + f" ({fmt} SpMV of the displacement matrix with fused d.h / residual / Chebyshev epilogues)"
+            timing_source = "CUDA events around every launch on the library's stream, inside the timed region"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args), "clocks": clocks, "gpu_launches": int(stats["kernel_launches"]),
             "e2e": e2e,
-            "roofline": {"bound": "hbm", "kernel": "k_spmv<32,*> (CSR SpMV of the displacement matrix, fused dot / Chebyshev epilogues)",
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "timing_source": timing_source,
                          "achieved": achieved, "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
-                         "traffic": None, "algorithmic_bytes_per_launch": stats["spmv_bytes_u"], "avg_launch_ms": spmv_ms,
+                         "traffic": None, "algorithmic_bytes_per_launch": stats["spmv_bytes_u"], "matrix_format": fmt, "avg_launch_ms": spmv_ms,
+                         "csr_equivalent_gbs": ((stats["nnz_u"] * 12.0 + stats["n_dofs_u"] * 20.0) / (spmv_ms * 1e-3) / 1e9) if spmv_ms > 0 else None,
                          "launches_timed": int(stats["spmv_timed_u"]),
                          "pressure_spmv": {"avg_launch_ms": spmv_ms_p, "achieved": (stats["spmv_bytes_p"] / (spmv_ms_p * 1e-3) / 1e9) if spmv_ms_p > 0 else None,
                                            "launches_timed": int(stats["spmv_timed_p"])},

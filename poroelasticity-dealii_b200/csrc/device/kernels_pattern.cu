@@ -299,7 +299,8 @@ void pe_build_pattern(pe_ctx* c, Field& F) {
     first_ghost_row<<<pe_div_up(F.n_owned, T), T, 0, c->stream>>>(F.n_owned, F.rowptr.p, F.col.p, first.p);
     PE_CUDA(cudaMemcpyAsync(&init, first.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     PE_CUDA(cudaStreamSynchronize(c->stream));
-    F.n_interior = (int64_t)(init / 32) * 32;  // whole 32-row warp blocks
+    const int unit = 32 * F.ncomp;  // whole warp blocks of 32 rows (CSR) and of 32 block rows (block CSR)
+    F.n_interior = (int64_t)(init / unit) * unit;
     c->st.kernel_launches++;
   }
 }

@@ -47,6 +47,7 @@ struct PcgArgs {
   const int32_t* send_nb;
   size_t ctrl_bytes, d_off;
   int max_iterations;    // iterations to run in this launch at most
+  BsrArgs bsr;           // block-CSR copy of the matrix (template parameter B > 0)
 };
 
 // Bounded wait used by every spin of the persistent kernel.  A timeout (a peer or CTA that never arrives) raises a
@@ -163,7 +164,8 @@ __device__ __forceinline__ void pcg_grid_barrier(const PcgArgs& a, int epoch) {
   __threadfence();
 }
 
-template <int LPR>
+// B == 0: CSR with LPR lanes per row; B > 0: block CSR with B x B blocks
+template <int LPR, int B>
 __global__ void __launch_bounds__(SPMV_T) k_pcg(PcgArgs a) {
   __shared__ double s_buf[32];
   __shared__ bool s_last;
@@ -173,7 +175,9 @@ __global__ void __launch_bounds__(SPMV_T) k_pcg(PcgArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsize = (int64_t)gridDim.x * blockDim.x;
   const int64_t gwarp = (int64_t)blockIdx.x * (SPMV_T / 32) + warp, nwarps = (int64_t)gridDim.x * (SPMV_T / 32);
-  const int64_t nb_all = (a.n + 31) >> 5, nb_int = a.n_neigh ? (a.n_interior >> 5) : nb_all;
+  constexpr int RB = B > 0 ? B : 1;  // scalar rows per (block) row
+  const int64_t n_rows = a.n / RB;   // rows (CSR) or block rows (BSR)
+  const int64_t nb_all = (n_rows + 31) >> 5, nb_int = a.n_neigh ? ((a.n_interior / RB) >> 5) : nb_all;
   const int it0 = st->it;
   const double tol = st->tol;
   const int max_it = st->max_it;
@@ -207,21 +211,30 @@ __global__ void __launch_bounds__(SPMV_T) k_pcg(PcgArgs a) {
     }
     // ---- h = A d on the interior rows, d.h
     double acc1[1] = {0.0};
-    for (int64_t rb = gwarp; rb < nb_int; rb += nwarps) {
-      const double mine = warp_block_rows<LPR>(a.rowptr, a.col, a.val, a.d, a.n, rb, lane);
-      const int64_t row = (rb << 5) + lane;
-      if (row < a.n) { a.h[row] = mine; acc1[0] += mine * a.d[row]; }
-    }
+    auto multiply_blocks = [&](int64_t first, int64_t last) {
+      for (int64_t rb = first + gwarp; rb < last; rb += nwarps) {
+        if constexpr (B == 0) {
+          const double mine = warp_block_rows<LPR>(a.rowptr, a.col, a.val, a.d, a.n, rb, lane);
+          const int64_t row = (rb << 5) + lane;
+          if (row < a.n) { a.h[row] = mine; acc1[0] += mine * a.d[row]; }
+        } else {
+          double mine[RB];
+          warp_block_brows<RB>(a.bsr, a.d, rb, lane, mine);
+          const int64_t brow = (rb << 5) + lane;
+          if (brow < n_rows) {
+#pragma unroll
+            for (int r = 0; r < RB; ++r) { a.h[brow * RB + r] = mine[r]; acc1[0] += mine[r] * a.d[brow * RB + r]; }
+          }
+        }
+      }
+    };
+    multiply_blocks(0, nb_int);
     bool ok = true;
     if (a.n_neigh) {  // the boundary rows need the neighbours' values
       if ((int)threadIdx.x < a.n_neigh) ok = pcg_wait(&my_ctl->halo_flag[a.field][a.neigh_rank[threadIdx.x]], a.halo_epoch0 + k, a.abort);
       ok = __syncthreads_and(ok ? 1 : 0) != 0;
       __threadfence_system();
-      for (int64_t rb = nb_int + gwarp; rb < nb_all; rb += nwarps) {
-        const double mine = warp_block_rows<LPR>(a.rowptr, a.col, a.val, a.d, a.n, rb, lane);
-        const int64_t row = (rb << 5) + lane;
-        if (row < a.n) { a.h[row] = mine; acc1[0] += mine * a.d[row]; }
-      }
+      multiply_blocks(nb_int, nb_all);
     }
     pcg_reduce_post<1>(a, acc1, 0, e_dh, s_buf, &s_last);
     // ---- alpha; g += alpha h; x += alpha d; z = D^-1 g; ||g||^2, g.z

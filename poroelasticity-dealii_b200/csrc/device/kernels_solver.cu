@@ -374,6 +374,39 @@ struct BlockRow {
   }
 };
 
+// Sums of the 32 consecutive block rows of warp block `wb`: lane L returns the B row sums of block row 32 wb + L.
+template <int B>
+__device__ __forceinline__ void warp_block_brows(const BsrArgs& m, const double* __restrict__ x, int64_t wb, int lane, double (&mine)[B]) {
+  const int64_t brow = (wb << 5) + lane;
+  const int64_t blo = brow < m.n_brows ? brow : m.n_brows, bhi = brow + 1 < m.n_brows ? brow + 1 : m.n_brows;
+  const int ptr_lo = m.bptr[blo], ptr_hi = m.bptr[bhi];
+#pragma unroll
+  for (int r = 0; r < B; ++r) mine[r] = 0.0;
+  for (int t = 0; t < 32; t += 2) {
+    const int sa = __shfl_sync(0xffffffffu, ptr_lo, t), ea = __shfl_sync(0xffffffffu, ptr_hi, t);
+    const int sb = __shfl_sync(0xffffffffu, ptr_lo, t + 1), eb = __shfl_sync(0xffffffffu, ptr_hi, t + 1);
+    BlockRow<B> RA, RB;
+    RA.issue(m, sa, ea - sa, lane);
+    RB.issue(m, sb, eb - sb, lane);
+    RA.issue_vals(m);
+    RB.issue_vals(m);
+    __syncwarp();  // scheduling fence, see k_spmv
+    double s_a[B], s_b[B];
+    RA.finish(m, x, sa, s_a);
+    RB.finish(m, x, sb, s_b);
+#pragma unroll
+    for (int r = 0; r < B; ++r) {
+      double va = s_a[r], vb = s_b[r];
+      for (int o = 16; o > 0; o >>= 1) {
+        va += __shfl_xor_sync(0xffffffffu, va, o);
+        vb += __shfl_xor_sync(0xffffffffu, vb, o);
+      }
+      if (lane == t) mine[r] = va;
+      if (lane == t + 1) mine[r] = vb;
+    }
+  }
+}
+
 template <int B, int EPI>
 __global__ void __launch_bounds__(SPMV_T) k_spmv_bsr(SpmvArgs a, BsrArgs m) {
   if (a.state && a.state->done) return;
@@ -389,34 +422,8 @@ __global__ void __launch_bounds__(SPMV_T) k_spmv_bsr(SpmvArgs a, BsrArgs m) {
   double acc[1] = {0.0};
   for (int64_t wb = (int64_t)blockIdx.x * (SPMV_T / 32) + warp; wb < n_wb; wb += (int64_t)gridDim.x * (SPMV_T / 32)) {
     const int64_t brow = (wb << 5) + lane;
-    const int64_t blo = brow < m.n_brows ? brow : m.n_brows, bhi = brow + 1 < m.n_brows ? brow + 1 : m.n_brows;
-    const int ptr_lo = m.bptr[blo], ptr_hi = m.bptr[bhi];
     double mine[B];
-#pragma unroll
-    for (int r = 0; r < B; ++r) mine[r] = 0.0;
-    for (int t = 0; t < 32; t += 2) {
-      const int sa = __shfl_sync(0xffffffffu, ptr_lo, t), ea = __shfl_sync(0xffffffffu, ptr_hi, t);
-      const int sb = __shfl_sync(0xffffffffu, ptr_lo, t + 1), eb = __shfl_sync(0xffffffffu, ptr_hi, t + 1);
-      BlockRow<B> RA, RB;
-      RA.issue(m, sa, ea - sa, lane);
-      RB.issue(m, sb, eb - sb, lane);
-      RA.issue_vals(m);
-      RB.issue_vals(m);
-      __syncwarp();  // scheduling fence, see k_spmv
-      double s_a[B], s_b[B];
-      RA.finish(m, a.x, sa, s_a);
-      RB.finish(m, a.x, sb, s_b);
-#pragma unroll
-      for (int r = 0; r < B; ++r) {
-        double va = s_a[r], vb = s_b[r];
-        for (int o = 16; o > 0; o >>= 1) {
-          va += __shfl_xor_sync(0xffffffffu, va, o);
-          vb += __shfl_xor_sync(0xffffffffu, vb, o);
-        }
-        if (lane == t) mine[r] = va;
-        if (lane == t + 1) mine[r] = vb;
-      }
-    }
+    warp_block_brows<B>(m, a.x, wb, lane, mine);
     if (brow < m.n_brows) {
 #pragma unroll
       for (int r = 0; r < B; ++r) {
@@ -724,15 +731,15 @@ void launch_spmv(pe_ctx* c, Field& F, SpmvArgs& a) {
 
 #include "kernels_pcg.cuh"
 
-template <int LPR>
+template <int LPR, int B>
 void launch_pcg_t(pe_ctx* c, PcgArgs& a, int& grid_cache) {
   if (grid_cache == 0) {
     int per_sm = 0;
-    PE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<LPR>, SPMV_T, 0));
+    PE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<LPR, B>, SPMV_T, 0));
     grid_cache = std::max(1, std::min(per_sm * c->sm_count, PE_MAX_RED_BLOCKS));
   }
   void* params[] = {&a};
-  PE_CUDA(cudaLaunchCooperativeKernel((const void*)k_pcg<LPR>, dim3(grid_cache), dim3(SPMV_T), params, 0, c->stream));
+  PE_CUDA(cudaLaunchCooperativeKernel((const void*)k_pcg<LPR, B>, dim3(grid_cache), dim3(SPMV_T), params, 0, c->stream));
   c->st.kernel_launches++;
 }
 
@@ -1037,8 +1044,8 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
   // (<= ~0.25 ms: 8-GPU blocks of the 128^3 problem, all pressure solves) and loses ~5-10 % on multi-ms passes.
   static const bool pcg_disabled = std::getenv("PE_PCG") && std::string(std::getenv("PE_PCG")) == "0";
   static const long long pcg_max_nnz = std::getenv("PE_PCG_MAX_NNZ") ? std::atoll(std::getenv("PE_PCG_MAX_NNZ")) : 100000000LL;
-  const bool has_bsr = F.bsr.B && val == c->A.p;  // the persistent kernel is CSR-only
-  if (!cheb && !pcg_disabled && !has_bsr && (!multi || fused) && F.nnz <= pcg_max_nnz) {
+  const bool has_bsr = F.bsr.B && val == c->A.p;
+  if (!cheb && !pcg_disabled && (!multi || fused) && F.nnz <= pcg_max_nnz) {
     // ---- the whole CG loop in one persistent cooperative launch (kernels_pcg.cuh)
     P2PField& PF = c->p2p.f[fi];
     PcgArgs pa{};
@@ -1083,11 +1090,17 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
       PE_CUDA(cudaEventCreate(&e1));
       PE_CUDA(cudaEventRecord(e0, c->stream));
     }
-    switch (lanes_per_row(F)) {
-      case 32: launch_pcg_t<32>(c, pa, c->pcg_grid[fi]); break;
-      case 16: launch_pcg_t<16>(c, pa, c->pcg_grid[fi]); break;
-      case 8: launch_pcg_t<8>(c, pa, c->pcg_grid[fi]); break;
-      default: launch_pcg_t<4>(c, pa, c->pcg_grid[fi]); break;
+    if (has_bsr) {
+      pa.bsr = BsrArgs{F.bsr.bptr.p, F.bsr.bcol.p, F.bsr.bval.p, F.bsr.n_brows};
+      if (F.bsr.B == 3) launch_pcg_t<32, 3>(c, pa, c->pcg_grid[fi]);
+      else launch_pcg_t<32, 2>(c, pa, c->pcg_grid[fi]);
+    } else {
+      switch (lanes_per_row(F)) {
+        case 32: launch_pcg_t<32, 0>(c, pa, c->pcg_grid[fi]); break;
+        case 16: launch_pcg_t<16, 0>(c, pa, c->pcg_grid[fi]); break;
+        case 8: launch_pcg_t<8, 0>(c, pa, c->pcg_grid[fi]); break;
+        default: launch_pcg_t<4, 0>(c, pa, c->pcg_grid[fi]); break;
+      }
     }
     if (c->profiling) PE_CUDA(cudaEventRecord(e1, c->stream));
     unsigned long long h_timing[2] = {0, 0};
