@@ -44,15 +44,18 @@ def input_text(refine, precond, cheb_degree, eig_ratio, max_its, cells=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md).  nvidia-smi needs
+    about a second to deliver its first line, so the sampler is started before the warm-up steps and only the samples
+    that arrive inside [mark_begin, mark_end] are reported (all samples under load if the window is shorter than
+    the sampling period)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.proc, self.t0, self.t1 = device, [], None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.device)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -61,20 +64,32 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
+        window = "timed region"
+        if len(inside) < 2:  # timed region shorter than the sampling period: fall back to the whole loaded interval
+            inside = [r for t, r in self.rows if self.t0 is None or t >= self.t0 - 5.0]
+            window = "warm-up + timed region (timed region shorter than two sampling periods)"
+        num = lambda x: x.replace(".", "", 1).isdigit()
+        sm = [float(r[0]) for r in inside if r and num(r[0])]
+        mx = [float(r[1]) for r in inside if len(r) > 1 and num(r[1])]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = sorted({names[i] for r in inside if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        pw = [float(r[2]) for r in inside if len(r) > 2 and num(r[2])]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window}
 
 
 def cpu_sample(refine, threads, golden, cg_sample_its=(2, 5, 5)):
@@ -234,6 +249,8 @@ def main():
     lib = be.lib
     stream = torch.cuda.ExternalStream(lib.pe_stream(be.ctx), device=torch.device("cuda", local))
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         prob.step()
     f64 = C.POINTER(C.c_double)
@@ -260,13 +277,13 @@ def main():
     be.reset_stats()
     lib.pe_set_profiling(be.ctx, 1)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     reports = [prob.step() for _ in range(args.steps)]
     e1.record(stream)
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
     if world > 1:
