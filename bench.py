@@ -321,6 +321,11 @@ def main():
         achieved = stats["spmv_bytes_u"] / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
         spmv_ms_p = stats["spmv_ms_p"] / max(1, stats["spmv_timed_p"])
         value = args.steps / (ms_total * 1e-3)
+        traffic = None
+        tr = ROOT / "profiles" / "traffic_r1.json"
+        if tr.exists() and world == 1 and args.refine == 7:
+            key = "k_spmv_bsr<3> C4 (128^3 cells, 1 GPU)" if stats["bsr_block_size"] == 3 else "k_spmv<32> C4 (CSR, PE_FORMAT=csr)"
+            traffic = json.loads(tr.read_text()).get(key, {}).get("traffic")
         bsr = int(stats["bsr_block_size"])
         fmt = f"block-CSR {bsr}x{bsr}" if bsr else "CSR"
         if stats["pcg_iterations_u"] > 0:
@@ -338,7 +343,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": kernel_name, "timing_source": timing_source,
                          "achieved": achieved, "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
-                         "traffic": None, "algorithmic_bytes_per_launch": stats["spmv_bytes_u"], "matrix_format": fmt, "avg_launch_ms": spmv_ms,
+                         "traffic": traffic, "traffic_source": "profiles/traffic_r1.json (ncu --set full capture of this kernel on this workload)" if traffic else None,
+                         "algorithmic_bytes_per_launch": stats["spmv_bytes_u"], "matrix_format": fmt, "avg_launch_ms": spmv_ms,
                          "csr_equivalent_gbs": ((stats["nnz_u"] * 12.0 + stats["n_dofs_u"] * 20.0) / (spmv_ms * 1e-3) / 1e9) if spmv_ms > 0 else None,
                          "launches_timed": int(stats["spmv_timed_u"]),
                          "pressure_spmv": {"avg_launch_ms": spmv_ms_p, "achieved": (stats["spmv_bytes_p"] / (spmv_ms_p * 1e-3) / 1e9) if spmv_ms_p > 0 else None,
