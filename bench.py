@@ -36,11 +36,20 @@ METRIC = "fixed_stress_time_steps_per_second"
 UNIT = "steps/s"
 
 
-def input_text(refine, precond, cheb_degree, eig_ratio, max_its, cells=None):
+def input_text(refine, precond, cheb_degree, eig_ratio, max_its, cells=None, size=None):
     import helpers as H
     extra = (f"  set Preconditioner = {precond}\n  set Chebyshev degree = {cheb_degree}\n"
              f"  set Chebyshev eigenvalue ratio = {eig_ratio}\n  set CG max iterations = {max_its}\n")
-    return H.make_input(dim=3, refine=refine, degree_u=1, extra_gpu=extra, cells=cells)
+    text = H.make_input(dim=3, refine=refine, degree_u=1, extra_gpu=extra, cells=cells)
+    if size:
+        text = text.replace("set Domain size              = 10, 10, 10", "set Domain size              = " + ", ".join(str(x) for x in size))
+    return text
+
+
+def weak_cells(n_gpus, per_axis=143):
+    """BASELINE config 5: one 143^3-cell block (~12 M DoFs) per GPU, stacked along z so that the contiguous cell
+    ranges of the lexicographic partition are exactly the blocks."""
+    return [per_axis, per_axis, per_axis * n_gpus], [10, 10, 10 * n_gpus]
 
 
 class ClockSampler:
@@ -191,6 +200,13 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args):
+    if args.workload == "c5":
+        cells, size = weak_cells(args.gpus)
+        nn = (cells[0] + 1) * (cells[1] + 1) * (cells[2] + 1)
+        return {"workload": f"3D weak scaling: one 143^3-cell block per GPU stacked along z ({cells[0]}x{cells[1]}x{cells[2]} cells, {3 * nn} u + {nn} p DoFs), "
+                            "Q1/Q1, shipped input.data properties; BASELINE.json configs[4]", "parallelism": f"z-slabs x{args.gpus}",
+                "l2_policy": "inputs larger than L2, no flush", "preconditioner": "chebyshev-jacobi" if args.precond == 1 else "jacobi",
+                "chebyshev_degree": args.cheb_degree, "cg_max_iterations": args.max_its}
     n = 2 ** args.refine
     return {"workload": f"3D unit-cube hex mesh, Q1 displacement / Q1 pressure, refine {args.refine} ({n}^3 cells, {3 * (n + 1) ** 3} u + {(n + 1) ** 3} p DoFs), "
                         "shipped input.data properties, dt=60, rollers on all faces, well source; BASELINE.json configs[3]",
@@ -210,6 +226,7 @@ def main():
     ap.add_argument("--cheb-degree", type=int, default=4)
     ap.add_argument("--eig-ratio", type=float, default=30.0)
     ap.add_argument("--max-its", type=int, default=4000)
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"], help="c4: 128^3 strong scaling (headline); c5: 143^3 cells per GPU, weak scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -240,7 +257,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    inp = capi.InputData(text=input_text(args.refine, args.precond, args.cheb_degree, args.eig_ratio, args.max_its))
+    cells, size = weak_cells(world) if args.workload == "c5" else (None, None)
+    inp = capi.InputData(text=input_text(args.refine, args.precond, args.cheb_degree, args.eig_ratio, args.max_its, cells=cells, size=size))
     prob = capi.Problem(inp, device=local, rank=rank, nranks=world, nccl_id=nccl_id)
     t0 = time.perf_counter()
     prob.initialize(verbose=False)
@@ -323,7 +341,7 @@ def main():
         value = args.steps / (ms_total * 1e-3)
         traffic = None
         tr = ROOT / "profiles" / "traffic_r1.json"
-        if tr.exists() and world == 1 and args.refine == 7:
+        if tr.exists() and world == 1 and args.refine == 7 and args.workload == "c4":
             key = "k_spmv_bsr<3> C4 (128^3 cells, 1 GPU)" if stats["bsr_block_size"] == 3 else "k_spmv<32> C4 (CSR, PE_FORMAT=csr)"
             traffic = json.loads(tr.read_text()).get(key, {}).get("traffic")
         bsr = int(stats["bsr_block_size"])
@@ -337,7 +355,7 @@ def main():
             timing_source = "CUDA events around every launch on the library's stream, inside the timed region"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload == "c5" else "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args), "clocks": clocks, "gpu_launches": int(stats["kernel_launches"]),
             "e2e": e2e,
             "roofline": {"bound": "hbm", "kernel": kernel_name, "timing_source": timing_source,
@@ -359,7 +377,7 @@ def main():
                                     "matrix_passes_u": stats["spmv_launches_u"] / args.steps, "matrix_passes_p": stats["spmv_launches_p"] / args.steps},
             "init_s": t_init, "setup_ms": stats["setup_ms"],
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "c4":
             try:
                 g = golden_counts(args.refine)
                 v, thr, detail = cpu_sample(args.refine, 0, g)

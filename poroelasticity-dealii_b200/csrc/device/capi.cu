@@ -593,7 +593,6 @@ int pe_get_stats(pe_ctx* c, pe_stats* s) {
 }
 int pe_reset_stats(pe_ctx* c) {
   PE_ENTER(c)
-  pe_stats k = c->st;
   c->st.cg_iterations_pressure = c->st.cg_iterations_displacement = c->st.cg_iterations_projection = 0;
   c->st.cg_solves_pressure = c->st.cg_solves_displacement = c->st.cg_solves_projection = 0;
   c->st.spmv_launches_p = c->st.spmv_launches_u = 0;
@@ -603,7 +602,6 @@ int pe_reset_stats(pe_ctx* c) {
   c->st.spmv_timed_p = c->st.spmv_timed_u = 0;
   c->st.pcg_ms_p = c->st.pcg_ms_u = 0;
   c->st.pcg_iterations_p = c->st.pcg_iterations_u = 0;
-  (void)k;
   PE_LEAVE(c)
 }
 int pe_synchronize(pe_ctx* c) {

@@ -198,24 +198,6 @@ __device__ __forceinline__ double group_reduce(double s) {
   return s;
 }
 
-template <int LPR>
-__device__ __forceinline__ double row_sum(const int32_t* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
-                                          int start, int end, int sub) {
-  RowChunks<LPR> R;
-  R.issue_cols(col, start, end, sub);
-  R.issue_vals(val);
-  return group_reduce<LPR>(R.finish(col, val, x));
-}
-
-// row pointer pair of the old one-row-per-group kernels
-template <int LPR>
-__device__ __forceinline__ double row_dot(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
-                                          const double* __restrict__ x, int64_t row, int sub, bool valid) {
-  int start = 0, end = 0;
-  if (valid) { start = rowptr[row]; end = rowptr[row + 1]; }
-  return row_sum<LPR>(col, val, x, start, end, sub);
-}
-
 // Sums of the 32 consecutive rows of row block `rb` (one warp): lane L returns (A x)[32 rb + L].
 template <int LPR>
 __device__ __forceinline__ double warp_block_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -1177,7 +1159,7 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
     PE_CUDA(cudaEventSynchronize(c->ev_poll[s]));
     last = c->h_state[s];
     if (last.done != 0) break;
-    if (launched >= max_it && inflight.empty()) break;  // unreachable: k_cg_check flags failure at max_it
+    if (launched >= max_it && inflight.empty()) break;  // unreachable: the folded check flags failure at max_it
   }
   while (!inflight.empty()) {
     PE_CUDA(cudaEventSynchronize(c->ev_poll[inflight.front()]));

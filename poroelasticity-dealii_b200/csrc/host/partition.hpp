@@ -60,9 +60,8 @@ inline std::vector<int32_t> dof_owner(const mesh::Mesh& m, const dofs::DofMap& d
 }
 
 inline void build_field(const mesh::Mesh& m, const dofs::DofMap& d, const std::vector<int32_t>& owner,
-                        const std::vector<std::vector<int>>& cell_ranks_of_local, const std::vector<int64_t>& local_cells,
-                        const std::vector<uint8_t>& cell_has_rank_mask_unused, int rank, FieldPart& F) {
-  (void)cell_has_rank_mask_unused;
+                        const std::vector<std::vector<int>>& cell_ranks_of_local, const std::vector<int64_t>& local_cells, int rank,
+                        FieldPart& F) {
   (void)m;
   // local dofs
   std::vector<int32_t> owned, ghost;
@@ -180,9 +179,8 @@ inline Part make_part(const mesh::Mesh& m, const dofs::DofMap& dp, const dofs::D
       P.mesh.bface_local.push_back(m.bface_local[b]);
       P.mesh.bface_id.push_back(m.bface_id[b]);
     }
-  std::vector<uint8_t> unused;
-  build_field(m, dp, own_p, cell_ranks, local_cells, unused, rank, P.field[0]);
-  build_field(m, du, own_u, cell_ranks, local_cells, unused, rank, P.field[1]);
+  build_field(m, dp, own_p, cell_ranks, local_cells, rank, P.field[0]);
+  build_field(m, du, own_u, cell_ranks, local_cells, rank, P.field[1]);
   return P;
 }
 
