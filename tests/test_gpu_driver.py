@@ -37,3 +37,28 @@ def test_fss_poroel_reports_errors(tmp_path):
     assert out.returncode == 1 and "Exception on processing" in out.stderr and "does not match" in out.stderr
     out = subprocess.run([str(BIN)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 1 and "specify the file name" in out.stdout              # PCL:7-10
+
+
+def test_fss_poroel_writes_vtk(tmp_path):
+    """the minimal legacy-VTK writer behind `Write VTK = 1` (FSS:227-291 writes ./solution/solution-NNNN.vtk)."""
+    text = H.make_input(dim=3, refine=2, degree_u=1, extra_gpu="  set Refine every = 0\n  set Write VTK = 1\n  set Max time steps = 2\n")
+    f = tmp_path / "input.data"
+    f.write_text(text)
+    (tmp_path / "solution").mkdir()
+    out = subprocess.run([str(BIN), str(f)], capture_output=True, text=True, timeout=300, cwd=tmp_path)
+    assert out.returncode == 0, out.stderr[-2000:]
+    files = sorted((tmp_path / "solution").glob("solution-*.vtk"))
+    assert [p.name for p in files] == ["solution-0001.vtk", "solution-0002.vtk"]
+    body = files[-1].read_text()
+    assert "DATASET UNSTRUCTURED_GRID" in body and "POINTS 125 double" in body and "CELLS 64 576" in body
+    for name in ("VECTORS u double", "SCALARS p double 1", "SCALARS eps_xx double 1", "SCALARS sigma_zz double 1"):
+        assert name in body
+
+
+def test_fss_poroel_default_iteration_cap(tmp_path):
+    """The shipped case also runs with the reference's own 1000-iteration CG cap (PS:175, DS:299)."""
+    f = tmp_path / "input.data"
+    f.write_text(H.SHIPPED_INPUT + "\nsubsection GPU\n  set Refine every = 0\n  set Max time steps = 3\nend\n")
+    out = subprocess.run([str(BIN), str(f)], capture_output=True, text=True, timeout=300, cwd=tmp_path)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("Coupling iteration: 1") == 3
