@@ -304,3 +304,43 @@ def test_effective_stresses_match_oracle(dim):
         assert np.allclose(dev.get_vector(capi.VEC_STRESS0 + 0), prm.lame_lambda * tr + 2 * prm.shear_modulus * eps[0], rtol=1e-13, atol=0)
     finally:
         dev.close(); ora.close()
+
+
+@pytest.mark.parametrize("dim,deg,cells", [(2, 1, [1, 1]), (2, 2, [1, 1]), (3, 1, [1, 1, 1]), (3, 1, [2, 1, 3]), (3, 2, [1, 2, 1]), (2, 1, [33, 1])])
+def test_degenerate_meshes(dim, deg, cells):
+    """Edge cases: a single cell (every node on the boundary), one-cell-thick strips, row counts below / just above one
+    32-row warp block.  Same parity bars as everywhere else."""
+    inp, mesh, dev, ora = both(H.make_input(dim=dim, refine=2, degree_u=deg, cells=cells))
+    try:
+        fss.initialize(dev, inp); fss.initialize(ora, inp)
+        for which in (capi.MAT_MASS, capi.MAT_LAPLACE, capi.MAT_ELASTICITY):
+            assert max_rel(dev.get_matrix(which), ora.get_matrix(which)) <= MATRIX_TOL
+        for _ in range(2):
+            r_d, r_o = fss.time_step(dev, inp), fss.time_step(ora, inp)
+            assert r_d["inner_counts"] == r_o["inner_counts"]
+            assert fss.rel_l2(dev.get_vector(capi.VEC_P), ora.get_vector(capi.VEC_P)) <= FIELD_TOL
+            assert fss.rel_l2(dev.get_vector(capi.VEC_U), ora.get_vector(capi.VEC_U)) <= FIELD_TOL
+    finally:
+        dev.close(); ora.close()
+
+
+@pytest.mark.parametrize("env", [{"PE_PCG": "0"}, {"PE_FORMAT": "csr"}, {"PE_PCG": "0", "PE_FORMAT": "csr"}])
+def test_all_solver_paths_agree(env):
+    """The multi-kernel CG path and the plain-CSR SpMV stay selectable (PE_PCG=0 / PE_FORMAT=csr); every combination has to meet
+    the same bars as the default (persistent kernel + block-CSR).  Run in a subprocess: the switches are read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, r'%s'); import helpers as H; capi, fss = H.capi, H.fss\n"
+        "inp = capi.InputData(text=H.make_input(dim=3, refine=3, degree_u=1)); mesh = fss.make_mesh(inp)\n"
+        "dev = capi.create_device_backend(0); ora = H.create_oracle_backend()\n"
+        "for b in (dev, ora):\n"
+        "    fss.upload_problem(b, inp, mesh); fss.initialize(b, inp); r = fss.time_step(b, inp)\n"
+        "ep = fss.rel_l2(dev.get_vector(capi.VEC_P), ora.get_vector(capi.VEC_P)); eu = fss.rel_l2(dev.get_vector(capi.VEC_U), ora.get_vector(capi.VEC_U))\n"
+        "print('RESULT', ep, eu, dev.stats()['bsr_block_size'], dev.stats()['pcg_iterations_u'])\n"
+        "assert ep <= 1e-8 and eu <= 1e-8\n" % str(H.ROOT / "tests"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env={**os.environ, **env, "PE_SKIP_BUILD": "1"})
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    res = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0].split()
+    assert int(res[3]) == (0 if env.get("PE_FORMAT") == "csr" else 3)
