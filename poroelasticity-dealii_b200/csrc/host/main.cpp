@@ -10,29 +10,21 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
-#include <list>
 #include <string>
 #include <thread>
 
 #include "problem.hpp"
 
 namespace parse_command_line {
+// Behaviour of parse_command_line (PCL:5-27): without arguments print a hint and exit(1); otherwise echo every
+// argument on its own line and take the first one as the input file name.
 std::string parse_command_line(int argc, char* const* argv) {
-  std::string filename;
   if (argc < 2) {
     std::cout << "specify the file name" << std::endl;
     std::exit(1);
   }
-  std::list<std::string> args;
-  for (int i = 1; i < argc; ++i) args.push_back(argv[i]);
-  int arg_number = 1;
-  while (args.size()) {
-    std::cout << args.front() << std::endl;
-    if (arg_number == 1) filename = args.front();
-    args.pop_front();
-    arg_number++;
-  }
-  return filename;
+  for (int i = 1; i < argc; ++i) std::cout << argv[i] << std::endl;
+  return std::string(argv[1]);
 }
 }  // namespace parse_command_line
 
