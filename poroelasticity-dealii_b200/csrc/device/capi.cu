@@ -114,7 +114,7 @@ int pe_create(pe_ctx** out, int device, int rank, int nranks, const void* nccl_i
     c->cg_state.alloc_zero(1, c->stream);
     c->pcg_tickets.alloc_zero(4, c->stream);
     c->pcg_flags.alloc_zero(2, c->stream);
-    c->pcg_timing.alloc_zero(2, c->stream);
+    c->pcg_timing.alloc_zero(10, c->stream);
     PE_CUDA(cudaMallocHost((void**)&c->h_state, 2 * sizeof(CgState)));
     PE_CUDA(cudaMallocHost((void**)&c->h_scalars, (PE_RED_SLOTS + 8) * sizeof(double)));
     PE_CUDA(cudaEventCreateWithFlags(&c->ev_poll[0], cudaEventDisableTiming));
@@ -136,6 +136,15 @@ int pe_create(pe_ctx** out, int device, int rank, int nranks, const void* nccl_i
 void pe_destroy(pe_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (std::getenv("PE_PCG_TIMING")) {
+    static const char* names[8] = {"halo send", "interior rows", "halo wait", "boundary rows", "reduce+fetch d.h", "update", "reduce+fetch res,gz", "direction+barrier"};
+    for (int f = 0; f < 2; ++f) {
+      if (!c->pcg_phase_its[f]) continue;
+      std::fprintf(stderr, "[pe rank %d] k_pcg %s: %lld iterations, us per iteration (CTA 0):", c->rank, f ? "displacement" : "pressure/projection", c->pcg_phase_its[f]);
+      for (int k = 0; k < 8; ++k) std::fprintf(stderr, " %s %.1f;", names[k], c->pcg_phase_ns[f][k] * 1e-3 / (double)c->pcg_phase_its[f]);
+      std::fprintf(stderr, "\n");
+    }
+  }
   if (c->stream) cudaStreamSynchronize(c->stream);
   pe_comm_release(c);
   if (c->comm) ncclCommDestroy(c->comm);

@@ -34,7 +34,7 @@ struct PcgArgs {
   unsigned* tickets;     // [0] reductions, [1] barrier, [2] halo
   int* bar_flag;         // grid barrier epoch
   int* abort;            // raised by any wait that times out
-  unsigned long long* timing;  // [0] ns in the SpMV(+dot) phase as seen by CTA 0, [1] number of phases
+  unsigned long long* timing;  // [0] ns in the SpMV(+dot) phase as seen by CTA 0, [1] number of phases, [2..9] sub-phase ns (PE_PCG_TIMING)
   // peers
   char* const* peer;
   int nranks, me, red_epoch0;
@@ -185,6 +185,16 @@ __global__ void __launch_bounds__(SPMV_T) k_pcg(PcgArgs a) {
   const P2PControl* my_ctl = reinterpret_cast<const P2PControl*>(a.peer[a.me]);
   int bar_epoch = pe_ld_flag(a.bar_flag);  // the same value in every CTA: the flag only moves inside barriers
   unsigned long long t_spmv = 0, n_spmv = 0;
+  unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // send, interior, halo wait, boundary, reduce+fetch d.h, update, reduce+fetch 2, direction+barrier
+  const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+  auto stamp = [&](unsigned long long& last, int slot) {
+    if (timer) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      ph[slot] += now - last;
+      last = now;
+    }
+  };
   __syncthreads();
 
   for (int k = 1; k <= a.max_iterations; ++k) {
@@ -192,6 +202,7 @@ __global__ void __launch_bounds__(SPMV_T) k_pcg(PcgArgs a) {
     const int e_dh = a.red_epoch0 + 2 * k - 1, e_upd = a.red_epoch0 + 2 * k;
     unsigned long long t0 = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned long long tl = t0;
     // ---- halo of d: store my boundary entries into the neighbours' ghost segments, then publish
     if (a.n_neigh) {
       for (int64_t i = gtid; i < a.n_send; i += gsize) {
@@ -228,13 +239,17 @@ __global__ void __launch_bounds__(SPMV_T) k_pcg(PcgArgs a) {
         }
       }
     };
+    stamp(tl, 0);
     multiply_blocks(0, nb_int);
+    stamp(tl, 1);
     bool ok = true;
     if (a.n_neigh) {  // the boundary rows need the neighbours' values
       if ((int)threadIdx.x < a.n_neigh) ok = pcg_wait(&my_ctl->halo_flag[a.field][a.neigh_rank[threadIdx.x]], a.halo_epoch0 + k, a.abort);
       ok = __syncthreads_and(ok ? 1 : 0) != 0;
       __threadfence_system();
+      stamp(tl, 2);
       multiply_blocks(nb_int, nb_all);
+      stamp(tl, 3);
     }
     pcg_reduce_post<1>(a, acc1, 0, e_dh, s_buf, &s_last);
     // ---- alpha; g += alpha h; x += alpha d; z = D^-1 g; ||g||^2, g.z
@@ -246,6 +261,7 @@ __global__ void __launch_bounds__(SPMV_T) k_pcg(PcgArgs a) {
       t_spmv += t1 - t0;
       n_spmv += 1;
     }
+    stamp(tl, 4);
     const double alpha = gh / dh[0];
     double acc2[2] = {0.0, 0.0};
     for (int64_t i = gtid; i < a.n; i += gsize) {
@@ -257,10 +273,12 @@ __global__ void __launch_bounds__(SPMV_T) k_pcg(PcgArgs a) {
       acc2[0] += gi * gi;
       acc2[1] += gi * zi;
     }
+    stamp(tl, 5);
     pcg_reduce_post<2>(a, acc2, 1, e_upd, s_buf, &s_last);
     // ---- SolverControl::check, beta, d = beta d - z
     double rz[2];
     ok = pcg_fetch<2>(a, 1, e_upd, rz, s_buf, &s_ok) && ok;
+    stamp(tl, 6);
     const double res = sqrt(rz[0]);
     const bool converged = ok && res <= tol;
     const bool failed = !ok || it >= max_it || isnan(res);
@@ -275,10 +293,12 @@ __global__ void __launch_bounds__(SPMV_T) k_pcg(PcgArgs a) {
     gh = rz[1];
     for (int64_t i = gtid; i < a.n; i += gsize) a.d[i] = beta * a.d[i] - a.z[i];
     pcg_grid_barrier(a, ++bar_epoch);
+    stamp(tl, 7);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     *a.gh = gh;
     atomicAdd(&a.timing[0], t_spmv);
     atomicAdd(&a.timing[1], n_spmv);
+    for (int k = 0; k < 8; ++k) atomicAdd(&a.timing[2 + k], ph[k]);
   }
 }

@@ -1064,7 +1064,7 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
     pa.ctrl_bytes = c->p2p.ctrl_bytes;
     pa.d_off = (size_t)(d - reinterpret_cast<double*>(c->p2p.region + c->p2p.ctrl_bytes));
     pa.max_iterations = max_it;
-    PE_CUDA(cudaMemsetAsync(c->pcg_timing.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    PE_CUDA(cudaMemsetAsync(c->pcg_timing.p, 0, 10 * sizeof(unsigned long long), c->stream));
     PE_CUDA(cudaMemsetAsync(c->pcg_flags.p + 1, 0, sizeof(int), c->stream));  // abort flag
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->profiling) {
@@ -1085,7 +1085,7 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
       }
     }
     if (c->profiling) PE_CUDA(cudaEventRecord(e1, c->stream));
-    unsigned long long h_timing[2] = {0, 0};
+    unsigned long long h_timing[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     PE_CUDA(cudaMemcpyAsync(&c->h_state[0], st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
     PE_CUDA(cudaMemcpyAsync(h_timing, c->pcg_timing.p, sizeof h_timing, cudaMemcpyDeviceToHost, c->stream));
     PE_CUDA(cudaStreamSynchronize(c->stream));
@@ -1095,6 +1095,8 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
     c->p2p.red_epoch += 2u * (unsigned)its;  // every rank executed the same number of posts
     if (multi) PF.epoch += (unsigned)its;
     *spmv_counter += its;
+    for (int k = 0; k < 8; ++k) c->pcg_phase_ns[fi][k] += (double)h_timing[2 + k];
+    c->pcg_phase_its[fi] += its;
     if (c->profiling) {
       float ms = 0.f;
       PE_CUDA(cudaEventElapsedTime(&ms, e0, e1));

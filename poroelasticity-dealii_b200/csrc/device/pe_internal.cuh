@@ -217,6 +217,8 @@ struct pe_ctx {
   DBuf<int> pcg_flags;
   DBuf<unsigned long long> pcg_timing;
   int pcg_grid[2] = {0, 0};  // cooperative grid size per field (0 = not queried yet)
+  double pcg_phase_ns[2][8] = {{0}};  // CTA-0 sub-phase times of the persistent kernel (printed with PE_PCG_TIMING=1)
+  long long pcg_phase_its[2] = {0, 0};
   DBuf<CgState> cg_state;
   CgState* h_state = nullptr;  // pinned
   double* h_scalars = nullptr; // pinned, PE_RED_SLOTS
