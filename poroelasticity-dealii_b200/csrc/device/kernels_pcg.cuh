@@ -15,7 +15,10 @@
 // multiply the interior rows (which reference no ghost column), and only then wait for the neighbours' flags
 // before the boundary rows — communication and rank skew hide behind the interior SpMV.
 // Cross-phase visibility follows the PTX memory model: writers fence before they arrive at a barrier / post a
-// flag, readers fence after they observe it (the gpu-scope fence also drops stale L1 lines of this SM).
+// flag, readers fence after they observe it (the gpu-scope fence also drops stale L1 lines of this SM).  Only ONE
+// thread (or warp) per CTA executes each fence: the CTA barrier in front of it makes the fence cumulative over the
+// whole CTA's writes, and a barrier behind the observer's fence extends the acquire to the whole CTA.  (With a
+// fence in every thread each sync point cost ~15 us; fences are per-SM L1 invalidations on this architecture.)
 
 struct PcgArgs {
   const int32_t* rowptr;
@@ -67,91 +70,42 @@ __device__ __forceinline__ bool pcg_wait(const int* flag, int epoch, int* abort)
   return true;
 }
 
-// sum over the CTA; valid in lane 0 of warp 0 (and every lane of warp 0)
-__device__ __forceinline__ double block_sum(double v, double* s_buf) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if (lane == 0) s_buf[w] = v;
-  __syncthreads();
-  double t = 0.0;
-  if (w == 0) {
-    t = lane < nw ? s_buf[lane] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-  }
-  return t;
-}
-
-// all CTAs: contribute NV partials; the last CTA posts the totals to every rank's mailbox under `epoch`
+// CTA-wide sums of NV values at once (two barriers in total); the results are valid in every lane of warp 0.
+// s_buf holds NV*32 doubles.
 template <int NV>
-__device__ __forceinline__ void pcg_reduce_post(const PcgArgs& a, double (&v)[NV], int slot0, int epoch, double* s_buf, bool* s_last) {
-  __threadfence();  // this thread's vector writes of the phase become visible before its CTA arrives
+__device__ __forceinline__ void block_sum_n(double (&v)[NV], double* s_buf) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    const double t = block_sum(v[k], s_buf);
-    if (threadIdx.x == 0) a.partials[(size_t)(slot0 + k) * PE_MAX_RED_BLOCKS + blockIdx.x] = t;
+    double x = v[k];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    v[k] = x;
   }
-  if (threadIdx.x == 0) {
-    __threadfence();
-    *s_last = (atomicAdd(&a.tickets[0], 1u) == gridDim.x - 1);
+  __syncthreads();  // s_buf may still be read by the previous user
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s_buf[k * 32 + w] = v[k];
   }
   __syncthreads();
-  if (*s_last) {
-    __threadfence();
-    double tot[NV];
+  if (w == 0) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      double p = 0.0;
-      for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) p += ((volatile double*)a.partials)[(size_t)(slot0 + k) * PE_MAX_RED_BLOCKS + i];
-      tot[k] = block_sum(p, s_buf);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      a.tickets[0] = 0u;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) s_buf[k] = tot[k];
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < a.nranks) {
-      P2PControl* ctl = reinterpret_cast<P2PControl*>(a.peer[threadIdx.x]);
-#pragma unroll
-      for (int k = 0; k < NV; ++k) ctl->red_val[epoch & 1][a.me][slot0 + k] = s_buf[k];
-      __threadfence_system();
-      pe_st_flag(&ctl->red_flag[a.me], epoch);
+      double t = lane < nw ? s_buf[k * 32 + lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      v[k] = t;
     }
   }
 }
 
-// all CTAs: wait until every rank has posted `epoch`, return the rank-ordered sums of NV slots
-template <int NV>
-__device__ __forceinline__ bool pcg_fetch(const PcgArgs& a, int slot0, int epoch, double (&out)[NV], double* s_buf, int* s_ok) {
-  const P2PControl* mine = reinterpret_cast<const P2PControl*>(a.peer[a.me]);
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    bool good = true;
-    if ((int)threadIdx.x < a.nranks) good = pcg_wait(&mine->red_flag[threadIdx.x], epoch, a.abort);
-    good = __all_sync(0xffffffffu, good);
-    __threadfence_system();
-    if ((int)threadIdx.x < NV) {
-      double sum = 0.0;
-      if (good)
-        for (int q = 0; q < a.nranks; ++q) sum += pe_ld_mail(&mine->red_val[epoch & 1][q][slot0 + threadIdx.x]);
-      s_buf[threadIdx.x] = sum;
-    }
-    if (threadIdx.x == 0) *s_ok = good ? 1 : 0;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < NV; ++k) out[k] = s_buf[k];
-  const bool ok = *s_ok != 0;
-  __threadfence();  // acquire: what the posting CTAs wrote before their fences is visible here
-  return ok;
+// Release fence of a post: system scope only when another GPU reads the mailbox.
+__device__ __forceinline__ void pcg_release_fence(int nranks) {
+  if (nranks > 1) __threadfence_system(); else __threadfence();
 }
 
 __device__ __forceinline__ void pcg_grid_barrier(const PcgArgs& a, int epoch) {
-  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();  // release (cumulative over the CTA)
     if (atomicAdd(&a.tickets[1], 1u) == gridDim.x - 1) {
       a.tickets[1] = 0u;
       __threadfence();
@@ -159,15 +113,73 @@ __device__ __forceinline__ void pcg_grid_barrier(const PcgArgs& a, int epoch) {
     } else {
       pcg_wait(a.bar_flag, epoch, a.abort);
     }
+    __threadfence();  // acquire
   }
   __syncthreads();
-  __threadfence();
+}
+
+// Global sum of NV values over all CTAs of all ranks; every thread of every CTA on every rank returns the same
+// bits.  Scheme: (1) CTA partials to a fixed slot, (2) grid barrier, (3) EVERY CTA adds all partials itself in a
+// fixed order (a few independent L2 loads per lane — cheaper than a last-CTA serial section followed by a
+// publish/fetch round trip), (4) multi-GPU only: CTA 0 posts the rank total to every rank's mailbox, all CTAs
+// wait for the flags and add the mailboxes in rank order.
+template <int NV>
+__device__ __forceinline__ bool pcg_allreduce(const PcgArgs& a, double (&v)[NV], int slot0, int red_epoch, int& bar_epoch, double* s_buf, int* s_ok) {
+  block_sum_n<NV>(v, s_buf);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) a.partials[(size_t)(slot0 + k) * PE_MAX_RED_BLOCKS + blockIdx.x] = v[k];
+  }
+  pcg_grid_barrier(a, ++bar_epoch);
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    double tot[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double p = 0.0;
+      for (int i = lane; i < (int)gridDim.x; i += 32) p += __ldcg(a.partials + (size_t)(slot0 + k) * PE_MAX_RED_BLOCKS + i);
+      for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      tot[k] = p;
+    }
+    bool good = true;
+    if (a.nranks > 1) {
+      if (blockIdx.x == 0 && lane < a.nranks) {
+        P2PControl* ctl = reinterpret_cast<P2PControl*>(a.peer[lane]);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) ctl->red_val[red_epoch & 1][a.me][slot0 + k] = tot[k];
+        __threadfence_system();
+        pe_st_flag(&ctl->red_flag[a.me], red_epoch);
+      }
+      const P2PControl* mine = reinterpret_cast<const P2PControl*>(a.peer[a.me]);
+      if (lane < a.nranks) good = pcg_wait(&mine->red_flag[lane], red_epoch, a.abort);
+      good = __all_sync(0xffffffffu, good);
+      __threadfence();  // orders the mailbox loads behind the flag loads (both bypass L1)
+      double mail[NV];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) mail[k] = (good && lane < a.nranks) ? pe_ld_mail(&mine->red_val[red_epoch & 1][lane][slot0 + k]) : 0.0;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        double sum = 0.0;
+        for (int q = 0; q < a.nranks; ++q) sum += __shfl_sync(0xffffffffu, mail[k], q);
+        tot[k] = sum;
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) s_buf[k] = tot[k];
+      *s_ok = good ? 1 : 0;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = s_buf[k];
+  return *s_ok != 0;
 }
 
 // B == 0: CSR with LPR lanes per row; B > 0: block CSR with B x B blocks
 template <int LPR, int B>
 __global__ void __launch_bounds__(SPMV_T) k_pcg(PcgArgs a) {
-  __shared__ double s_buf[32];
+  __shared__ double s_buf[3 * 32];
   __shared__ bool s_last;
   __shared__ int s_ok;
   CgState* st = a.state;
@@ -209,12 +221,14 @@ __global__ void __launch_bounds__(SPMV_T) k_pcg(PcgArgs a) {
         double* dst = reinterpret_cast<double*>(a.peer[a.neigh_rank[a.send_nb[i]]] + a.ctrl_bytes) + a.d_off;
         dst[a.send_dest[i]] = a.d[a.send_idx[i]];
       }
-      __threadfence_system();
       __syncthreads();
-      if (threadIdx.x == 0) s_last = (atomicAdd(&a.tickets[2], 1u) == gridDim.x - 1);
+      if (threadIdx.x == 0) {
+        __threadfence_system();  // release of the CTA's remote stores
+        s_last = (atomicAdd(&a.tickets[2], 1u) == gridDim.x - 1);
+        if (s_last) __threadfence_system();
+      }
       __syncthreads();
       if (s_last) {
-        __threadfence_system();
         if ((int)threadIdx.x < a.n_neigh)
           pe_st_flag(&reinterpret_cast<P2PControl*>(a.peer[a.neigh_rank[threadIdx.x]])->halo_flag[a.field][a.me], a.halo_epoch0 + k);
         if (threadIdx.x == 0) a.tickets[2] = 0u;
@@ -245,16 +259,15 @@ __global__ void __launch_bounds__(SPMV_T) k_pcg(PcgArgs a) {
     bool ok = true;
     if (a.n_neigh) {  // the boundary rows need the neighbours' values
       if ((int)threadIdx.x < a.n_neigh) ok = pcg_wait(&my_ctl->halo_flag[a.field][a.neigh_rank[threadIdx.x]], a.halo_epoch0 + k, a.abort);
+      if (threadIdx.x < 32) __threadfence_system();  // acquire by the polling warp, extended to the CTA by the barrier below
       ok = __syncthreads_and(ok ? 1 : 0) != 0;
-      __threadfence_system();
       stamp(tl, 2);
       multiply_blocks(nb_int, nb_all);
       stamp(tl, 3);
     }
-    pcg_reduce_post<1>(a, acc1, 0, e_dh, s_buf, &s_last);
+    ok = pcg_allreduce<1>(a, acc1, 0, e_dh, bar_epoch, s_buf, &s_ok) && ok;
     // ---- alpha; g += alpha h; x += alpha d; z = D^-1 g; ||g||^2, g.z
-    double dh[1];
-    ok = pcg_fetch<1>(a, 0, e_dh, dh, s_buf, &s_ok) && ok;
+    const double dh[1] = {acc1[0]};
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -274,10 +287,9 @@ __global__ void __launch_bounds__(SPMV_T) k_pcg(PcgArgs a) {
       acc2[1] += gi * zi;
     }
     stamp(tl, 5);
-    pcg_reduce_post<2>(a, acc2, 1, e_upd, s_buf, &s_last);
+    ok = pcg_allreduce<2>(a, acc2, 1, e_upd, bar_epoch, s_buf, &s_ok) && ok;
     // ---- SolverControl::check, beta, d = beta d - z
-    double rz[2];
-    ok = pcg_fetch<2>(a, 1, e_upd, rz, s_buf, &s_ok) && ok;
+    const double rz[2] = {acc2[0], acc2[1]};
     stamp(tl, 6);
     const double res = sqrt(rz[0]);
     const bool converged = ok && res <= tol;
