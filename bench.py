@@ -30,14 +30,13 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, str(ROOT / "tests"))
 
 METRIC = "fixed_stress_time_steps_per_second"
 UNIT = "steps/s"
 
 
 def input_text(refine, precond, cheb_degree, eig_ratio, max_its, cells=None, size=None):
-    import helpers as H
+    H = importlib.import_module("poroelasticity-dealii_b200").inputs
     extra = (f"  set Preconditioner = {precond}\n  set Chebyshev degree = {cheb_degree}\n"
              f"  set Chebyshev eigenvalue ratio = {eig_ratio}\n  set CG max iterations = {max_its}\n")
     text = H.make_input(dim=3, refine=refine, degree_u=1, extra_gpu=extra, cells=cells)
@@ -107,6 +106,7 @@ def cpu_sample(refine, threads, golden, cg_sample_its=(2, 5, 5)):
     Builds the full-size systems, then times a few iterations of each solver and one call of each assembly
     operator, and extrapolates one time step with the oracle's own iteration counts recorded offline by
     tests/golden/make_oracle_counts.py (a full oracle step at 128^3 takes tens of minutes)."""
+    sys.path.insert(0, str(ROOT / "tests"))  # the oracle binding lives with the tests; only the CPU legs import it
     import helpers as H
     capi, fss = H.capi, H.fss
     lib = H.load_oracle()
