@@ -186,9 +186,23 @@ void pe_comm_setup(pe_ctx* c, size_t n_work) {
     const char* env = std::getenv("PE_COMM");
     const bool want = !(env && std::strcmp(env, "nccl") == 0) && c->nranks <= PE_P2P_MAX_RANKS;
     if (want) {
-      // exchange the IPC handles of all regions through NCCL
+      // exchange the IPC handles of all regions through NCCL.  Every step that can fail for environmental reasons
+      // (IPC disabled in the container, no peer access between two devices) is followed by a collective vote, so
+      // either every rank uses the peer-memory transport or every rank stays on NCCL.
+      auto all_agree = [&](bool mine_ok) {
+        int v = mine_ok ? 1 : 0;
+        DBuf<int> d;
+        d.upload(&v, 1, s);
+        PE_NCCL(ncclAllReduce(d.p, d.p, 1, ncclInt, ncclMin, c->comm_nccl(), s));
+        PE_CUDA(cudaMemcpyAsync(&v, d.p, sizeof v, cudaMemcpyDeviceToHost, s));
+        PE_CUDA(cudaStreamSynchronize(s));
+        return v == 1;
+      };
       cudaIpcMemHandle_t mine;
-      PE_CUDA(cudaIpcGetMemHandle(&mine, M.region));
+      std::memset(&mine, 0, sizeof mine);
+      bool ok = cudaIpcGetMemHandle(&mine, M.region) == cudaSuccess;
+      (void)cudaGetLastError();
+      if (env && std::strcmp(env, "ipcfail") == 0 && c->rank == c->nranks - 1) ok = false;  // test hook: one rank cannot export
       DBuf<char> all;
       all.alloc((size_t)c->nranks * sizeof mine);
       PE_CUDA(cudaMemcpyAsync(all.p + (size_t)c->rank * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice, s));
@@ -196,8 +210,21 @@ void pe_comm_setup(pe_ctx* c, size_t n_work) {
       std::vector<cudaIpcMemHandle_t> h(c->nranks);
       PE_CUDA(cudaMemcpyAsync(h.data(), all.p, all.n, cudaMemcpyDeviceToHost, s));
       PE_CUDA(cudaStreamSynchronize(s));
-      for (int r = 0; r < c->nranks; ++r)
-        if (r != c->rank) PE_CUDA(cudaIpcOpenMemHandle((void**)&M.peer[r], h[r], cudaIpcMemLazyEnablePeerAccess));
+      ok = all_agree(ok);
+      if (ok) {
+        for (int r = 0; r < c->nranks && ok; ++r)
+          if (r != c->rank) ok = cudaIpcOpenMemHandle((void**)&M.peer[r], h[r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        (void)cudaGetLastError();
+        ok = all_agree(ok);
+      }
+      if (!ok) {  // fall back to NCCL inside the CG loop as well
+        for (int r = 0; r < c->nranks; ++r)
+          if (r != c->rank && M.peer[r]) { cudaIpcCloseMemHandle(M.peer[r]); M.peer[r] = nullptr; }
+        (void)cudaGetLastError();
+        std::fprintf(stderr, "[poroel rank %d] peer-memory transport unavailable (cudaIpc), using NCCL inside the CG loop\n", c->rank);
+        PE_CUDA(cudaStreamSynchronize(s));
+        return;
+      }
       M.d_peer.upload(M.peer, s);
       M.ticket.alloc_zero(1, s);
       // landing offsets: neighbour k must be told where its values go inside MY vector (n_owned + recv_ptr[k]);
