@@ -58,3 +58,31 @@ def test_product_fails_loudly_without_a_gpu():
         capi.create_device_backend(0)
     assert e.value.status == capi.PE_ERR_CUDA
     assert "no CPU fallback" in str(e.value)
+
+
+def test_ctypes_struct_offsets_match_a_c_compile_of_the_header(tmp_path):
+    """Compile a C program against include/poroel.h and include/poroel_host.h and compare every field offset with the ctypes mirror."""
+    def emit(struct, cname, fields):
+        lines = [f'  printf("{struct} size %zu\\n", sizeof({cname}));']
+        for f in fields:
+            lines.append(f'  printf("{struct} {f} %zu\\n", offsetof({cname}, {f}));')
+        return "\n".join(lines)
+
+    mirrors = {"pe_params": capi.PeParams, "pe_stats": capi.PeStats, "peh_step_report": capi.StepReport, "peh_mesh_view": capi.MeshView,
+               "peh_dofs_view": capi.DofsView, "peh_input_view": capi.InputView, "peh_part_field_view": capi.PartFieldView, "peh_part_view": capi.PartView}
+    body = "\n".join(emit(name, name, [f for f, _ in cls._fields_]) for name, cls in mirrors.items())
+    src = tmp_path / "offsets.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "poroel_host.h"\nint main(void) {\n' + body + "\n  return 0;\n}\n")
+    exe = tmp_path / "offsets"
+    subprocess.check_call(["gcc", "-std=c11", "-I", str(H.ROOT / "include"), str(src), "-o", str(exe)])  # the headers are plain C
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        struct, field, value = line.split()
+        cls = mirrors[struct]
+        if field == "size":
+            assert C.sizeof(cls) == int(value), (struct, C.sizeof(cls), value)
+        else:
+            assert getattr(cls, field).offset == int(value), (struct, field)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in mirrors.values())
