@@ -1023,9 +1023,10 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
   const int max_it = c->prm.cg_max_iterations;
   // The persistent kernel removes every launch gap and host/NCCL round trip, but its static row assignment cannot
   // balance slow SMs the way CTA scheduling does: measured on B200, it wins when a matrix pass is short
-  // (<= ~0.25 ms: 8-GPU blocks of the 128^3 problem, all pressure solves) and loses ~5-10 % on multi-ms passes.
+  // (<= ~0.3 ms: 4- and 8-GPU blocks of the 128^3 problem, all pressure solves; 148 vs 161 ms per step at 4 GPUs)
+  // and loses ~5-10 % on multi-ms passes.
   static const bool pcg_disabled = std::getenv("PE_PCG") && std::string(std::getenv("PE_PCG")) == "0";
-  static const long long pcg_max_nnz = std::getenv("PE_PCG_MAX_NNZ") ? std::atoll(std::getenv("PE_PCG_MAX_NNZ")) : 100000000LL;
+  static const long long pcg_max_nnz = std::getenv("PE_PCG_MAX_NNZ") ? std::atoll(std::getenv("PE_PCG_MAX_NNZ")) : 150000000LL;
   const bool has_bsr = F.bsr.B && val == c->A.p;
   if (!cheb && !pcg_disabled && (!multi || fused) && F.nnz <= pcg_max_nnz) {
     // ---- the whole CG loop in one persistent cooperative launch (kernels_pcg.cuh)
