@@ -5,12 +5,11 @@
 // d = beta d - z; call sites PS:176-179, DS:300-305, SP:210-214) runs inside ONE cooperative launch.  One CTA set
 // stays resident (grid = SMs x occupancy); the three phases of an iteration are separated by on-device
 // synchronisation only:
-//   * the two dot-product reductions double as grid barriers: every CTA deposits its partial, the last one to
-//     arrive (atomic ticket) sums them in a fixed order and POSTS the total to the mailbox of every rank
-//     (peer memory over NVLink; with one rank the mailbox is local) — all CTAs of all ranks then read the same
-//     mailboxes and add them in rank order, so alpha, beta and the stopping decision are bitwise identical
-//     everywhere and no host or NCCL round trip exists inside the loop;
-//   * one explicit grid barrier after the direction update.
+//   * each of the two dot-product reductions is "CTA partials -> grid barrier -> EVERY CTA adds all partials in a
+//     fixed order"; with several ranks CTA 0 then posts the rank total to the mailbox of every rank (peer memory
+//     over NVLink) and all CTAs of all ranks add the mailboxes in rank order — alpha, beta and the stopping
+//     decision are bitwise identical everywhere and no host or NCCL round trip exists inside the loop;
+//   * one more grid barrier after the direction update.
 // Halo: the CTAs first store the boundary entries of d straight into the neighbours' ghost segments, then
 // multiply the interior rows (which reference no ghost column), and only then wait for the neighbours' flags
 // before the boundary rows — communication and rank skew hide behind the interior SpMV.
