@@ -253,3 +253,69 @@ def test_patch_test_on_distorted_gmsh_meshes(dim, fname, deg):
     rep = fss.time_step(b, inp)
     assert rep["fss_iterations"] == 1
     b.close()
+
+
+@pytest.mark.parametrize("dim,deg", [(2, 1), (2, 2), (3, 1)])
+def test_t6_elasticity_element_matrix_against_sympy(dim, deg):
+    """the single-cell elasticity matrix a(phi_i, phi_j) = int (C : eps(phi_i)) : eps(phi_j) (DS:237-242 with
+    CM:45-57) integrated EXACTLY with sympy from the Lagrange basis definition, against the oracle's assembled matrix
+    (no Dirichlet data, so nothing is eliminated).  Pins FE_Q(deg), the local dof order, QGauss(deg+1) and the tensor
+    contraction independently of any quadrature code."""
+    import sympy as sp
+    size = 10
+    inp = capi.InputData(text=H.make_input(dim=dim, refine=2, degree_u=deg, cells=[1] * dim, dirichlet=([], [], [])))
+    mesh = fss.make_mesh(inp)
+    b = H.create_oracle_backend()
+    dp, du, (line_dof, _) = fss.upload_problem(b, inp, mesh)
+    assert len(line_dof) == 0
+    b.pressure_set_uniform(0.0)
+    b.displacement_assemble()
+    A = b.get_matrix(capi.MAT_ELASTICITY).toarray()
+    prm = inp.params()
+    lam, mu = sp.nsimplify(prm.lame_lambda), sp.nsimplify(prm.shear_modulus)
+    xs = sp.symbols("x0:%d" % dim)
+    nodes1d = [sp.Rational(k, deg) for k in range(deg + 1)]
+
+    def lagr(i, x):
+        e = sp.Integer(1)
+        for k, t in enumerate(nodes1d):
+            if k != i:
+                e *= (x - t) / (nodes1d[i] - t)
+        return e
+
+    spts = du.support_points()
+    comp = np.zeros(du.n_dofs, int)
+    for c in range(dim):
+        comp[du.cell_dofs[:, c::dim].ravel()] = c
+    shapes = []
+    for d in range(du.n_dofs):  # physical cell [-5,5]^dim: unit coordinate xi = (x + 5)/10
+        xi = [(spts[d][a] + size / 2) / size for a in range(dim)]
+        idx = [int(round(v * deg)) for v in xi]
+        N = sp.Integer(1)
+        for a in range(dim):
+            N *= lagr(idx[a], (xs[a] + sp.Rational(size, 2)) / size)
+        shapes.append((N, int(comp[d])))
+
+    def strain(N, c):
+        g = [sp.diff(N, x) for x in xs]
+        E = sp.zeros(dim, dim)
+        for a in range(dim):
+            E[c, a] += g[a] / 2
+            E[a, c] += g[a] / 2
+        return E
+
+    eps = [strain(N, c) for N, c in shapes]
+    lims = [(x, -sp.Rational(size, 2), sp.Rational(size, 2)) for x in xs]
+    worst = 0.0
+    n = du.n_dofs
+    pairs = [(i, j) for i in range(n) for j in range(i, n)]
+    if n > 20:  # keep the symbolic work bounded: a deterministic subset of the upper triangle
+        pairs = pairs[::7]
+    for i, j in pairs:
+        sig = lam * eps[i].trace() * sp.eye(dim) + 2 * mu * eps[i]
+        integrand = sum(sig[a, c] * eps[j][a, c] for a in range(dim) for c in range(dim))
+        exact = float(sp.integrate(sp.expand(integrand), *lims))
+        scale = max(abs(exact), abs(A).max() * 1e-3)
+        worst = max(worst, abs(A[i, j] - exact) / scale, abs(A[j, i] - exact) / scale)
+    assert worst <= 1e-12, worst
+    b.close()
