@@ -156,6 +156,12 @@ def test_t9_independent_numpy_restatement(dim, n, deg):
     assert fss.rel_l2(b.get_vector(capi.VEC_U_RHS), R.rhs_displacement(R.p)[pu]) <= 1e-12
     assert fss.rel_l2(b.get_vector(capi.VEC_U), R.u[pu]) <= 1e-10
     assert fss.rel_l2(b.get_vector(capi.VEC_VOL_STRAIN0), R.ev0[pp]) <= 1e-6  # projection CG stops at 1e-8 relative residual
+    # projection right-hand sides (SP:159-196) entry by entry, before any solve tolerance enters
+    vol = fss.VOLUMETRIC_COMPONENTS[dim]
+    _, rhs_np = R.project_strains(R.u, vol)
+    for comp_t in vol:
+        got = b.get_vector(capi.VEC_PROJ_RHS0 + fss.TENSOR_TO_ENTRY[dim][comp_t])
+        assert np.abs(got - rhs_np[comp_t][pp]).max() <= 1e-9 * np.abs(rhs_np[comp_t]).max()
     for _ in range(2):
         rep = fss.time_step(b, inp)
         hist = R.time_step(inp.time_step)
