@@ -1093,6 +1093,10 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
     PE_CUDA(cudaGetLastError());
     const CgState last = c->h_state[0];
     const int its = last.it;
+    if (last.pad) {  // a wait timed out: barriers may have been left half-arrived; make the next launch start clean
+      PE_CUDA(cudaMemsetAsync(c->pcg_tickets.p, 0, 4 * sizeof(unsigned), c->stream));
+      PE_CUDA(cudaStreamSynchronize(c->stream));
+    }
     c->p2p.red_epoch += 2u * (unsigned)its;  // every rank executed the same number of posts
     if (multi) PF.epoch += (unsigned)its;
     *spmv_counter += its;
