@@ -367,3 +367,25 @@ def test_distorted_gmsh_meshes(dim, fname, deg):
             assert np.abs(s_d - s_o).max() <= 1e-6 * max(np.abs(s_o).max(), 1e-30)
     finally:
         dev.close(); ora.close()
+
+
+def test_shipped_case_all_17_steps():
+    """BASELINE configs[0]: the reference's shipped input.data as-is (2D, refine 4, Q2/Q1, dt = 60, t_max = 1e3 => 17 steps,
+    AMR off).  Every step: same inner-loop counts, p and u within 1e-8 relative L2 of the oracle."""
+    text = H.SHIPPED_INPUT + "\nsubsection GPU\n  set Refine every = 0\n  set CG max iterations = 5000\nend\n"
+    inp, mesh, dev, ora = both(text)
+    try:
+        assert inp.displacement_degree == 2 and mesh.arrays.n_cells == 256
+        fss.initialize(dev, inp); fss.initialize(ora, inp)
+        t, steps = 0.0, 0
+        while t < inp.t_max:  # FSS:327
+            t += inp.time_step
+            steps += 1
+            r_d, r_o = fss.time_step(dev, inp), fss.time_step(ora, inp)
+            assert r_d["inner_counts"] == r_o["inner_counts"], (steps, r_d["residual_history"], r_o["residual_history"])
+            assert r_d["fss_iterations"] == 1
+            assert fss.rel_l2(dev.get_vector(capi.VEC_P), ora.get_vector(capi.VEC_P)) <= FIELD_TOL, steps
+            assert fss.rel_l2(dev.get_vector(capi.VEC_U), ora.get_vector(capi.VEC_U)) <= FIELD_TOL, steps
+        assert steps == 17
+    finally:
+        dev.close(); ora.close()
