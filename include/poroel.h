@@ -65,7 +65,8 @@ enum pe_matrix {
   PE_MAT_MASS = 0,      /* pressure_solver.mass_matrix     PS:44 */
   PE_MAT_LAPLACE = 1,   /* pressure_solver.laplace_matrix  PS:44 */
   PE_MAT_JACOBIAN = 2,  /* pressure_solver.jacobian        PS:44 */
-  PE_MAT_ELASTICITY = 3 /* displacement_solver.system_matrix DS:52 */
+  PE_MAT_ELASTICITY = 3, /* displacement_solver.system_matrix DS:52 */
+  PE_MAT_PROJECTION = 4  /* strain_projector.projection_matrix SP:101-106 (the condensed mass matrix) */
 };
 
 typedef struct pe_params {

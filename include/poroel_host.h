@@ -77,6 +77,36 @@ int  peh_dofs_support_points(const peh_mesh*, const peh_dofs*, double* out /* n_
 int64_t peh_make_dirichlet(const peh_mesh*, const peh_dofs*, int n, const int32_t* labels, const int32_t* comps,
                            const double* values, int32_t* line_dof, double* inhomogeneity);
 
+/* ---- adaptive refinement of the time loop (FSS:333-340, 447-498): refinement forest, hanging-node constraints,
+ *      Kelly estimator, fixed-fraction marking, FE_Q(1) solution transfer (csrc/host/amr.hpp) ---- */
+typedef struct peh_forest peh_forest;
+typedef struct peh_constraints peh_constraints;
+peh_forest* peh_forest_create(const peh_mesh* initial, int base_level);  /* cells of `initial` become roots at base_level */
+void peh_forest_destroy(peh_forest*);
+peh_mesh* peh_forest_active_mesh(const peh_forest*);  /* new handle; active cells level by level (deal.II order) */
+int64_t peh_forest_active_levels(const peh_forest*, int32_t* level_or_null);  /* returns the number of active cells */
+int  peh_forest_set_flags(peh_forest*, int64_t n_active, const int8_t* refine, const int8_t* coarsen);
+int  peh_forest_get_flags(const peh_forest*, int64_t n_active, int8_t* refine, int8_t* coarsen);
+int  peh_forest_prepare(peh_forest*);   /* Triangulation::prepare_coarsening_and_refinement, FSS:481 */
+int  peh_forest_execute(peh_forest*, int32_t* n_coarsened_families, int32_t* n_refined_cells);  /* FSS:483 */
+/* KellyErrorEstimator<dim>::estimate(pressure dof_handler, QGauss<dim-1>(2), {}, p, eta), FSS:454-458 */
+int  peh_forest_kelly(const peh_forest*, const peh_mesh* active, const peh_dofs* dofs_p, const double* p, float* eta);
+/* GridRefinement::refine_and_coarsen_fixed_fraction + the level limits of FSS:460-472 */
+int  peh_forest_mark_fixed_fraction(peh_forest*, int64_t n_active, const float* criteria, double top_fraction, double bottom_fraction,
+                                    int min_level, int max_level);
+/* SolutionTransfer<dim> of FE_Q(1) vectors (FSS:475-497): store before execute, fetch on the new active mesh */
+int  peh_forest_store(peh_forest*, const peh_mesh* active, const peh_dofs* dofs_p, int n_vec, const double* values /* n_vec*n_dofs */);
+int  peh_forest_fetch(const peh_forest*, const peh_mesh* active, const peh_dofs* dofs_p, int n_vec, double* values);
+/* make_hanging_node_constraints + interpolate_boundary_values per (label, component, value) + close (PS:71-78, DS:109-137) */
+typedef struct peh_constraints_view {
+  int64_t n_lines, n_entries;
+  const int32_t* line_dof; const int64_t* entry_ptr; const int32_t* entry_dof; const double* entry_w; const double* inhomogeneity;
+} peh_constraints_view;
+peh_constraints* peh_constraints_make(const peh_forest*, const peh_mesh* active, const peh_dofs*, int n_dirichlet, const int32_t* labels,
+                                      const int32_t* comps, const double* values);
+void peh_constraints_destroy(peh_constraints*);
+int  peh_constraints_view_get(const peh_constraints*, peh_constraints_view* out);
+
 /* ---- cell partition of a mesh for one rank (owned + ghost cell layer, local numbering) ---- */
 typedef struct peh_part peh_part;
 peh_part* peh_partition(const peh_mesh*, const peh_dofs* dofs_p, const peh_dofs* dofs_u, int rank, int nranks);

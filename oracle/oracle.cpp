@@ -21,6 +21,11 @@
 //   ssor_apply ....................................... SparseMatrix::precondition_SSOR PS:177-178, DS:302-303, SP:211-212
 //   pressure_residual / jacobian / solve ............. PS:113-155, PS:158-169, PS:172-185, PS:187-194
 //   projection rhs / solve ........................... SP:109-198, SP:201-232
+//   hanging-node constraints (adaptive meshes) ....... ConstraintMatrix::condense (vector and SparseMatrix, in place),
+//                                                      distribute, distribute_local_to_global with weights,
+//                                                      DoFTools::make_sparsity_pattern(dh, dsp, constraints, true)
+//                                                      as called at PS:71-88, PS:153, PS:168, PS:180, DS:109-146, DS:279-286,
+//                                                      DS:306, SP:104-105, SP:193-194, SP:215
 // Deliberate, documented deviations that do not change results beyond round-off:
 //   * strain tensors of shape functions are computed once per (i,q), not inside the j loop (DS:238-239);
 //   * in rhs-only calls (DS:285-286) the cell matrix is evaluated only on cells that own a
@@ -31,6 +36,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <vector>
 #ifdef _OPENMP
@@ -214,6 +220,133 @@ Pattern make_pattern(int64_t n_dofs, int64_t n_cells, int n_loc, const int32_t* 
   return P;
 }
 
+// ConstraintMatrix after close(): x_i = sum_j w_ij x_j + g_i; masters are never constrained themselves
+struct Lines {
+  vector<int32_t> line_of;  // dof -> line or -1
+  vector<int32_t> dof;
+  vector<int64_t> eptr;
+  vector<int32_t> edof;
+  vector<double> ew, g;
+  int64_t n() const { return (int64_t)dof.size(); }
+  bool any_entries() const { return !edof.empty(); }
+  void set(int64_t n_dofs, int64_t nl, const int32_t* ld, const int64_t* ep, const int32_t* ed, const double* w, const double* inh) {
+    dof.assign(ld, ld + nl);
+    g.assign(nl, 0.0);
+    if (inh) g.assign(inh, inh + nl);
+    eptr.assign(nl + 1, 0);
+    edof.clear();
+    ew.clear();
+    if (ep && ep[nl] > 0) {
+      eptr.assign(ep, ep + nl + 1);
+      edof.assign(ed, ed + ep[nl]);
+      ew.assign(w, w + ep[nl]);
+    }
+    line_of.assign(n_dofs, -1);
+    for (int64_t i = 0; i < nl; ++i) line_of[ld[i]] = (int32_t)i;
+  }
+  // ConstraintMatrix::condense(Vector&): constrained entries are added to their masters, then zeroed
+  void condense(Vec& v) const {
+    for (int64_t l = 0; l < n(); ++l) {
+      for (int64_t e = eptr[l]; e < eptr[l + 1]; ++e) v[edof[e]] += v[dof[l]] * ew[e];
+      v[dof[l]] = 0;
+    }
+  }
+  // ConstraintMatrix::distribute
+  void distribute(Vec& v) const {
+    for (int64_t l = 0; l < n(); ++l) {
+      double s = g[l];
+      for (int64_t e = eptr[l]; e < eptr[l + 1]; ++e) s += v[edof[e]] * ew[e];
+      v[dof[l]] = s;
+    }
+  }
+};
+
+// DoFTools::make_sparsity_pattern(dof_handler, dsp, constraints, keep_constrained_dofs = true): every pair of local dofs
+// of a cell, plus every pair of the cell's resolved dofs (unconstrained local dofs and the masters of constrained ones).
+Pattern make_pattern_constrained(int64_t n_dofs, int64_t n_cells, int n_loc, const int32_t* cell_dofs, const Lines& L) {
+  vector<vector<int32_t>> rows(n_dofs);
+  vector<int32_t> res;
+  for (int64_t c = 0; c < n_cells; ++c) {
+    const int32_t* cd = cell_dofs + c * n_loc;
+    res.clear();
+    for (int k = 0; k < n_loc; ++k) {
+      const int32_t l = L.line_of[cd[k]];
+      if (l < 0) res.push_back(cd[k]);
+      else for (int64_t e = L.eptr[l]; e < L.eptr[l + 1]; ++e) res.push_back(L.edof[e]);
+    }
+    std::sort(res.begin(), res.end());
+    res.erase(std::unique(res.begin(), res.end()), res.end());
+    for (int i = 0; i < n_loc; ++i) rows[cd[i]].insert(rows[cd[i]].end(), cd, cd + n_loc);
+    bool differs = (int)res.size() != n_loc;
+    if (!differs) {
+      vector<int32_t> loc(cd, cd + n_loc);
+      std::sort(loc.begin(), loc.end());
+      differs = loc != res;
+    }
+    if (differs)
+      for (int32_t r : res) rows[r].insert(rows[r].end(), res.begin(), res.end());
+  }
+  Pattern P;
+  P.n = n_dofs;
+  P.rowptr.assign(n_dofs + 1, 0);
+  for (int64_t r = 0; r < n_dofs; ++r) {
+    auto& t = rows[r];
+    t.push_back((int32_t)r);
+    std::sort(t.begin(), t.end());
+    t.erase(std::unique(t.begin(), t.end()), t.end());
+    P.rowptr[r + 1] = P.rowptr[r] + (int64_t)t.size();
+  }
+  P.col.resize(P.rowptr[n_dofs]);
+  P.right_of_diag.resize(n_dofs);
+  for (int64_t r = 0; r < n_dofs; ++r) {
+    int64_t p = P.rowptr[r];
+    P.col[p++] = (int32_t)r;
+    P.right_of_diag[r] = P.rowptr[r + 1];
+    bool found = false;
+    for (int32_t c : rows[r]) {
+      if (c == r) continue;
+      if (!found && c > r) { P.right_of_diag[r] = p; found = true; }
+      P.col[p++] = c;
+    }
+  }
+  return P;
+}
+
+// ConstraintMatrix::condense(SparseMatrix&), in place (deal.II 8.4): regular rows hand their entries in constrained
+// columns to the master columns; constrained rows hand everything to the master rows; a constrained diagonal is set to
+// the average absolute diagonal of the uncondensed matrix.
+void condense_matrix(const Pattern& P, const Lines& L, Vec& A) {
+  if (L.n() == 0) return;
+  double average_diagonal = 0;
+  for (int64_t i = 0; i < P.n; ++i) average_diagonal += std::fabs(A[P.rowptr[i]]);
+  average_diagonal /= (double)P.n;
+  auto add = [&](int32_t r, int32_t c, double v) {
+    const int64_t pos = P.find(r, c);
+    if (pos < 0) throw std::runtime_error("condense: entry missing from the sparsity pattern");
+    A[pos] += v;
+  };
+  for (int64_t row = 0; row < P.n; ++row) {
+    const int32_t lr = L.line_of[row];
+    for (int64_t j = P.rowptr[row]; j < P.rowptr[row + 1]; ++j) {
+      const int32_t column = P.col[j];
+      const int32_t lc = L.line_of[column];
+      const double v = A[j];
+      if (lr < 0) {
+        if (lc < 0) continue;
+        for (int64_t q = L.eptr[lc]; q < L.eptr[lc + 1]; ++q) add((int32_t)row, L.edof[q], v * L.ew[q]);
+        A[j] = 0;
+      } else if (lc < 0) {
+        for (int64_t q = L.eptr[lr]; q < L.eptr[lr + 1]; ++q) add(L.edof[q], column, v * L.ew[q]);
+        A[j] = 0;
+      } else {
+        for (int64_t p = L.eptr[lr]; p < L.eptr[lr + 1]; ++p)
+          for (int64_t q = L.eptr[lc]; q < L.eptr[lc + 1]; ++q) add(L.edof[p], L.edof[q], v * L.ew[p] * L.ew[q]);
+        A[j] = (row == column) ? average_diagonal : 0.0;
+      }
+    }
+  }
+}
+
 // SparseMatrix::vmult
 void vmult(const Pattern& P, const Vec& val, const Vec& x, Vec& y) {
   const int64_t n = P.n;
@@ -349,6 +482,7 @@ struct Ctx {
   vector<int32_t> u_cline;  // dof -> line index or -1
   vector<int32_t> line_dof;
   vector<double> line_g;
+  Lines cu, cp;  // full tables (hanging-node entries included); cp is empty on uniform meshes (PS:71-78)
   // neumann
   vector<int32_t> nm_label, nm_comp;
   vector<double> nm_value;
@@ -602,6 +736,38 @@ void displacement_assemble(Ctx& C) {
       for (int i = 0; i < nl; ++i) avg_diag += std::fabs(cm[(size_t)i * nl + i]);
       avg_diag /= nl;
     }
+    if (C.cu.any_entries()) {  // general lines: local row i goes to its masters with the line's weights
+      const Lines& L = C.cu;
+      for (int i = 0; i < nl; ++i) {
+        const int32_t li = L.line_of[cd[i]];
+        if (li >= 0 && build) {
+          double dgl = std::fabs(cm[(size_t)i * nl + i]);
+          C.A[C.Pu.find(cd[i], cd[i])] += (dgl != 0 ? dgl : avg_diag);
+        }
+        double t = cr[i];  // f_i - sum_l a_il g_l over the inhomogeneously constrained local dofs
+        for (int j = 0; j < nl; ++j) {
+          const int32_t lj = L.line_of[cd[j]];
+          if (lj >= 0 && L.g[lj] != 0) t -= cm[(size_t)i * nl + j] * L.g[lj];
+        }
+        const int64_t i0 = li < 0 ? 0 : L.eptr[li], i1 = li < 0 ? 1 : L.eptr[li + 1];
+        for (int64_t pi = i0; pi < i1; ++pi) {
+          const int32_t gi = li < 0 ? cd[i] : L.edof[pi];
+          const double wi = li < 0 ? 1.0 : L.ew[pi];
+          C.b[gi] += wi * t;
+          if (!build) continue;
+          for (int j = 0; j < nl; ++j) {
+            const int32_t lj = L.line_of[cd[j]];
+            const int64_t j0 = lj < 0 ? 0 : L.eptr[lj], j1 = lj < 0 ? 1 : L.eptr[lj + 1];
+            for (int64_t pj = j0; pj < j1; ++pj) {
+              const int32_t gj = lj < 0 ? cd[j] : L.edof[pj];
+              const double wj = lj < 0 ? 1.0 : L.ew[pj];
+              C.A[C.Pu.find(gi, gj)] += wi * wj * cm[(size_t)i * nl + j];
+            }
+          }
+        }
+      }
+      continue;
+    }
     for (int i = 0; i < nl; ++i) {
       int li = C.u_cline[cd[i]];
       if (li >= 0) {
@@ -665,7 +831,11 @@ void projection_rhs(Ctx& C, int n_comp, const int32_t* comps) {
       }
     }
     for (int c = 0; c < n_comp; ++c)
-      for (int i = 0; i < nsp; ++i) C.proj_rhs[entries[c]][cdp[i]] += cr[(size_t)c * nsp + i];
+      for (int i = 0; i < nsp; ++i) {  // constraints.distribute_local_to_global(cell_rhs[c], ...), SP:193-194
+        const int32_t li = C.cp.n() ? C.cp.line_of[cdp[i]] : -1;
+        if (li < 0) { C.proj_rhs[entries[c]][cdp[i]] += cr[(size_t)c * nsp + i]; continue; }
+        for (int64_t e = C.cp.eptr[li]; e < C.cp.eptr[li + 1]; ++e) C.proj_rhs[entries[c]][C.cp.edof[e]] += C.cp.ew[e] * cr[(size_t)c * nsp + i];
+      }
   }
   }  // omp parallel
   }  // schedule
@@ -740,24 +910,35 @@ int po_upload_dofs(Ctx* c, int field, int64_t n, const int32_t* cd) {
     c->np = n;
     c->nloc_p = 1 << dim;
     c->cd_p.assign(cd, cd + c->n_cells * c->nloc_p);
+    c->cp = Lines();
   } else {
     c->nu = n;
     c->ns_u = (int)unit_support(dim, c->prm.degree_u).size() / dim;
     c->nloc_u = c->ns_u * dim;
     c->cd_u.assign(cd, cd + c->n_cells * c->nloc_u);
     c->u_cline.assign(n, -1);
+    c->line_dof.clear();
+    c->line_g.clear();
+    c->cu = Lines();
   }
+  c->setup_done = false;
   return 0;
 }
 
-int po_upload_constraints(Ctx* c, int field, int64_t nl, const int32_t* ld, const int64_t* eptr, const int32_t*, const double*,
+int po_upload_constraints(Ctx* c, int field, int64_t nl, const int32_t* ld, const int64_t* eptr, const int32_t* edof, const double* ew,
                           const double* inh) {
-  if (field != PE_FIELD_DISPLACEMENT) return nl == 0 ? 0 : fail(c, PE_ERR_UNSUPPORTED, "pressure constraints are hanging-node only (PS:71-78)");
-  if (eptr && eptr[nl] != 0) return fail(c, PE_ERR_UNSUPPORTED, "hanging-node lines not supported");
+  if (field == PE_FIELD_PRESSURE) {
+    if (!c->np) return fail(c, PE_ERR_STATE, "upload the pressure dofs first");
+    for (int64_t i = 0; i < nl; ++i)
+      if (inh && inh[i] != 0) return fail(c, PE_ERR_UNSUPPORTED, "pressure constraints are homogeneous hanging-node lines (PS:71-78)");
+    c->cp.set(c->np, nl, ld, eptr, edof, ew, inh);
+    return 0;
+  }
+  if (!c->nu) return fail(c, PE_ERR_STATE, "upload the displacement dofs first");
+  c->cu.set(c->nu, nl, ld, eptr, edof, ew, inh);
   c->line_dof.assign(ld, ld + nl);
-  c->line_g.assign(inh, inh + nl);
-  c->u_cline.assign(c->nu, -1);
-  for (int64_t i = 0; i < nl; ++i) c->u_cline[ld[i]] = (int32_t)i;
+  c->line_g = c->cu.g;
+  c->u_cline = c->cu.line_of;
   return 0;
 }
 
@@ -779,8 +960,13 @@ int po_setup(Ctx* c) {
   c->p_qu = c->geo_qu;
   c->u_q2 = make_shape(dim, c->prm.degree_u, c->q2.pts, c->q2.n);
   c->u_qu = make_shape(dim, c->prm.degree_u, c->qu.pts, c->qu.n);
-  c->Pp = make_pattern(c->np, c->n_cells, c->nloc_p, c->cd_p.data());
-  c->Pu = make_pattern(c->nu, c->n_cells, c->nloc_u, c->cd_u.data());
+  if (c->cp.any_entries() || c->cu.any_entries()) g_threads = 1;  // the vertex colouring of cell_schedule ignores master dofs
+  if (c->cp.line_of.empty()) c->cp.set(c->np, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+  if (c->cu.line_of.empty()) c->cu.set(c->nu, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+  c->Pp = c->cp.any_entries() ? make_pattern_constrained(c->np, c->n_cells, c->nloc_p, c->cd_p.data(), c->cp)
+                              : make_pattern(c->np, c->n_cells, c->nloc_p, c->cd_p.data());
+  c->Pu = c->cu.any_entries() ? make_pattern_constrained(c->nu, c->n_cells, c->nloc_u, c->cd_u.data(), c->cu)
+                              : make_pattern(c->nu, c->n_cells, c->nloc_u, c->cd_u.data());
   assemble_mass_laplace(*c);
   c->J.assign(c->Pp.nnz(), 0);
   c->n_stress = (dim * dim + dim) / 2;
@@ -827,6 +1013,7 @@ int po_pressure_assemble_residual(Ctx* c, double dt, double* l2) {  // PS:113-15
     c->resid[i] += c->frhs[i];
     c->resid[i] *= -1;
   }
+  c->cp.condense(c->resid);  // PS:153
   if (l2) *l2 = l2norm(c->resid);
   return 0;
 }
@@ -834,6 +1021,7 @@ int po_pressure_assemble_residual(Ctx* c, double dt, double* l2) {  // PS:113-15
 int po_pressure_assemble_jacobian(Ctx* c, double dt) {  // PS:158-169
   const double m = 1. / c->prm.m_modulus / dt, f = c->prm.perm_over_visc;
   for (int64_t i = 0; i < c->Pp.nnz(); ++i) c->J[i] = c->M[i] * m + f * c->K[i];
+  try { condense_matrix(c->Pp, c->cp, c->J); } catch (const std::exception& e) { return fail(c, PE_ERR_STATE, e.what()); }  // PS:168
   c->jac_dt = dt;
   return 0;
 }
@@ -841,6 +1029,7 @@ int po_pressure_assemble_jacobian(Ctx* c, double dt) {  // PS:158-169
 int po_pressure_solve(Ctx* c, int* its, double* res) {  // PS:172-185
   double tol = c->prm.cg_rel_tol_pressure * l2norm(c->resid);
   CgResult r = cg_solve(c->Pp, c->J, c->dp, c->resid, c->precond_kind < 0 ? c->omega_p : 0.0, c->prm.cg_max_iterations, tol);
+  c->cp.distribute(c->dp);  // PS:180
   c->st.cg_iterations_pressure += r.its;
   c->st.cg_solves_pressure++;
   if (its) *its = r.its;
@@ -855,7 +1044,7 @@ int po_displacement_assemble(Ctx* c) { displacement_assemble(*c); return 0; }
 
 int po_displacement_solve(Ctx* c, int* its, double* res) {  // DS:294-307
   CgResult r = cg_solve(c->Pu, c->A, c->u, c->b, c->precond_kind < 0 ? c->omega_u : 0.0, c->prm.cg_max_iterations, c->prm.cg_abs_tol_displacement);
-  for (size_t i = 0; i < c->line_dof.size(); ++i) c->u[c->line_dof[i]] = c->line_g[i];  // constraints.distribute
+  c->cu.distribute(c->u);  // constraints.distribute(solution), DS:306
   c->st.cg_iterations_displacement += r.its;
   c->st.cg_solves_displacement++;
   if (its) *its = r.its;
@@ -863,7 +1052,11 @@ int po_displacement_solve(Ctx* c, int* its, double* res) {  // DS:294-307
   return r.ok ? 0 : fail(c, std::isnan(r.res) ? PE_ERR_NAN : PE_ERR_NO_CONVERGENCE, "displacement CG: SolverControl::NoConvergence");
 }
 
-int po_project_assemble_matrix(Ctx* c) { c->PM = c->M; return 0; }  // SP:101-106
+int po_project_assemble_matrix(Ctx* c) {  // SP:101-106
+  c->PM = c->M;
+  try { condense_matrix(c->Pp, c->cp, c->PM); } catch (const std::exception& e) { return fail(c, PE_ERR_STATE, e.what()); }
+  return 0;
+}
 
 int po_project_assemble_rhs(Ctx* c, int n, const int32_t* comps) { projection_rhs(*c, n, comps); return 0; }
 
@@ -871,6 +1064,7 @@ int po_project_solve(Ctx* c, int entry, int* its) {  // SP:201-232
   if (c->PM.empty()) return fail(c, PE_ERR_STATE, "projection matrix not assembled");
   double tol = c->prm.cg_rel_tol_projection * l2norm(c->proj_rhs[entry]);
   CgResult r = cg_solve(c->Pp, c->PM, c->strains[entry], c->proj_rhs[entry], c->precond_kind < 0 ? c->omega_m : 0.0, c->prm.cg_max_iterations, tol);
+  c->cp.distribute(c->strains[entry]);  // SP:215
   c->st.cg_iterations_projection += r.its;
   c->st.cg_solves_projection++;
   if (its) *its = r.its;
@@ -919,6 +1113,7 @@ static const Pattern* mat_by_id(Ctx& C, int m, const Vec** val) {
     case PE_MAT_LAPLACE: *val = &C.K; return &C.Pp;
     case PE_MAT_JACOBIAN: *val = &C.J; return &C.Pp;
     case PE_MAT_ELASTICITY: *val = &C.A; return &C.Pu;
+    case PE_MAT_PROJECTION: *val = &C.PM; return &C.Pp;
   }
   return nullptr;
 }

@@ -24,7 +24,7 @@ FIELD_PRESSURE, FIELD_DISPLACEMENT = 0, 1
 PRECOND_JACOBI, PRECOND_CHEBYSHEV = 0, 1
 VEC_P, VEC_P_OLD, VEC_P_UPDATE, VEC_P_RESIDUAL, VEC_VOL_STRAIN, VEC_VOL_STRAIN0, VEC_WELL_RHS, VEC_U, VEC_U_RHS = range(9)
 VEC_STRAIN0, VEC_PROJ_RHS0, VEC_STRESS0 = 16, 32, 48
-MAT_MASS, MAT_LAPLACE, MAT_JACOBIAN, MAT_ELASTICITY = 0, 1, 2, 3
+MAT_MASS, MAT_LAPLACE, MAT_JACOBIAN, MAT_ELASTICITY, MAT_PROJECTION = 0, 1, 2, 3, 4
 
 i32p = C.POINTER(C.c_int32)
 i64p = C.POINTER(C.c_int64)
@@ -89,6 +89,11 @@ class DofsView(C.Structure):
     _fields_ = [("degree", C.c_int32), ("n_comp", C.c_int32), ("n_loc", C.c_int32), ("reserved", C.c_int32), ("n_dofs", C.c_int64), ("cell_dofs", i32p)]
 
 
+class ConstraintsView(C.Structure):
+    _fields_ = [("n_lines", C.c_int64), ("n_entries", C.c_int64), ("line_dof", i32p), ("entry_ptr", i64p), ("entry_dof", i32p),
+                ("entry_w", f64p), ("inhomogeneity", f64p)]
+
+
 class PartFieldView(C.Structure):
     _fields_ = [
         ("n_owned", C.c_int64), ("n_local", C.c_int64), ("n_neighbors", C.c_int32), ("reserved", C.c_int32),
@@ -125,6 +130,9 @@ HOST_SYMBOLS = [
     "peh_last_error", "peh_input_create", "peh_input_destroy", "peh_input_read_file", "peh_input_read_string", "peh_input_view_get",
     "peh_input_to_params", "peh_mesh_create_rectangle", "peh_mesh_create_subdivided", "peh_mesh_read_msh", "peh_mesh_destroy",
     "peh_mesh_view_get", "peh_dofs_distribute", "peh_dofs_destroy", "peh_dofs_view_get", "peh_dofs_support_points", "peh_make_dirichlet",
+    "peh_forest_create", "peh_forest_destroy", "peh_forest_active_mesh", "peh_forest_active_levels", "peh_forest_set_flags",
+    "peh_forest_get_flags", "peh_forest_prepare", "peh_forest_execute", "peh_forest_kelly", "peh_forest_mark_fixed_fraction",
+    "peh_forest_store", "peh_forest_fetch", "peh_constraints_make", "peh_constraints_destroy", "peh_constraints_view_get",
     "peh_partition", "peh_part_destroy", "peh_part_view_get", "peh_problem_create", "peh_problem_destroy", "peh_problem_initialize",
     "peh_problem_step", "peh_problem_run", "peh_problem_ctx", "peh_problem_mesh", "peh_problem_global_ids",
 ]
@@ -239,6 +247,26 @@ def load_host():
     lib.peh_dofs_support_points.argtypes = [P, P, f64p]
     lib.peh_make_dirichlet.argtypes = [P, P, C.c_int, i32p, i32p, f64p, i32p, f64p]
     lib.peh_make_dirichlet.restype = C.c_int64
+    f32p = C.POINTER(C.c_float)
+    lib.peh_forest_create.argtypes = [P, C.c_int]
+    lib.peh_forest_create.restype = P
+    lib.peh_forest_destroy.argtypes = [P]
+    lib.peh_forest_active_mesh.argtypes = [P]
+    lib.peh_forest_active_mesh.restype = P
+    lib.peh_forest_active_levels.argtypes = [P, i32p]
+    lib.peh_forest_active_levels.restype = C.c_int64
+    lib.peh_forest_set_flags.argtypes = [P, C.c_int64, i8p, i8p]
+    lib.peh_forest_get_flags.argtypes = [P, C.c_int64, i8p, i8p]
+    lib.peh_forest_prepare.argtypes = [P]
+    lib.peh_forest_execute.argtypes = [P, i32p, i32p]
+    lib.peh_forest_kelly.argtypes = [P, P, P, f64p, f32p]
+    lib.peh_forest_mark_fixed_fraction.argtypes = [P, C.c_int64, f32p, C.c_double, C.c_double, C.c_int, C.c_int]
+    lib.peh_forest_store.argtypes = [P, P, P, C.c_int, f64p]
+    lib.peh_forest_fetch.argtypes = [P, P, P, C.c_int, f64p]
+    lib.peh_constraints_make.argtypes = [P, P, P, C.c_int, i32p, i32p, f64p]
+    lib.peh_constraints_make.restype = P
+    lib.peh_constraints_destroy.argtypes = [P]
+    lib.peh_constraints_view_get.argtypes = [P, C.POINTER(ConstraintsView)]
     lib.peh_partition.argtypes = [P, P, P, C.c_int, C.c_int]
     lib.peh_partition.restype = P
     lib.peh_part_destroy.argtypes = [P]
@@ -364,6 +392,112 @@ def make_dirichlet(mesh: HostMesh, dofs: HostDofs, labels, comps, values):
     return ld, g
 
 
+class ConstraintLines:
+    """Closed constraint table x_i = sum_j w_ij x_j + g_i in the flat form of pe_upload_constraints."""
+
+    def __init__(self, line_dof, entry_ptr, entry_dof, entry_w, inhomogeneity):
+        self.line_dof = np.asarray(line_dof, dtype=np.int32)
+        self.entry_ptr = np.asarray(entry_ptr, dtype=np.int64)
+        self.entry_dof = np.asarray(entry_dof, dtype=np.int32)
+        self.entry_w = np.asarray(entry_w, dtype=np.float64)
+        self.inhomogeneity = np.asarray(inhomogeneity, dtype=np.float64)
+
+    @property
+    def n_lines(self):
+        return len(self.line_dof)
+
+    def line(self, i):
+        a, b = self.entry_ptr[i], self.entry_ptr[i + 1]
+        return self.line_dof[i], self.entry_dof[a:b], self.entry_w[a:b], self.inhomogeneity[i]
+
+
+def make_constraints(forest, mesh: "HostMesh", dofs: "HostDofs", labels=(), comps=(), values=()) -> ConstraintLines:
+    """make_hanging_node_constraints (when `forest` is given) + Dirichlet lines + close (PS:71-78, DS:109-137)."""
+    lib = load_host()
+    l = np.asarray(labels, dtype=np.int32)
+    c = np.asarray(comps, dtype=np.int32)
+    v = np.asarray(values, dtype=np.float64)
+    h = lib.peh_constraints_make(forest.h if forest is not None else None, mesh.h, dofs.h, len(l), _p(l, C.c_int32), _p(c, C.c_int32), _p(v, C.c_double))
+    if not h:
+        raise HostError(lib.peh_last_error().decode())
+    view = ConstraintsView()
+    lib.peh_constraints_view_get(h, C.byref(view))
+    out = ConstraintLines(_np(view.line_dof, view.n_lines, np.int32), _np(view.entry_ptr, view.n_lines + 1, np.int64),
+                          _np(view.entry_dof, view.n_entries, np.int32), _np(view.entry_w, view.n_entries, np.float64),
+                          _np(view.inhomogeneity, view.n_lines, np.float64))
+    lib.peh_constraints_destroy(h)
+    return out
+
+
+class Forest:
+    """Refinement forest of the adaptive time loop (FSS:333-340, 447-498; csrc/host/amr.hpp)."""
+
+    def __init__(self, mesh: "HostMesh", base_level=0):
+        lib = load_host()
+        self.lib = lib
+        self.h = lib.peh_forest_create(mesh.h, base_level)
+        if not self.h:
+            raise HostError(lib.peh_last_error().decode())
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise HostError(self.lib.peh_last_error().decode())
+
+    def active_mesh(self) -> "HostMesh":
+        return HostMesh(self.lib.peh_forest_active_mesh(self.h))
+
+    def levels(self):
+        n = self.lib.peh_forest_active_levels(self.h, None)
+        out = np.zeros(n, dtype=np.int32)
+        self.lib.peh_forest_active_levels(self.h, _p(out, C.c_int32))
+        return out
+
+    def set_flags(self, refine=None, coarsen=None):
+        n = self.lib.peh_forest_active_levels(self.h, None)
+        r = np.zeros(n, dtype=np.int8) if refine is None else np.ascontiguousarray(refine, dtype=np.int8)
+        c = np.zeros(n, dtype=np.int8) if coarsen is None else np.ascontiguousarray(coarsen, dtype=np.int8)
+        self._ck(self.lib.peh_forest_set_flags(self.h, n, r.ctypes.data_as(i8p), c.ctypes.data_as(i8p)))
+
+    def get_flags(self):
+        n = self.lib.peh_forest_active_levels(self.h, None)
+        r = np.zeros(n, dtype=np.int8)
+        c = np.zeros(n, dtype=np.int8)
+        self._ck(self.lib.peh_forest_get_flags(self.h, n, r.ctypes.data_as(i8p), c.ctypes.data_as(i8p)))
+        return r.astype(bool), c.astype(bool)
+
+    def prepare(self):
+        self._ck(self.lib.peh_forest_prepare(self.h))
+
+    def execute(self):
+        nc, nr = C.c_int32(), C.c_int32()
+        self._ck(self.lib.peh_forest_execute(self.h, C.byref(nc), C.byref(nr)))
+        return nc.value, nr.value
+
+    def kelly(self, mesh: "HostMesh", dofs_p: "HostDofs", p):
+        pp = np.ascontiguousarray(p, dtype=np.float64)
+        eta = np.zeros(mesh.arrays.n_cells, dtype=np.float32)
+        self._ck(self.lib.peh_forest_kelly(self.h, mesh.h, dofs_p.h, _p(pp, C.c_double), eta.ctypes.data_as(C.POINTER(C.c_float))))
+        return eta
+
+    def mark_fixed_fraction(self, criteria, top, bottom, min_level, max_level):
+        cr = np.ascontiguousarray(criteria, dtype=np.float32)
+        self._ck(self.lib.peh_forest_mark_fixed_fraction(self.h, len(cr), cr.ctypes.data_as(C.POINTER(C.c_float)), top, bottom, min_level, max_level))
+
+    def store(self, mesh: "HostMesh", dofs_p: "HostDofs", vectors):
+        v = np.ascontiguousarray(np.stack([np.asarray(x, dtype=np.float64) for x in vectors]))
+        self._ck(self.lib.peh_forest_store(self.h, mesh.h, dofs_p.h, v.shape[0], _p(v, C.c_double)))
+
+    def fetch(self, mesh: "HostMesh", dofs_p: "HostDofs", n_vec):
+        out = np.zeros((n_vec, dofs_p.n_dofs))
+        self._ck(self.lib.peh_forest_fetch(self.h, mesh.h, dofs_p.h, n_vec, _p(out, C.c_double)))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.peh_forest_destroy(self.h)
+            self.h = None
+
+
 class InputData:
     """InputDataPoroel (ID:28-72) through the host library's parser."""
 
@@ -451,6 +585,12 @@ class OperatorBackend:
         g = np.ascontiguousarray(inhom, dtype=np.float64)
         ep = np.zeros(len(ld) + 1, dtype=np.int64)
         self._ck(self._f("upload_constraints")(self.ctx, field, len(ld), _p(ld, C.c_int32), _p(ep, C.c_int64), None, None, _p(g, C.c_double)),
+                 "upload_constraints")
+
+    def upload_constraint_lines(self, field, L: "ConstraintLines"):
+        """General lines (hanging nodes + Dirichlet), PS:71-78 / DS:109-137."""
+        self._ck(self._f("upload_constraints")(self.ctx, field, L.n_lines, _p(L.line_dof, C.c_int32), _p(L.entry_ptr, C.c_int64),
+                                               _p(L.entry_dof, C.c_int32), _p(L.entry_w, C.c_double), _p(L.inhomogeneity, C.c_double)),
                  "upload_constraints")
 
     def upload_neumann(self, labels, comps, values):

@@ -1,0 +1,653 @@
+// amr.hpp — adaptive refinement of the time loop (PoroelasticityFSS.h:333-340, 447-498) without deal.II.
+//
+// What the reference gets from deal.II and what stands in for it here:
+//   Triangulation<dim> + execute_coarsening_and_refinement ... Forest: a quadtree/octree forest over the cells of the
+//       initial mesh (isotropic refinement, children in lexicographic order, boundary ids inherited).  Vertices,
+//       lines and quads are identified by their vertex numbers, so the same code serves the colorized box
+//       (FSS:418-435) and Gmsh meshes (FSS:438-445) whatever the relative orientation of neighbouring cells.
+//   prepare_coarsening_and_refinement (no mesh smoothing: `Triangulation<dim> triangulation;`, FSS:75) ... Forest::prepare:
+//       a family is coarsened only if all of its children are active and flagged; after refinement and coarsening two
+//       cells that share a line (2D: a face; 3D: a face or an edge) differ by at most one level; refinement wins over
+//       coarsening.  The closure is the smallest flag set with these properties, hence unique.
+//   DoFTools::make_hanging_node_constraints (PS:74-75, DS:112-113) ... hanging_node_constraints() for FE_Q(1|2)^n_comp.
+//   KellyErrorEstimator<dim>::estimate (FSS:454-458) ... kelly_estimate(): eta_K^2 = h_K/24 sum_F int_F [dp/dn]^2,
+//       QGauss<dim-1>(2), no Neumann function map (boundary faces contribute nothing), result stored as float.
+//   GridRefinement::refine_and_coarsen_fixed_fraction(0.6, 0.4) + the level limits of FSS:463-472 ... mark_fixed_fraction().
+//   SolutionTransfer<dim>::interpolate for the FE_Q(1) pressure handler (FSS:475-497) ... vertex-keyed transfer: a dof that
+//       exists before and after keeps its value, a vertex created by refinement gets the parent's Q1 interpolant.
+// Stated deviations: active cells are ordered by (level, creation index) — deal.II re-uses the storage of coarsened
+// cells, so the order inside a level can differ after coarsening (results are compared by coordinates); new vertices of
+// curved/distorted parents are placed at the mean of the parent entity's vertices.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <numeric>
+#include <stdexcept>
+#include <vector>
+
+#include "dofs.hpp"
+#include "mesh.hpp"
+
+namespace amr {
+
+struct Cell {
+  int32_t level = 0, parent = -1, child0 = -1, center_v = -1;
+  int8_t child_index = 0;
+  bool active = true, dead = false, refine_flag = false, coarsen_flag = false;
+  int32_t v[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+  int32_t bid[6] = {-1, -1, -1, -1, -1, -1};  // boundary id per face, -1 = interior
+};
+
+struct Forest {
+  int dim = 0;
+  std::vector<double> xyz;  // every vertex ever created (unused ones are harmless)
+  std::vector<Cell> cells;
+  dofs::EntityMap edge_mid, face_mid;  // line / quad (3D) -> midpoint vertex
+  // vertex-keyed payload of the solution transfer (FSS:475-497)
+  int n_transfer = 0;
+  std::vector<double> vval;     // n_vertices * n_transfer
+  std::vector<uint8_t> vknown;  // vertex carried a dof of the old mesh
+
+  int vpc() const { return 1 << dim; }
+  int64_t n_vertices() const { return (int64_t)xyz.size() / dim; }
+
+  static Forest from_mesh(const mesh::Mesh& m, int base_level) {
+    Forest F;
+    F.dim = m.dim;
+    F.xyz = m.xyz;
+    const int vpc = m.vpc();
+    F.cells.resize(m.n_cells());
+    for (int64_t c = 0; c < m.n_cells(); ++c) {
+      F.cells[c].level = base_level;
+      for (int k = 0; k < vpc; ++k) F.cells[c].v[k] = m.cell_vertices[c * vpc + k];
+    }
+    for (int64_t b = 0; b < m.n_bfaces(); ++b) F.cells[m.bface_cell[b]].bid[m.bface_local[b]] = m.bface_id[b];
+    return F;
+  }
+
+  // active cells in deal.II's iteration order: level by level
+  std::vector<int32_t> active_cells() const {
+    std::vector<int32_t> a;
+    for (size_t i = 0; i < cells.size(); ++i)
+      if (cells[i].active && !cells[i].dead) a.push_back((int32_t)i);
+    std::stable_sort(a.begin(), a.end(), [&](int32_t x, int32_t y) { return cells[x].level < cells[y].level; });
+    return a;
+  }
+  int n_levels() const {
+    int l = 0;
+    for (auto& c : cells)
+      if (c.active && !c.dead) l = std::max(l, c.level + 1);
+    return l;
+  }
+
+  mesh::Mesh active_mesh(std::vector<int32_t>* ids = nullptr) const {
+    mesh::Mesh m;
+    m.dim = dim;
+    m.xyz = xyz;
+    std::vector<int32_t> a = active_cells();
+    const int nv = vpc();
+    m.cell_vertices.resize(a.size() * nv);
+    for (size_t i = 0; i < a.size(); ++i) {
+      const Cell& c = cells[a[i]];
+      for (int k = 0; k < nv; ++k) m.cell_vertices[i * nv + k] = c.v[k];
+      for (int f = 0; f < 2 * dim; ++f)
+        if (c.bid[f] >= 0) {
+          m.bface_cell.push_back((int32_t)i);
+          m.bface_local.push_back((int8_t)f);
+          m.bface_id.push_back(c.bid[f]);
+        }
+    }
+    if (ids) *ids = a;
+    return m;
+  }
+
+  int32_t new_vertex(const int32_t* corners, int n) {
+    const int32_t id = (int32_t)n_vertices();
+    for (int a = 0; a < dim; ++a) {
+      double s = 0;
+      for (int k = 0; k < n; ++k) s += xyz[(int64_t)corners[k] * dim + a];
+      xyz.push_back(s / n);
+    }
+    if (n_transfer) {
+      vval.resize((size_t)(id + 1) * n_transfer, 0.0);
+      vknown.resize(id + 1, 0);
+    }
+    return id;
+  }
+
+  // vertex of the 3^dim refinement lattice of cell c; idx[a] in {0,1,2}
+  int32_t lattice_vertex(int32_t c, const int idx[3]) {
+    int32_t corners[8];
+    int n = 0;
+    for (int k = 0; k < vpc(); ++k) {
+      bool ok = true;
+      for (int a = 0; a < dim; ++a) {
+        const int bit = (k >> a) & 1;
+        if ((idx[a] == 0 && bit) || (idx[a] == 2 && !bit)) ok = false;
+      }
+      if (ok) corners[n++] = cells[c].v[k];
+    }
+    if (n == 1) return corners[0];
+    if (n == 2) {
+      auto key = dofs::edge_key(corners[0], corners[1]);
+      auto it = edge_mid.find(key);
+      if (it != edge_mid.end()) return it->second;
+      int32_t id = new_vertex(corners, 2);
+      edge_mid[key] = id;
+      return id;
+    }
+    if (n == 4 && dim == 3) {
+      auto key = dofs::quad_key(corners[0], corners[1], corners[2], corners[3]);
+      auto it = face_mid.find(key);
+      if (it != face_mid.end()) return it->second;
+      int32_t id = new_vertex(corners, 4);
+      face_mid[key] = id;
+      return id;
+    }
+    if (cells[c].center_v < 0) {
+      const int32_t id = new_vertex(corners, n);
+      cells[c].center_v = id;
+    }
+    return cells[c].center_v;
+  }
+
+  void refine_cell(int32_t c) {
+    if (!cells[c].active || cells[c].dead) throw std::runtime_error("amr: refine of a non-active cell");
+    const int nv = vpc();
+    const int32_t first = (int32_t)cells.size();
+    std::vector<Cell> kids(nv);
+    for (int ci = 0; ci < nv; ++ci) {
+      Cell& k = kids[ci];
+      k.level = cells[c].level + 1;
+      k.parent = c;
+      k.child_index = (int8_t)ci;
+      for (int v = 0; v < nv; ++v) {
+        int idx[3] = {0, 0, 0};
+        for (int a = 0; a < dim; ++a) idx[a] = ((ci >> a) & 1) + ((v >> a) & 1);
+        k.v[v] = lattice_vertex(c, idx);
+      }
+      for (int f = 0; f < 2 * dim; ++f) k.bid[f] = (((ci >> (f / 2)) & 1) == (f % 2)) ? cells[c].bid[f] : -1;
+    }
+    // solution transfer: vertices that carried no dof get the parent's Q1 interpolant (mean of the parent entity)
+    if (n_transfer)
+      for (int i = 0; i < (dim == 2 ? 9 : 27); ++i) {
+        int idx[3] = {i % 3, (i / 3) % 3, dim == 3 ? i / 9 : 0};
+        const int32_t v = lattice_vertex(c, idx);
+        if (vknown[v]) continue;
+        int n = 0;
+        std::vector<double> acc(n_transfer, 0.0);
+        for (int k = 0; k < nv; ++k) {
+          bool ok = true;
+          for (int a = 0; a < dim; ++a) {
+            const int bit = (k >> a) & 1;
+            if ((idx[a] == 0 && bit) || (idx[a] == 2 && !bit)) ok = false;
+          }
+          if (!ok) continue;
+          ++n;
+          for (int t = 0; t < n_transfer; ++t) acc[t] += vval[(size_t)cells[c].v[k] * n_transfer + t];
+        }
+        for (int t = 0; t < n_transfer; ++t) vval[(size_t)v * n_transfer + t] = acc[t] / n;
+        vknown[v] = 2;  // interpolated in this pass: may serve as a source for nothing else (one level per pass)
+      }
+    cells[c].active = false;
+    cells[c].child0 = first;
+    for (auto& k : kids) cells.push_back(k);
+  }
+
+  void coarsen_cell(int32_t p) {
+    const int nv = vpc();
+    for (int k = 0; k < nv; ++k) {
+      Cell& ch = cells[cells[p].child0 + k];
+      ch.active = false;
+      ch.dead = true;
+    }
+    cells[p].child0 = -1;
+    cells[p].active = true;
+  }
+
+  bool has_active_children_only(int32_t p) const {
+    if (cells[p].child0 < 0) return false;
+    for (int k = 0; k < vpc(); ++k) {
+      const Cell& ch = cells[cells[p].child0 + k];
+      if (!ch.active || ch.dead) return false;
+    }
+    return true;
+  }
+
+  // pairs of active cells that share a line or half a line (2D: faces; 3D: faces and edges)
+  std::vector<std::pair<int32_t, int32_t>> line_adjacency() const {
+    dofs::RefElement ref = dofs::make_ref_element(dim, 1);
+    std::unordered_map<dofs::EntityKey, std::vector<int32_t>, dofs::PairHash> by_line;
+    for (size_t i = 0; i < cells.size(); ++i) {
+      const Cell& c = cells[i];
+      if (!c.active || c.dead) continue;
+      for (auto& l : ref.lines) by_line[dofs::edge_key(c.v[l[0]], c.v[l[1]])].push_back((int32_t)i);
+    }
+    std::vector<std::pair<int32_t, int32_t>> pairs;
+    for (auto& kv : by_line) {
+      const auto& g = kv.second;
+      for (size_t i = 0; i < g.size(); ++i)
+        for (size_t j = i + 1; j < g.size(); ++j) pairs.push_back({g[i], g[j]});
+      auto mid = edge_mid.find(kv.first);
+      if (mid == edge_mid.end()) continue;
+      const int64_t ends[2] = {kv.first.first, kv.first.second};
+      for (int e = 0; e < 2; ++e) {
+        auto half = by_line.find(dofs::edge_key(ends[e], mid->second));
+        if (half == by_line.end()) continue;
+        for (int32_t x : g)
+          for (int32_t y : half->second) pairs.push_back({x, y});
+      }
+    }
+    std::sort(pairs.begin(), pairs.end());
+    pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+    return pairs;
+  }
+
+  void clear_family_coarsen(int32_t c) {
+    const int32_t p = cells[c].parent;
+    if (p < 0 || cells[p].child0 < 0) { cells[c].coarsen_flag = false; return; }
+    for (int k = 0; k < vpc(); ++k) cells[cells[p].child0 + k].coarsen_flag = false;
+  }
+
+  // Triangulation::prepare_coarsening_and_refinement (FSS:481)
+  void prepare() {
+    auto pairs = line_adjacency();
+    bool changed = true;
+    while (changed) {
+      changed = false;
+      for (size_t i = 0; i < cells.size(); ++i) {
+        Cell& c = cells[i];
+        if (!c.active || c.dead) { c.refine_flag = c.coarsen_flag = false; continue; }
+        if (c.refine_flag && c.coarsen_flag) { c.coarsen_flag = false; changed = true; }
+        if (c.coarsen_flag && c.parent < 0) { c.coarsen_flag = false; changed = true; }
+      }
+      // a family is coarsened as a whole or not at all
+      for (size_t p = 0; p < cells.size(); ++p) {
+        if (cells[p].dead || cells[p].active || cells[p].child0 < 0) continue;
+        int n_flag = 0, n_ok = 0;
+        for (int k = 0; k < vpc(); ++k) {
+          const Cell& ch = cells[cells[p].child0 + k];
+          if (ch.active && !ch.dead) ++n_ok;
+          if (ch.active && ch.coarsen_flag) ++n_flag;
+        }
+        if (n_flag > 0 && (n_flag < vpc() || n_ok < vpc())) {
+          for (int k = 0; k < vpc(); ++k) cells[cells[p].child0 + k].coarsen_flag = false;
+          changed = true;
+        }
+      }
+      auto future = [&](int32_t c) { return cells[c].level + (cells[c].refine_flag ? 1 : 0) - (cells[c].coarsen_flag ? 1 : 0); };
+      for (auto& pr : pairs)
+        for (int s = 0; s < 2; ++s) {
+          const int32_t hi = s ? pr.second : pr.first, lo = s ? pr.first : pr.second;
+          if (future(hi) - future(lo) <= 1) continue;
+          if (cells[lo].coarsen_flag) clear_family_coarsen(lo);
+          else cells[lo].refine_flag = true;
+          changed = true;
+        }
+    }
+  }
+
+  // Triangulation::execute_coarsening_and_refinement (FSS:483); returns {n_coarsened_families, n_refined}
+  std::pair<int, int> execute() {
+    prepare();
+    int nc = 0, nr = 0;
+    const size_t n0 = cells.size();
+    for (size_t p = 0; p < n0; ++p) {
+      if (cells[p].dead || cells[p].active || !has_active_children_only((int32_t)p)) continue;
+      bool all = true;
+      for (int k = 0; k < vpc(); ++k) all = all && cells[cells[p].child0 + k].coarsen_flag;
+      if (all) { coarsen_cell((int32_t)p); ++nc; }
+    }
+    std::vector<int32_t> todo;
+    for (size_t i = 0; i < n0; ++i)
+      if (cells[i].active && !cells[i].dead && cells[i].refine_flag) todo.push_back((int32_t)i);
+    for (int32_t c : todo) { refine_cell(c); ++nr; }
+    for (auto& c : cells) c.refine_flag = c.coarsen_flag = false;
+    return {nc, nr};
+  }
+
+  // ---- solution transfer of FE_Q(1) fields keyed by vertex (FSS:475-497)
+  void store_vertex_values(const mesh::Mesh& m, const dofs::DofMap& dp, int n_vec, const double* const* vec) {
+    if (dp.degree != 1 || dp.n_comp != 1) throw std::runtime_error("amr: the transfer handles the FE_Q(1) pressure handler only (FSS:475)");
+    n_transfer = n_vec;
+    vval.assign((size_t)n_vertices() * n_vec, 0.0);
+    vknown.assign(n_vertices(), 0);
+    const int nv = vpc();
+    for (int64_t c = 0; c < m.n_cells(); ++c)
+      for (int k = 0; k < nv; ++k) {
+        const int32_t v = m.cell_vertices[c * nv + k], d = dp.cell_dofs[c * nv + k];
+        vknown[v] = 1;
+        for (int t = 0; t < n_vec; ++t) vval[(size_t)v * n_vec + t] = vec[t][d];
+      }
+  }
+  void fetch_vertex_values(const mesh::Mesh& m, const dofs::DofMap& dp, int n_vec, double* const* vec) const {
+    if (n_vec != n_transfer) throw std::runtime_error("amr: fetch without a matching store");
+    const int nv = vpc();
+    for (int64_t c = 0; c < m.n_cells(); ++c)
+      for (int k = 0; k < nv; ++k) {
+        const int32_t v = m.cell_vertices[c * nv + k], d = dp.cell_dofs[c * nv + k];
+        if (!vknown[v]) throw std::runtime_error("amr: vertex without a transferred value");
+        for (int t = 0; t < n_vec; ++t) vec[t][d] = vval[(size_t)v * n_vec + t];
+      }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// DoFTools::make_hanging_node_constraints for FE_Q(1|2)^n_comp on the active mesh of F
+// ------------------------------------------------------------------------------------------------
+inline void q2_weights_1d(double x, double w[3]) {  // nodes 0, 1/2, 1
+  w[0] = 2 * x * x - 3 * x + 1;
+  w[1] = 4 * x * (1 - x);
+  w[2] = 2 * x * x - x;
+}
+
+inline void hanging_node_constraints(const Forest& F, const mesh::Mesh& m, const dofs::DofMap& d, const dofs::NodeMaps& maps,
+                                     dofs::ConstraintTable& T) {
+  const int dim = F.dim, vpc = 1 << dim, nc = d.n_comp;
+  dofs::RefElement ref = dofs::make_ref_element(dim, 1);
+  std::vector<uint8_t> used(F.n_vertices(), 0);
+  for (int64_t c = 0; c < m.n_cells(); ++c)
+    for (int k = 0; k < vpc; ++k) used[m.cell_vertices[c * vpc + k]] = 1;
+  auto line_dof = [&](int64_t a, int64_t b) {
+    auto it = maps.line_dof.find(dofs::edge_key(a, b));
+    return it == maps.line_dof.end() ? -1 : it->second;
+  };
+  auto add = [&](int32_t base, const std::vector<std::pair<int32_t, double>>& e) {  // same weights for every component
+    if (base < 0) return;
+    for (int k = 0; k < nc; ++k) {
+      std::vector<std::pair<int32_t, double>> ek;
+      for (auto& x : e)
+        if (x.second != 0.0) ek.push_back({x.first + k, x.second});
+      T.add_line(base + k, ek, 0.0);
+    }
+  };
+  for (int64_t c = 0; c < m.n_cells(); ++c) {
+    const int32_t* cv = &m.cell_vertices[c * vpc];
+    // lines of the cell whose midpoint is a vertex of finer active cells
+    for (auto& l : ref.lines) {
+      const int32_t a = cv[l[0]], b = cv[l[1]];
+      auto it = F.edge_mid.find(dofs::edge_key(a, b));
+      if (it == F.edge_mid.end() || !used[it->second]) continue;
+      const int32_t mv = it->second;
+      if (d.degree == 1) {
+        add(maps.vdof[mv], {{maps.vdof[a], 0.5}, {maps.vdof[b], 0.5}});
+      } else {
+        const int32_t L = line_dof(a, b);
+        add(maps.vdof[mv], {{L, 1.0}});
+        add(line_dof(a, mv), {{maps.vdof[a], 0.375}, {L, 0.75}, {maps.vdof[b], -0.125}});
+        add(line_dof(mv, b), {{maps.vdof[a], -0.125}, {L, 0.75}, {maps.vdof[b], 0.375}});
+      }
+    }
+    if (dim != 3) continue;
+    // quads of the cell that are refined on the other side
+    for (auto& q : ref.quads) {
+      const int32_t f[4] = {cv[q[0]], cv[q[1]], cv[q[2]], cv[q[3]]};  // lexicographic in the face frame
+      auto it = F.face_mid.find(dofs::quad_key(f[0], f[1], f[2], f[3]));
+      if (it == F.face_mid.end() || !used[it->second]) continue;
+      const int32_t fc = it->second;
+      if (d.degree == 1) {
+        add(maps.vdof[fc], {{maps.vdof[f[0]], 0.25}, {maps.vdof[f[1]], 0.25}, {maps.vdof[f[2]], 0.25}, {maps.vdof[f[3]], 0.25}});
+        continue;
+      }
+      // 3 x 3 lattice of fine vertices on the coarse face and the 9 coarse face dofs, both indexed (i, j) in {0,1,2}^2
+      auto emid = [&](int32_t a, int32_t b) { return F.edge_mid.at(dofs::edge_key(a, b)); };
+      int32_t P[3][3];
+      P[0][0] = f[0]; P[2][0] = f[1]; P[0][2] = f[2]; P[2][2] = f[3];
+      P[1][0] = emid(f[0], f[1]); P[1][2] = emid(f[2], f[3]); P[0][1] = emid(f[0], f[2]); P[2][1] = emid(f[1], f[3]);
+      P[1][1] = fc;
+      int32_t D[3][3];
+      D[0][0] = maps.vdof[f[0]]; D[2][0] = maps.vdof[f[1]]; D[0][2] = maps.vdof[f[2]]; D[2][2] = maps.vdof[f[3]];
+      D[1][0] = line_dof(f[0], f[1]); D[1][2] = line_dof(f[2], f[3]); D[0][1] = line_dof(f[0], f[2]); D[2][1] = line_dof(f[1], f[3]);
+      {
+        auto qit = maps.quad_dof.find(dofs::quad_key(f[0], f[1], f[2], f[3]));
+        D[1][1] = qit == maps.quad_dof.end() ? -1 : qit->second;
+      }
+      auto constrain = [&](int32_t base, double xi, double eta) {
+        double wx[3], wy[3];
+        q2_weights_1d(xi, wx);
+        q2_weights_1d(eta, wy);
+        std::vector<std::pair<int32_t, double>> e;
+        for (int j = 0; j < 3; ++j)
+          for (int i = 0; i < 3; ++i)
+            if (wx[i] * wy[j] != 0.0) e.push_back({D[i][j], wx[i] * wy[j]});
+        add(base, e);
+      };
+      constrain(maps.vdof[fc], 0.5, 0.5);
+      // the four child lines that meet at the face centre
+      constrain(line_dof(P[1][0], fc), 0.5, 0.25);
+      constrain(line_dof(fc, P[1][2]), 0.5, 0.75);
+      constrain(line_dof(P[0][1], fc), 0.25, 0.5);
+      constrain(line_dof(fc, P[2][1]), 0.75, 0.5);
+      // the four child quads
+      for (int j = 0; j < 2; ++j)
+        for (int i = 0; i < 2; ++i) {
+          auto qit = maps.quad_dof.find(dofs::quad_key(P[i][j], P[i + 1][j], P[i][j + 1], P[i + 1][j + 1]));
+          if (qit != maps.quad_dof.end()) constrain(qit->second, 0.25 + 0.5 * i, 0.25 + 0.5 * j);
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// KellyErrorEstimator<dim>::estimate for a scalar FE_Q(1) field given per vertex
+// ------------------------------------------------------------------------------------------------
+namespace detail {
+
+inline double det_inv_T(int dim, const double* J, double* JiT) {  // J[a*dim+b] = dx_a/dxi_b
+  if (dim == 2) {
+    const double det = J[0] * J[3] - J[1] * J[2];
+    JiT[0] = J[3] / det; JiT[1] = -J[2] / det; JiT[2] = -J[1] / det; JiT[3] = J[0] / det;
+    return det;
+  }
+  const double c00 = J[4] * J[8] - J[5] * J[7], c01 = J[5] * J[6] - J[3] * J[8], c02 = J[3] * J[7] - J[4] * J[6];
+  const double det = J[0] * c00 + J[1] * c01 + J[2] * c02;
+  JiT[0] = c00 / det; JiT[1] = c01 / det; JiT[2] = c02 / det;
+  JiT[3] = (J[2] * J[7] - J[1] * J[8]) / det; JiT[4] = (J[0] * J[8] - J[2] * J[6]) / det; JiT[5] = (J[1] * J[6] - J[0] * J[7]) / det;
+  JiT[6] = (J[1] * J[5] - J[2] * J[4]) / det; JiT[7] = (J[2] * J[3] - J[0] * J[5]) / det; JiT[8] = (J[0] * J[4] - J[1] * J[3]) / det;
+  return det;
+}
+
+// Q1 geometry and field gradient of one cell at a reference point
+inline double cell_gradient(const Forest& F, const Cell& c, const double* xi, const double* vertex_value, double* grad, double* JiT) {
+  const int dim = F.dim, vpc = 1 << dim;
+  double J[9] = {0}, gref[3] = {0, 0, 0};
+  for (int v = 0; v < vpc; ++v) {
+    double dN[3];
+    for (int a = 0; a < dim; ++a) {
+      double g = ((v >> a) & 1) ? 1.0 : -1.0;
+      for (int b = 0; b < dim; ++b)
+        if (b != a) g *= ((v >> b) & 1) ? xi[b] : 1 - xi[b];
+      dN[a] = g;
+    }
+    const double* X = &F.xyz[(int64_t)c.v[v] * dim];
+    for (int a = 0; a < dim; ++a) {
+      gref[a] += vertex_value[c.v[v]] * dN[a];
+      for (int b = 0; b < dim; ++b) J[a * dim + b] += X[a] * dN[b];
+    }
+  }
+  const double det = det_inv_T(dim, J, JiT);
+  for (int a = 0; a < dim; ++a) {
+    double s = 0;
+    for (int b = 0; b < dim; ++b) s += JiT[a * dim + b] * gref[b];
+    grad[a] = s;
+  }
+  return det;
+}
+
+// parametric position of vertex v inside face f of cell N (corner, line midpoint or face centre)
+inline bool face_param(const Forest& F, const Cell& N, int f, int32_t v, double out[2]) {
+  const int dim = F.dim, nfv = 1 << (dim - 1);
+  int fv[4];
+  mesh::face_vertices(dim, f, fv);
+  int32_t P[4];
+  for (int k = 0; k < nfv; ++k) P[k] = N.v[fv[k]];
+  for (int k = 0; k < nfv; ++k)
+    if (P[k] == v) { out[0] = k & 1; out[1] = (k >> 1) & 1; return true; }
+  for (int k1 = 0; k1 < nfv; ++k1)
+    for (int k2 = k1 + 1; k2 < nfv; ++k2) {
+      const int diff = k1 ^ k2;
+      if (diff != 1 && diff != 2) continue;
+      auto it = F.edge_mid.find(dofs::edge_key(P[k1], P[k2]));
+      if (it != F.edge_mid.end() && it->second == v) {
+        out[0] = 0.5 * ((k1 & 1) + (k2 & 1));
+        out[1] = 0.5 * (((k1 >> 1) & 1) + ((k2 >> 1) & 1));
+        return true;
+      }
+    }
+  if (dim == 3) {
+    auto it = F.face_mid.find(dofs::quad_key(P[0], P[1], P[2], P[3]));
+    if (it != F.face_mid.end() && it->second == v) { out[0] = out[1] = 0.5; return true; }
+  }
+  return false;
+}
+
+inline void embed_face_point(int dim, int f, const double* s, double* xi) {
+  const int axis = f / 2, side = f % 2;
+  int t = 0;
+  for (int a = 0; a < dim; ++a) xi[a] = (a == axis) ? (double)side : s[t++];
+}
+
+}  // namespace detail
+
+// vertex_value: one value per forest vertex (pressure dof of that vertex).  Returns eta per active cell, in the order
+// of Forest::active_cells(), rounded to float like the reference's Vector<float> (FSS:452).
+inline std::vector<float> kelly_estimate(const Forest& F, const std::vector<double>& vertex_value) {
+  const int dim = F.dim, nfv = 1 << (dim - 1);
+  std::vector<int32_t> act = F.active_cells();
+  std::vector<int32_t> pos(F.cells.size(), -1);
+  for (size_t i = 0; i < act.size(); ++i) pos[act[i]] = (int32_t)i;
+  auto face_key_of = [&](const Cell& c, int f) {
+    int fv[4];
+    mesh::face_vertices(dim, f, fv);
+    return dim == 2 ? dofs::edge_key(c.v[fv[0]], c.v[fv[1]]) : dofs::quad_key(c.v[fv[0]], c.v[fv[1]], c.v[fv[2]], c.v[fv[3]]);
+  };
+  std::unordered_map<dofs::EntityKey, std::vector<std::pair<int32_t, int>>, dofs::PairHash> active_face;
+  for (int32_t c : act)
+    for (int f = 0; f < 2 * dim; ++f) active_face[face_key_of(F.cells[c], f)].push_back({c, f});
+  // QGauss<dim-1>(2)
+  const double ga = 0.5 - 0.5 / std::sqrt(3.0), gb = 0.5 + 0.5 / std::sqrt(3.0);
+  std::vector<std::array<double, 2>> qp;
+  std::vector<double> qw;
+  if (dim == 2) { qp = {{ga, 0}, {gb, 0}}; qw = {0.5, 0.5}; }
+  else { qp = {{ga, ga}, {gb, ga}, {ga, gb}, {gb, gb}}; qw = {0.25, 0.25, 0.25, 0.25}; }
+  std::vector<double> sum(act.size(), 0.0);
+  auto integrate = [&](int32_t k, int f, int32_t n, int fn) {  // face f of K is (a part of) face fn of N
+    const Cell& K = F.cells[k];
+    const Cell& N = F.cells[n];
+    int fv[4];
+    mesh::face_vertices(dim, f, fv);
+    double par[4][2];
+    for (int i = 0; i < nfv; ++i)
+      if (!detail::face_param(F, N, fn, K.v[fv[i]], par[i])) throw std::runtime_error("amr: faces do not match (mesh not 2:1 balanced?)");
+    double integral = 0;
+    for (size_t q = 0; q < qp.size(); ++q) {
+      double xiK[3], xiN[3], sN[2] = {0, 0};
+      detail::embed_face_point(dim, f, qp[q].data(), xiK);
+      for (int i = 0; i < nfv; ++i) {
+        const double w = ((i & 1) ? qp[q][0] : 1 - qp[q][0]) * (dim == 3 ? (((i >> 1) & 1) ? qp[q][1] : 1 - qp[q][1]) : 1.0);
+        sN[0] += w * par[i][0];
+        sN[1] += w * par[i][1];
+      }
+      detail::embed_face_point(dim, fn, sN, xiN);
+      double gK[3], gN[3], JiT[9], JiTn[9];
+      const double det = detail::cell_gradient(F, K, xiK, vertex_value.data(), gK, JiT);
+      detail::cell_gradient(F, N, xiN, vertex_value.data(), gN, JiTn);
+      const int axis = f / 2;
+      double nv[3], nn = 0;
+      for (int a = 0; a < dim; ++a) { nv[a] = JiT[a * dim + axis]; nn += nv[a] * nv[a]; }
+      nn = std::sqrt(nn);
+      double jump = 0;
+      for (int a = 0; a < dim; ++a) jump += (gK[a] - gN[a]) * nv[a] / nn;
+      integral += jump * jump * std::fabs(det) * nn * qw[q];
+    }
+    sum[pos[k]] += integral;
+    sum[pos[n]] += integral;
+  };
+  for (int32_t k : act) {
+    const Cell& K = F.cells[k];
+    for (int f = 0; f < 2 * dim; ++f) {
+      if (K.bid[f] >= 0) continue;  // no Neumann function map at FSS:456: boundary faces contribute nothing
+      bool done = false;
+      for (auto& e : active_face[face_key_of(K, f)])
+        if (e.first != k) {
+          if (k < e.first) integrate(k, f, e.first, e.second);
+          done = true;
+        }
+      if (done || K.parent < 0) continue;
+      if (((K.child_index >> (f / 2)) & 1) != (f % 2)) continue;  // interior face of the parent
+      auto it = active_face.find(face_key_of(F.cells[K.parent], f));
+      if (it == active_face.end()) continue;
+      for (auto& e : it->second) integrate(k, f, e.first, e.second);  // coarser neighbour: sub-face integral
+    }
+  }
+  std::vector<float> eta(act.size());
+  for (size_t i = 0; i < act.size(); ++i) {
+    const Cell& K = F.cells[act[i]];
+    double h = 0;  // cell->diameter(): longest diagonal
+    for (int v = 0; v < (1 << (dim - 1)); ++v) {
+      const int w = ((1 << dim) - 1) ^ v;
+      double s = 0;
+      for (int a = 0; a < dim; ++a) {
+        const double dd = F.xyz[(int64_t)K.v[v] * dim + a] - F.xyz[(int64_t)K.v[w] * dim + a];
+        s += dd * dd;
+      }
+      h = std::max(h, std::sqrt(s));
+    }
+    eta[i] = (float)std::sqrt(sum[i] * h / 24.0);
+  }
+  return eta;
+}
+
+// GridRefinement::refine_and_coarsen_fixed_fraction(tria, criteria, top, bottom) followed by the level limits of
+// FSS:463-472.  criteria[i] belongs to active cell i of Forest::active_cells().
+inline void mark_fixed_fraction(Forest& F, const std::vector<float>& criteria, double top_fraction, double bottom_fraction, int min_level,
+                                int max_level) {
+  std::vector<int32_t> act = F.active_cells();
+  if (criteria.size() != act.size()) throw std::runtime_error("amr: one criterion per active cell expected");
+  if (act.empty()) return;
+  for (int32_t c : act) F.cells[c].refine_flag = F.cells[c].coarsen_flag = false;
+  std::vector<float> tmp(criteria);
+  double total_error = 0;
+  for (float v : tmp) total_error += std::fabs((double)v);
+  std::sort(tmp.begin(), tmp.end(), std::greater<float>());
+  size_t pp = 0;
+  for (double s = 0; s < top_fraction * total_error && pp != tmp.size() - 1; ++pp) s += tmp[pp];
+  double top_threshold = pp != 0 ? ((double)tmp[pp] + (double)tmp[pp - 1]) / 2 : (double)tmp[pp];
+  size_t qq = tmp.size() - 1;
+  for (double s = 0; s < bottom_fraction * total_error && qq != 0; --qq) s += tmp[qq];
+  double bottom_threshold = qq != tmp.size() - 1 ? ((double)tmp[qq] + (double)tmp[qq + 1]) / 2 : 0.0;
+  const double cmax = *std::max_element(criteria.begin(), criteria.end()), cmin = *std::min_element(criteria.begin(), criteria.end());
+  if (top_threshold == cmax && top_fraction != 1) top_threshold *= 0.999;
+  if (bottom_threshold >= top_threshold) bottom_threshold = 0.999 * top_threshold;
+  if (top_threshold < cmax) {  // GridRefinement::refine(tria, criteria, top_threshold, pp)
+    bool all_zero = true;
+    for (float v : criteria) all_zero = all_zero && v == 0;
+    if (!all_zero) {
+      double thr = top_threshold;
+      if (thr == 0) {
+        thr = criteria[0];
+        for (float v : criteria)
+          if (v > 0 && v < thr) thr = v;
+      }
+      size_t marked = 0;
+      for (size_t i = 0; i < act.size(); ++i)
+        if (std::fabs((double)criteria[i]) >= thr) {
+          if (marked >= pp) break;
+          ++marked;
+          F.cells[act[i]].refine_flag = true;
+        }
+    }
+  }
+  if (bottom_threshold > cmin)  // GridRefinement::coarsen
+    for (size_t i = 0; i < act.size(); ++i)
+      if (std::fabs((double)criteria[i]) <= bottom_threshold && !F.cells[act[i]].refine_flag) F.cells[act[i]].coarsen_flag = true;
+  // FSS:463-472
+  if (F.n_levels() > max_level)
+    for (int32_t c : act)
+      if (F.cells[c].level >= max_level) F.cells[c].refine_flag = false;
+  for (int32_t c : act)
+    if (F.cells[c].level == min_level) F.cells[c].coarsen_flag = false;
+}
+
+}  // namespace amr

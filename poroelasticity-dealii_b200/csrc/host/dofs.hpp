@@ -13,6 +13,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <stdexcept>
 #include <unordered_map>
 #include <vector>
 
@@ -66,8 +67,24 @@ struct PairHash {
     return std::hash<int64_t>()(p.first * 1000003LL ^ (p.second + 0x9e3779b97f4a7c15LL));
   }
 };
+typedef std::pair<int64_t, int64_t> EntityKey;
+typedef std::unordered_map<EntityKey, int32_t, PairHash> EntityMap;
 
-inline DofMap distribute_dofs(const mesh::Mesh& m, int degree, int n_comp) {
+// A line is identified by its two vertices, a quad by its four (orientation-free keys).
+inline EntityKey edge_key(int64_t a, int64_t b) { return a < b ? EntityKey{a, b} : EntityKey{b, a}; }
+inline EntityKey quad_key(int64_t a, int64_t b, int64_t c, int64_t d) {
+  int64_t vs[4] = {a, b, c, d};
+  std::sort(vs, vs + 4);
+  return {(vs[0] << 31) | vs[1], (vs[2] << 31) | vs[3]};
+}
+
+// first dof (component 0) of every vertex / line / quad node; used by the hanging-node constraints
+struct NodeMaps {
+  std::vector<int32_t> vdof;
+  EntityMap line_dof, quad_dof;
+};
+
+inline DofMap distribute_dofs(const mesh::Mesh& m, int degree, int n_comp, NodeMaps* maps = nullptr) {
   RefElement ref = make_ref_element(m.dim, degree);
   DofMap d;
   d.degree = degree;
@@ -77,7 +94,7 @@ inline DofMap distribute_dofs(const mesh::Mesh& m, int degree, int n_comp) {
   const int64_t nc = m.n_cells();
   d.cell_dofs.resize(nc * d.n_loc);
   std::vector<int32_t> vdof(m.n_vertices(), -1);
-  std::unordered_map<std::pair<int64_t, int64_t>, int32_t, PairHash> line_dof, quad_dof;
+  EntityMap line_dof, quad_dof;
   int64_t next = 0;
   for (int64_t c = 0; c < nc; ++c) {
     const int32_t* cv = &m.cell_vertices[c * vpc];
@@ -89,20 +106,16 @@ inline DofMap distribute_dofs(const mesh::Mesh& m, int degree, int n_comp) {
     }
     if (degree == 2) {
       for (auto& l : ref.lines) {
-        int64_t a = cv[l[0]], b = cv[l[1]];
-        if (a > b) std::swap(a, b);
-        auto it = line_dof.find({a, b});
+        const EntityKey key = edge_key(cv[l[0]], cv[l[1]]);
+        auto it = line_dof.find(key);
         int32_t base;
-        if (it == line_dof.end()) { base = (int32_t)next; line_dof[{a, b}] = base; next += n_comp; }
+        if (it == line_dof.end()) { base = (int32_t)next; line_dof[key] = base; next += n_comp; }
         else base = it->second;
         for (int k = 0; k < n_comp; ++k) out[s * n_comp + k] = base + k;
         ++s;
       }
       for (auto& q : ref.quads) {
-        int64_t vs[4] = {cv[q[0]], cv[q[1]], cv[q[2]], cv[q[3]]};
-        std::sort(vs, vs + 4);
-        // a quad face is identified by its two smallest... all four vertices; pack (v0,v1) and (v2,v3)
-        std::pair<int64_t, int64_t> key{vs[0] * (int64_t)m.n_vertices() + vs[1], vs[2] * (int64_t)m.n_vertices() + vs[3]};
+        const EntityKey key = quad_key(cv[q[0]], cv[q[1]], cv[q[2]], cv[q[3]]);
         auto it = quad_dof.find(key);
         int32_t base;
         if (it == quad_dof.end()) { base = (int32_t)next; quad_dof[key] = base; next += n_comp; }
@@ -116,6 +129,11 @@ inline DofMap distribute_dofs(const mesh::Mesh& m, int degree, int n_comp) {
     }
   }
   d.n_dofs = next;
+  if (maps) {
+    maps->vdof.swap(vdof);
+    maps->line_dof.swap(line_dof);
+    maps->quad_dof.swap(quad_dof);
+  }
   return d;
 }
 
@@ -143,10 +161,104 @@ inline std::vector<double> support_points(const mesh::Mesh& m, const DofMap& d) 
   return sp;
 }
 
+// General linear constraints x_i = sum_j w_ij x_j + g_i (deal.II ConstraintMatrix as used at PS:71-78,
+// DS:109-137): hanging-node lines carry entries, Dirichlet lines only an inhomogeneity.
+struct ConstraintLine {
+  int32_t dof = -1;
+  std::vector<std::pair<int32_t, double>> entries;
+  double inhomogeneity = 0;
+};
+struct ConstraintTable {
+  std::vector<ConstraintLine> lines;
+  std::vector<int32_t> line_of;  // dof -> index into lines, or -1
+  void init(int64_t n_dofs) { lines.clear(); line_of.assign(n_dofs, -1); }
+  bool is_constrained(int32_t dof) const { return line_of[dof] >= 0; }
+  // like add_line + add_entries + set_inhomogeneity; an existing line is never overwritten
+  bool add_line(int32_t dof, const std::vector<std::pair<int32_t, double>>& entries, double g) {
+    if (line_of[dof] >= 0) return false;
+    line_of[dof] = (int32_t)lines.size();
+    ConstraintLine l;
+    l.dof = dof;
+    l.entries = entries;
+    l.inhomogeneity = g;
+    lines.push_back(std::move(l));
+    return true;
+  }
+  // ConstraintMatrix::close(): entries that refer to constrained dofs are replaced by those dofs' own lines
+  // (chains of hanging nodes; hanging nodes whose parents carry Dirichlet values), duplicates are merged,
+  // entries and lines are sorted by dof.
+  void close() {
+    bool again = true;
+    int sweeps = 0;
+    while (again) {
+      again = false;
+      if (++sweeps > 64) throw std::runtime_error("ConstraintTable::close: cyclic constraints");
+      for (auto& l : lines) {
+        std::vector<std::pair<int32_t, double>> out;
+        bool touched = false;
+        for (auto& e : l.entries) {
+          const int32_t lj = line_of[e.first];
+          if (lj < 0) { out.push_back(e); continue; }
+          touched = true;
+          const ConstraintLine& o = lines[lj];
+          for (auto& oe : o.entries) out.push_back({oe.first, e.second * oe.second});
+          l.inhomogeneity += e.second * o.inhomogeneity;
+        }
+        if (touched) { l.entries.swap(out); again = true; }
+      }
+    }
+    for (auto& l : lines) {
+      std::sort(l.entries.begin(), l.entries.end());
+      std::vector<std::pair<int32_t, double>> merged;
+      for (auto& e : l.entries) {
+        if (!merged.empty() && merged.back().first == e.first) merged.back().second += e.second;
+        else merged.push_back(e);
+      }
+      l.entries.swap(merged);
+    }
+    std::sort(lines.begin(), lines.end(), [](const ConstraintLine& a, const ConstraintLine& b) { return a.dof < b.dof; });
+    for (size_t i = 0; i < lines.size(); ++i) line_of[lines[i].dof] = (int32_t)i;
+  }
+  int64_t n_entries() const {
+    int64_t n = 0;
+    for (auto& l : lines) n += (int64_t)l.entries.size();
+    return n;
+  }
+  // flat form for pe_upload_constraints
+  void flatten(std::vector<int32_t>& line_dof, std::vector<int64_t>& entry_ptr, std::vector<int32_t>& entry_dof, std::vector<double>& entry_w,
+               std::vector<double>& inhomogeneity) const {
+    line_dof.clear(); entry_ptr.assign(1, 0); entry_dof.clear(); entry_w.clear(); inhomogeneity.clear();
+    for (auto& l : lines) {
+      line_dof.push_back(l.dof);
+      inhomogeneity.push_back(l.inhomogeneity);
+      for (auto& e : l.entries) { entry_dof.push_back(e.first); entry_w.push_back(e.second); }
+      entry_ptr.push_back((int64_t)entry_dof.size());
+    }
+  }
+};
+
 struct Constraints {  // pure-Dirichlet lines x_i = g_i, sorted by dof (ConstraintMatrix::close)
   std::vector<int32_t> line_dof;
   std::vector<double> inhomogeneity;
 };
+
+// DS:117-135 on top of existing (hanging-node) lines: VectorTools::interpolate_boundary_values never overwrites a
+// dof that is already constrained.  Call ConstraintTable::close() afterwards (DS:136).
+inline void add_dirichlet(ConstraintTable& T, const mesh::Mesh& m, const DofMap& d, const std::vector<int>& labels, const std::vector<int>& comps,
+                          const std::vector<double>& values) {
+  RefElement ref = make_ref_element(m.dim, d.degree);
+  for (size_t cond = 0; cond < labels.size(); ++cond)
+    for (int64_t b = 0; b < m.n_bfaces(); ++b) {
+      if (m.bface_id[b] != labels[cond]) continue;
+      int f = m.bface_local[b], axis = f / 2;
+      double side = f % 2;
+      for (int s = 0; s < ref.n_scalar; ++s) {
+        if (ref.unit_support[s * m.dim + axis] != side) continue;
+        int32_t dof = d.cell_dofs[(int64_t)m.bface_cell[b] * d.n_loc + s * d.n_comp + comps[cond]];
+        T.add_line(dof, {}, values[cond]);
+      }
+    }
+}
 
 // DS:117-135
 inline Constraints make_dirichlet(const mesh::Mesh& m, const DofMap& d, const std::vector<int>& labels,

@@ -3,6 +3,7 @@
 #include <string>
 
 #include "../../../include/poroel_host.h"
+#include "amr.hpp"
 #include "dofs.hpp"
 #include "input_data.hpp"
 #include "mesh.hpp"
@@ -16,7 +17,14 @@ struct peh_input {
   std::vector<int32_t> dl, dc, nl, nc;
 };
 struct peh_mesh { mesh::Mesh m; };
-struct peh_dofs { dofs::DofMap d; };
+struct peh_dofs { dofs::DofMap d; dofs::NodeMaps maps; };
+struct peh_forest { amr::Forest F; };
+struct peh_constraints {
+  dofs::ConstraintTable T;
+  std::vector<int32_t> line_dof, entry_dof;
+  std::vector<int64_t> entry_ptr;
+  std::vector<double> entry_w, inhomogeneity;
+};
 struct peh_part { partition::Part p; };
 struct peh_problem {
   std::unique_ptr<poro_elastisity::PoroElasticProblem> P;
@@ -135,7 +143,7 @@ peh_dofs* peh_dofs_distribute(const peh_mesh* m, int degree, int n_comp) {
   PEH_TRY
   if (degree < 1 || degree > 2) throw std::runtime_error("degree must be 1 or 2");
   auto* d = new peh_dofs();
-  d->d = dofs::distribute_dofs(m->m, degree, n_comp);
+  d->d = dofs::distribute_dofs(m->m, degree, n_comp, &d->maps);
   return d;
   PEH_CATCH(nullptr)
 }
@@ -162,6 +170,130 @@ int64_t peh_make_dirichlet(const peh_mesh* m, const peh_dofs* d, int n, const in
   if (inhomogeneity) std::memcpy(inhomogeneity, cs.inhomogeneity.data(), cs.inhomogeneity.size() * sizeof(double));
   return (int64_t)cs.line_dof.size();
   PEH_CATCH(-1)
+}
+
+// ---- adaptive refinement
+peh_forest* peh_forest_create(const peh_mesh* m, int base_level) {
+  PEH_TRY
+  auto* f = new peh_forest();
+  f->F = amr::Forest::from_mesh(m->m, base_level);
+  return f;
+  PEH_CATCH(nullptr)
+}
+void peh_forest_destroy(peh_forest* f) { delete f; }
+peh_mesh* peh_forest_active_mesh(const peh_forest* f) {
+  PEH_TRY
+  auto* m = new peh_mesh();
+  m->m = f->F.active_mesh();
+  return m;
+  PEH_CATCH(nullptr)
+}
+int64_t peh_forest_active_levels(const peh_forest* f, int32_t* level) {
+  PEH_TRY
+  std::vector<int32_t> a = f->F.active_cells();
+  if (level) for (size_t i = 0; i < a.size(); ++i) level[i] = f->F.cells[a[i]].level;
+  return (int64_t)a.size();
+  PEH_CATCH(-1)
+}
+int peh_forest_set_flags(peh_forest* f, int64_t n, const int8_t* refine, const int8_t* coarsen) {
+  PEH_TRY
+  std::vector<int32_t> a = f->F.active_cells();
+  if ((int64_t)a.size() != n) throw std::runtime_error("flag arrays must have one entry per active cell");
+  for (int64_t i = 0; i < n; ++i) {
+    f->F.cells[a[i]].refine_flag = refine && refine[i];
+    f->F.cells[a[i]].coarsen_flag = coarsen && coarsen[i] && !(refine && refine[i]);
+  }
+  return 0;
+  PEH_CATCH(PE_ERR_BAD_INPUT)
+}
+int peh_forest_get_flags(const peh_forest* f, int64_t n, int8_t* refine, int8_t* coarsen) {
+  PEH_TRY
+  std::vector<int32_t> a = f->F.active_cells();
+  if ((int64_t)a.size() != n) throw std::runtime_error("flag arrays must have one entry per active cell");
+  for (int64_t i = 0; i < n; ++i) {
+    if (refine) refine[i] = f->F.cells[a[i]].refine_flag;
+    if (coarsen) coarsen[i] = f->F.cells[a[i]].coarsen_flag;
+  }
+  return 0;
+  PEH_CATCH(PE_ERR_BAD_INPUT)
+}
+int peh_forest_prepare(peh_forest* f) {
+  PEH_TRY
+  f->F.prepare();
+  return 0;
+  PEH_CATCH(PE_ERR_STATE)
+}
+int peh_forest_execute(peh_forest* f, int32_t* nc, int32_t* nr) {
+  PEH_TRY
+  auto r = f->F.execute();
+  if (nc) *nc = r.first;
+  if (nr) *nr = r.second;
+  return 0;
+  PEH_CATCH(PE_ERR_STATE)
+}
+static std::vector<double> vertex_values(const amr::Forest& F, const mesh::Mesh& m, const dofs::DofMap& d, const double* p) {
+  if (d.degree != 1 || d.n_comp != 1) throw std::runtime_error("the estimator runs on the FE_Q(1) pressure handler (FSS:454)");
+  std::vector<double> vv(F.n_vertices(), 0.0);
+  const int vpc = m.vpc();
+  for (int64_t c = 0; c < m.n_cells(); ++c)
+    for (int k = 0; k < vpc; ++k) vv[m.cell_vertices[c * vpc + k]] = p[d.cell_dofs[c * vpc + k]];
+  return vv;
+}
+int peh_forest_kelly(const peh_forest* f, const peh_mesh* m, const peh_dofs* d, const double* p, float* eta) {
+  PEH_TRY
+  std::vector<float> e = amr::kelly_estimate(f->F, vertex_values(f->F, m->m, d->d, p));
+  std::memcpy(eta, e.data(), e.size() * sizeof(float));
+  return 0;
+  PEH_CATCH(PE_ERR_BAD_INPUT)
+}
+int peh_forest_mark_fixed_fraction(peh_forest* f, int64_t n, const float* criteria, double top, double bottom, int min_level, int max_level) {
+  PEH_TRY
+  amr::mark_fixed_fraction(f->F, std::vector<float>(criteria, criteria + n), top, bottom, min_level, max_level);
+  return 0;
+  PEH_CATCH(PE_ERR_BAD_INPUT)
+}
+int peh_forest_store(peh_forest* f, const peh_mesh* m, const peh_dofs* d, int n_vec, const double* values) {
+  PEH_TRY
+  std::vector<const double*> v(n_vec);
+  for (int t = 0; t < n_vec; ++t) v[t] = values + (int64_t)t * d->d.n_dofs;
+  f->F.store_vertex_values(m->m, d->d, n_vec, v.data());
+  return 0;
+  PEH_CATCH(PE_ERR_BAD_INPUT)
+}
+int peh_forest_fetch(const peh_forest* f, const peh_mesh* m, const peh_dofs* d, int n_vec, double* values) {
+  PEH_TRY
+  std::vector<double*> v(n_vec);
+  for (int t = 0; t < n_vec; ++t) v[t] = values + (int64_t)t * d->d.n_dofs;
+  f->F.fetch_vertex_values(m->m, d->d, n_vec, v.data());
+  return 0;
+  PEH_CATCH(PE_ERR_BAD_INPUT)
+}
+peh_constraints* peh_constraints_make(const peh_forest* f, const peh_mesh* m, const peh_dofs* d, int n, const int32_t* labels, const int32_t* comps,
+                                      const double* values) {
+  PEH_TRY
+  auto* c = new peh_constraints();
+  c->T.init(d->d.n_dofs);
+  if (f) amr::hanging_node_constraints(f->F, m->m, d->d, d->maps, c->T);
+  if (n > 0) {
+    std::vector<int> l(labels, labels + n), cc(comps, comps + n);
+    std::vector<double> v(values, values + n);
+    dofs::add_dirichlet(c->T, m->m, d->d, l, cc, v);
+  }
+  c->T.close();
+  c->T.flatten(c->line_dof, c->entry_ptr, c->entry_dof, c->entry_w, c->inhomogeneity);
+  return c;
+  PEH_CATCH(nullptr)
+}
+void peh_constraints_destroy(peh_constraints* c) { delete c; }
+int peh_constraints_view_get(const peh_constraints* c, peh_constraints_view* v) {
+  v->n_lines = (int64_t)c->line_dof.size();
+  v->n_entries = (int64_t)c->entry_dof.size();
+  v->line_dof = c->line_dof.data();
+  v->entry_ptr = c->entry_ptr.data();
+  v->entry_dof = c->entry_dof.data();
+  v->entry_w = c->entry_w.data();
+  v->inhomogeneity = c->inhomogeneity.data();
+  return 0;
 }
 
 peh_part* peh_partition(const peh_mesh* m, const peh_dofs* dp, const peh_dofs* du, int rank, int nranks) {
