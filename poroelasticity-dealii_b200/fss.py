@@ -27,11 +27,28 @@ def make_mesh(inp: capi.InputData, mesh_file=None):
     return capi.mesh_rectangle(inp.dim, inp.domain_size[: inp.dim], inp.initial_refinement_level)
 
 
-def upload_problem(backend: capi.OperatorBackend, inp: capi.InputData, mesh: capi.HostMesh, prm: capi.PeParams | None = None):
-    """setup_dofs() (FSS:131-151) + set_boundary_conditions (FSS:300-306) for a single-rank backend."""
+def upload_problem(backend: capi.OperatorBackend, inp: capi.InputData, mesh: capi.HostMesh, prm: capi.PeParams | None = None,
+                   forest: capi.Forest | None = None):
+    """setup_dofs() (FSS:131-151) + set_boundary_conditions (FSS:300-306) for a single-rank backend.
+
+    With ``forest`` the mesh is the forest's active mesh and both handlers get their hanging-node constraints
+    (PS:74-77, DS:112-114); the displacement table also holds the Dirichlet lines and is closed (DS:117-137)."""
     prm = prm or inp.params()
     dofs_p = capi.HostDofs(mesh, 1, 1)
     dofs_u = capi.HostDofs(mesh, prm.degree_u, inp.dim)
+    if forest is not None:
+        Lp = capi.make_constraints(forest, mesh, dofs_p)
+        Lu = capi.make_constraints(forest, mesh, dofs_u, inp.displacement_boundary_labels, inp.displacement_boundary_components,
+                                   inp.displacement_boundary_values)
+        backend.set_params(prm)
+        backend.upload_mesh(mesh.arrays)
+        backend.upload_dofs(capi.FIELD_PRESSURE, dofs_p.n_dofs, dofs_p.cell_dofs)
+        backend.upload_dofs(capi.FIELD_DISPLACEMENT, dofs_u.n_dofs, dofs_u.cell_dofs)
+        backend.upload_constraint_lines(capi.FIELD_PRESSURE, Lp)
+        backend.upload_constraint_lines(capi.FIELD_DISPLACEMENT, Lu)
+        backend.upload_neumann(inp.stress_boundary_labels, inp.stress_boundary_components, inp.stress_boundary_values)
+        backend.setup()
+        return dofs_p, dofs_u, (Lp, Lu)
     line_dof, g = capi.make_dirichlet(mesh, dofs_u, inp.displacement_boundary_labels, inp.displacement_boundary_components,
                                       inp.displacement_boundary_values)
     backend.set_params(prm)

@@ -1,0 +1,168 @@
+"""The CPU oracle on hanging-node meshes (the adaptive part of the time loop, FSS:333-340).
+
+deal.II's ConstraintMatrix is restated twice and the two are compared: oracle.cpp works cell by cell
+(distribute_local_to_global with weights, in-place condense) like the library does; oracle/oracle_np.py::AdaptiveNP finds
+hanging nodes by geometry and applies them as global sparse triple products with direct solves.
+"""
+import sys
+
+import numpy as np
+import pytest
+
+import helpers as H
+from test_amr import corner_refined_forest, cell_boxes
+
+sys.path.insert(0, str(H.ROOT / "oracle"))
+from oracle_np import AdaptiveNP  # noqa: E402
+
+capi, fss = H.capi, H.fss
+
+
+def key(x):
+    return tuple(np.round(np.asarray(x) * 1e6).astype(np.int64))
+
+
+def perm_by_coords(src, dst):
+    d = {key(x): i for i, x in enumerate(src)}
+    return np.array([d[key(x)] for x in dst])
+
+
+def adaptive_oracle(dim, deg, rounds, **kw):
+    inp = capi.InputData(text=H.make_input(dim=dim, refine=2, degree_u=deg, **kw))
+    F = corner_refined_forest(dim, rounds=rounds)
+    am = F.active_mesh()
+    b = H.create_oracle_backend()
+    dp, du, (Lp, Lu) = fss.upload_problem(b, inp, am, forest=F)
+    return inp, F, am, b, dp, du, Lp, Lu
+
+
+def components(du, dim):
+    comp = np.zeros(du.n_dofs, int)
+    for c in range(dim):
+        comp[du.cell_dofs[:, c::dim].ravel()] = c
+    return comp
+
+
+@pytest.mark.parametrize("dim,deg,rounds", [(2, 1, 3), (2, 2, 3), (3, 1, 2), (3, 2, 1)])
+def test_patch_test_with_hanging_nodes(dim, deg, rounds):
+    """The shipped boundary data has the exact solution u_a = -1e-5 (x_a + 5)/10; a conforming space with correctly
+    condensed systems reproduces it to round-off on any mesh, hanging nodes included."""
+    inp, F, am, b, dp, du, Lp, Lu = adaptive_oracle(dim, deg, rounds)
+    assert Lp.n_lines > 0 and len(Lu.entry_dof) > 0
+    fss.initialize(b, inp)
+    u = b.get_vector(capi.VEC_U)
+    sp = du.support_points()
+    exact = -1e-5 * (sp[np.arange(du.n_dofs), components(du, dim)] + 5.0) / 10.0
+    assert np.abs(u - exact).max() <= 2e-15
+    for c in fss.VOLUMETRIC_COMPONENTS[dim]:
+        assert np.allclose(b.get_vector(capi.VEC_STRAIN0 + fss.TENSOR_TO_ENTRY[dim][c]), -1e-6, rtol=3e-7)
+    assert np.allclose(b.get_vector(capi.VEC_VOL_STRAIN0), -1e-6 * dim, rtol=3e-7)
+    # matrices: symmetric; the unconstrained mass matrix integrates 1 to the volume; constrained rows/columns of the
+    # condensed matrices are diagonal only
+    M, A, PM = b.get_matrix(capi.MAT_MASS), b.get_matrix(capi.MAT_ELASTICITY), b.get_matrix(capi.MAT_PROJECTION)
+    assert M.sum() == pytest.approx(10.0 ** dim, rel=1e-12)
+    for X in (M, A, PM):
+        assert abs(X - X.T).max() <= 1e-13 * abs(X).max()
+    for X, lines in ((A, Lu.line_dof), (PM, Lp.line_dof)):
+        Xd = X.tocsr()[lines].toarray()
+        diag = Xd[np.arange(len(lines)), lines].copy()
+        Xd[np.arange(len(lines)), lines] = 0
+        assert np.all(Xd == 0) and np.all(diag > 0)
+    # condensed mass matrix still integrates constants: 1^T E^T M E 1 restricted to free dofs = |Omega|
+    free = np.ones(dp.n_dofs, bool)
+    free[Lp.line_dof] = False
+    assert PM[free][:, free].sum() == pytest.approx(10.0 ** dim, rel=1e-12)
+    assert np.allclose(PM.diagonal()[~free], np.abs(M.diagonal()).mean(), rtol=1e-14)  # ConstraintMatrix::condense
+    b.close()
+
+
+@pytest.mark.parametrize("dim,deg,rounds", [(2, 1, 3), (2, 2, 2), (3, 1, 2), (3, 2, 1)])
+def test_oracle_matches_the_geometric_numpy_restatement(dim, deg, rounds):
+    # well inside the refined corner, so that the source hits cells of several levels
+    inp, F, am, b, dp, du, Lp, Lu = adaptive_oracle(dim, deg, rounds)
+    prm = inp.params()
+    P = {k: getattr(prm, k) for k in ("lame_lambda", "shear_modulus", "bulk_modulus", "biot_coef", "m_modulus", "perm_over_visc", "well_radius", "flow_rate")}
+    lo, hi = cell_boxes(am.arrays)
+    R = AdaptiveNP(dim, lo, hi, deg, P)
+    R.assemble_displacement([(int(l), int(c), float(v)) for l, c, v in zip(inp.displacement_boundary_labels, inp.displacement_boundary_components,
+                                                                         inp.displacement_boundary_values)])
+    # FE_Q(2) on a refined line keeps TWO dofs at the line's midpoint — the coarse cell's line dof and the fine cells'
+    # vertex dof, tied by an identity constraint; the coordinate-keyed numpy restatement has one node there.  Hence the
+    # map C++ dof -> numpy dof may be many-to-one, but it is one-to-one on the unconstrained dofs.
+    assert R.np_ == dp.n_dofs
+    pp = perm_by_coords(R.xp, dp.support_points())
+    pu = perm_by_coords(R.xu, du.support_points()) * dim + components(du, dim)
+    free_u = np.ones(du.n_dofs, bool)
+    free_u[Lu.line_dof] = False
+    assert len(set(pu[free_u].tolist())) == free_u.sum() == (~R.cons).sum()
+    # the constraint tables agree line by line (tree-based C++ vs geometry-based numpy)
+    assert {int(pp[d]) for d in Lp.line_dof} == set(R.lines_p)
+    for i in range(Lp.n_lines):
+        d, ed, ew, g = Lp.line(i)
+        ref = R.lines_p[int(pp[d])]
+        assert {int(pp[e]) for e in ed} == set(ref) and all(abs(ref[int(pp[e])] - w) < 1e-14 for e, w in zip(ed, ew))
+    seen = set()
+    for i in range(Lu.n_lines):
+        d, ed, ew, g = Lu.line(i)
+        if int(pu[d]) not in R.lines_u:  # the identity constraint of a duplicated midpoint dof
+            assert deg == 2 and len(ed) == 1 and ew[0] == 1.0 and g == 0.0 and pu[ed[0]] == pu[d]
+            continue
+        seen.add(int(pu[d]))
+        ref_w, ref_g = R.lines_u[int(pu[d])]
+        assert {int(pu[e]) for e in ed} == set(ref_w) and all(abs(ref_w[int(pu[e])] - w) < 1e-14 for e, w in zip(ed, ew))
+        assert abs(ref_g - g) <= 1e-20
+    assert seen == set(R.lines_u)
+    fss.initialize(b, inp)
+    R.initialize(inp.p_init)
+    rel = lambda X, Y: abs(X - Y).max() / abs(Y).max()
+    assert rel(b.get_matrix(capi.MAT_MASS), R.M[pp][:, pp]) <= 1e-13
+    assert rel(b.get_matrix(capi.MAT_LAPLACE), R.K[pp][:, pp]) <= 1e-13
+    assert rel(b.get_matrix(capi.MAT_PROJECTION), R.condensed(R.M)[pp][:, pp]) <= 1e-13
+    fu = np.nonzero(free_u)[0]
+    A = b.get_matrix(capi.MAT_ELASTICITY)
+    assert rel(A[fu][:, fu], R.condensed_elasticity()[pu[fu]][:, pu[fu]]) <= 1e-13
+    assert abs(A[Lu.line_dof][:, fu]).max() == 0 and abs(A[fu][:, Lu.line_dof]).max() == 0
+    assert fss.rel_l2(b.get_vector(capi.VEC_U_RHS)[fu], R.rhs_displacement(R.p)[pu[fu]]) <= 1e-12
+    assert abs(b.get_vector(capi.VEC_U_RHS)[Lu.line_dof]).max() == 0
+    assert fss.rel_l2(b.get_vector(capi.VEC_U), R.u[pu]) <= 1e-10
+    vol = fss.VOLUMETRIC_COMPONENTS[dim]
+    _, rhs_np = R.project_strains(R.u, vol)
+    for comp_t in vol:
+        got = b.get_vector(capi.VEC_PROJ_RHS0 + fss.TENSOR_TO_ENTRY[dim][comp_t])
+        assert np.abs(got - rhs_np[comp_t][pp]).max() <= 1e-9 * np.abs(rhs_np[comp_t]).max()
+    assert fss.rel_l2(b.get_vector(capi.VEC_VOL_STRAIN0), R.ev0[pp]) <= 1e-6
+    for step in range(2):
+        rep = fss.time_step(b, inp)
+        hist = R.time_step(inp.time_step)
+        if step == 0:
+            dt = inp.time_step
+            Jn = R.condensed(R.M * (1.0 / prm.m_modulus / dt) + prm.perm_over_visc * R.K)
+            assert rel(b.get_matrix(capi.MAT_JACOBIAN), Jn[pp][:, pp]) <= 1e-13
+        assert rep["inner_counts"] == [len(hist)]
+        assert rep["fss_iterations"] == 1
+        assert fss.rel_l2(b.get_vector(capi.VEC_P), R.p[pp]) <= 1e-10
+        assert fss.rel_l2(b.get_vector(capi.VEC_U), R.u[pu]) <= 1e-9
+        # fields stay conforming: every hanging value equals its line (PS:180, DS:306)
+        p = b.get_vector(capi.VEC_P)
+        for i in range(Lp.n_lines):
+            d, ed, ew, g = Lp.line(i)
+            assert abs(p[d] - p[ed] @ ew) <= 1e-9 * abs(p).max()
+    b.close()
+
+
+def test_uniform_mesh_through_the_constraint_path_equals_the_plain_path():
+    """A forest without refinement has no hanging nodes; feeding the (Dirichlet-only) table through the general-line upload
+    must reproduce the established path bit for bit."""
+    inp = capi.InputData(text=H.make_input(dim=2, refine=3, degree_u=2))
+    mesh = fss.make_mesh(inp)
+    F = capi.Forest(mesh, 3)
+    am = F.active_mesh()
+    out = []
+    for forest in (None, F):
+        b = H.create_oracle_backend()
+        fss.upload_problem(b, inp, am if forest else mesh, forest=forest)
+        fss.initialize(b, inp)
+        rep = fss.time_step(b, inp)
+        out.append((b.get_vector(capi.VEC_P), b.get_vector(capi.VEC_U), rep["inner_counts"], rep["cg_its_displacement"]))
+        b.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2:] == out[1][2:]
