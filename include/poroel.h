@@ -127,9 +127,11 @@ int  pe_upload_mesh(pe_ctx*, int dim, int64_t n_vertices, const double* xyz /* n
                     int64_t n_bfaces, const int32_t* bface_cell, const int8_t* bface_local,
                     const int32_t* bface_id);
 int  pe_upload_dofs(pe_ctx*, int field, int64_t n_dofs_local, const int32_t* cell_dofs /* n_cells * n_loc */);
-/* general linear constraint table x_i = sum_j a_ij x_j + g_i (ConstraintMatrix, DS:113-135).
- * Lines with entries (hanging nodes) are accepted by the ABI but rejected by pe_setup in
- * this build (uniform meshes only; AMR is a "next" row).                                   */
+/* general linear constraint table x_i = sum_j a_ij x_j + g_i (ConstraintMatrix after close(), PS:71-78,
+ * DS:109-137).  Lines without entries are Dirichlet values; lines with entries are hanging nodes of
+ * an adaptively refined mesh (FSS:333-340) and may also carry an inhomogeneity.  Entries must refer
+ * to unconstrained dofs (closed table).  Pressure lines are homogeneous hanging-node lines only.
+ * Hanging-node meshes run on one rank.                                                        */
 int  pe_upload_constraints(pe_ctx*, int field, int64_t n_lines, const int32_t* line_dof,
                            const int64_t* entry_ptr, const int32_t* entry_dof, const double* entry_w,
                            const double* inhomogeneity);

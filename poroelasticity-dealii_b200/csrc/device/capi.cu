@@ -64,6 +64,7 @@ static MatRef mat_by_id(pe_ctx* c, int m) {
     case PE_MAT_LAPLACE: return {c->K.p, &c->fp};
     case PE_MAT_JACOBIAN: return {c->J.p, &c->fp};
     case PE_MAT_ELASTICITY: return {c->A.p, &c->fu};
+    case PE_MAT_PROJECTION: return {c->fp.hang.n ? c->Mc.p : c->M.p, &c->fp};
   }
   throw PeError(PE_ERR_BAD_INPUT, "bad matrix id");
 }
@@ -227,23 +228,69 @@ int pe_upload_dofs(pe_ctx* c, int field, int64_t n_local, const int32_t* cell_do
   F.n_lines = 0;
   F.h_line_dof.clear();
   F.h_line_g.clear();
+  F.hang.clear();
   F.halo.reset();
   c->setup_done = false;
   PE_LEAVE(c)
 }
 
-int pe_upload_constraints(pe_ctx* c, int field, int64_t n_lines, const int32_t* line_dof, const int64_t* entry_ptr, const int32_t*,
-                          const double*, const double* inhomogeneity) {
+int pe_upload_constraints(pe_ctx* c, int field, int64_t n_lines, const int32_t* line_dof, const int64_t* entry_ptr, const int32_t* entry_dof,
+                          const double* entry_w, const double* inhomogeneity) {
   PE_ENTER(c)
   Field& F = field_of(c, field);
   require(F.have_dofs, PE_ERR_STATE, "pe_upload_dofs first");
   require(n_lines >= 0, PE_ERR_BAD_INPUT, "negative line count");
-  if (entry_ptr && n_lines > 0)
-    require(entry_ptr[n_lines] == 0, PE_ERR_UNSUPPORTED, "constraint lines with entries (hanging nodes) are not supported in this build");
-  for (int64_t i = 0; i < n_lines; ++i) require(line_dof[i] >= 0 && line_dof[i] < F.n_local, PE_ERR_BAD_INPUT, "constrained dof out of range");
-  F.n_lines = n_lines;
-  F.h_line_dof.assign(line_dof, line_dof + n_lines);
-  F.h_line_g.assign(inhomogeneity, inhomogeneity + n_lines);
+  require(n_lines == 0 || line_dof != nullptr, PE_ERR_BAD_INPUT, "null line array");
+  const bool have_entries = entry_ptr && n_lines > 0 && entry_ptr[n_lines] > 0;
+  if (have_entries) require(entry_dof && entry_w, PE_ERR_BAD_INPUT, "constraint entries without dof / weight arrays");
+  std::vector<uint8_t> is_line((size_t)F.n_local, 0);
+  for (int64_t i = 0; i < n_lines; ++i) {
+    require(line_dof[i] >= 0 && line_dof[i] < F.n_local, PE_ERR_BAD_INPUT, "constrained dof out of range");
+    require(!is_line[line_dof[i]], PE_ERR_BAD_INPUT, "dof constrained twice");
+    is_line[line_dof[i]] = 1;
+  }
+  // lines without entries are Dirichlet values (handled inside the cell kernels); lines with entries are hanging nodes
+  // (handled on the assembled objects, kernels_constraints.cu)
+  std::vector<int32_t> d_dof;
+  std::vector<double> d_g;
+  Field::Hanging H;
+  H.h_ptr.push_back(0);
+  for (int64_t i = 0; i < n_lines; ++i) {
+    const int64_t e0 = have_entries ? entry_ptr[i] : 0, e1 = have_entries ? entry_ptr[i + 1] : 0;
+    require(e0 <= e1, PE_ERR_BAD_INPUT, "entry_ptr must be non-decreasing");
+    const double g = inhomogeneity ? inhomogeneity[i] : 0.0;
+    if (e0 == e1) {
+      d_dof.push_back(line_dof[i]);
+      d_g.push_back(g);
+      continue;
+    }
+    H.h_dof.push_back(line_dof[i]);
+    H.h_g.push_back(g);
+    if (g != 0.0) H.any_g = true;
+    for (int64_t e = e0; e < e1; ++e) {
+      require(entry_dof[e] >= 0 && entry_dof[e] < F.n_local, PE_ERR_BAD_INPUT, "constraint entry out of range");
+      require(!is_line[entry_dof[e]], PE_ERR_BAD_INPUT, "constraint table is not closed: an entry refers to a constrained dof");
+      H.h_edof.push_back(entry_dof[e]);
+      H.h_w.push_back(entry_w[e]);
+    }
+    H.h_ptr.push_back((int32_t)H.h_edof.size());
+  }
+  H.n = (int64_t)H.h_dof.size();
+  H.n_entries = (int64_t)H.h_edof.size();
+  if (field == PE_FIELD_PRESSURE)
+    require(d_dof.empty() && !H.any_g, PE_ERR_UNSUPPORTED, "pressure constraints are homogeneous hanging-node lines only (PS:71-78)");
+  F.n_lines = (int64_t)d_dof.size();
+  F.h_line_dof.swap(d_dof);
+  F.h_line_g.swap(d_g);
+  F.hang.clear();
+  F.hang.n = H.n;
+  F.hang.n_entries = H.n_entries;
+  F.hang.any_g = H.any_g;
+  F.hang.h_dof.swap(H.h_dof);
+  F.hang.h_ptr.swap(H.h_ptr);
+  F.hang.h_edof.swap(H.h_edof);
+  F.hang.h_w.swap(H.h_w);
+  F.hang.h_g.swap(H.h_g);
   c->setup_done = false;
   PE_LEAVE(c)
 }
@@ -289,7 +336,9 @@ int pe_setup(pe_ctx* c) {
   PE_ENTER(c)
   require(c->have_mesh && c->fp.have_dofs && c->fu.have_dofs, PE_ERR_STATE, "mesh and both dof maps must be uploaded");
   require(c->nranks == 1 || (c->fp.have_partition && c->fu.have_partition), PE_ERR_STATE, "nranks > 1 needs pe_upload_partition for both fields");
-  require(c->fp.n_lines == 0, PE_ERR_UNSUPPORTED, "pressure constraints would be hanging-node lines (PS:71-78): not supported");
+  require(c->fp.n_lines == 0, PE_ERR_UNSUPPORTED, "pressure constraints are hanging-node lines only (PS:71-78)");
+  require((c->fp.hang.n == 0 && c->fu.hang.n == 0) || c->nranks == 1, PE_ERR_UNSUPPORTED,
+          "hanging-node (adaptive) meshes run on one rank; partitioned runs need uniform meshes");
   auto t0 = std::chrono::steady_clock::now();
   cudaStream_t s = c->stream;
   for (Field* F : {&c->fp, &c->fu}) {
@@ -302,7 +351,12 @@ int pe_setup(pe_ctx* c) {
     F->line_dof.upload(F->h_line_dof, s);
     F->line_g.upload(F->h_line_g, s);
     PE_CUDA(cudaStreamSynchronize(s));
-    pe_build_pattern(c, *F);
+    F->bsr.B = 0;
+    if (F->hang.n) {
+      pe_hanging_upload(c, *F);
+      pe_build_pattern_lists(c, *F);  // make_sparsity_pattern(dh, dsp, constraints, true), PS:80-88 / DS:140-146
+    } else
+      pe_build_pattern(c, *F);
   }
   pe_build_tables(c);
   pe_color_cells(c);
@@ -327,8 +381,21 @@ int pe_setup(pe_ctx* c) {
   c->invdiag_J.alloc((size_t)c->fp.n_owned);
   c->invdiag_A.alloc((size_t)c->fu.n_owned);
   pe_assemble_pressure_matrices(c);  // PS:96-101 (+ cached well source, PS:142-147)
-  pe_extract_invdiag(c, c->fp, c->M.p, c->invdiag_M.p);
-  c->eig_M = 1.1 * pe_estimate_eig_max(c, c->fp, c->M.p, c->invdiag_M.p);
+  if (c->fp.hang.n) {
+    // constraints.condense() of PS:168 and SP:105 is linear in the matrix, so it is applied once to M and K;
+    // constrained diagonals get the average |diagonal| of the uncondensed matrix (ConstraintMatrix::condense)
+    c->Mc.alloc((size_t)c->fp.nnz);
+    c->Kc.alloc((size_t)c->fp.nnz);
+    const double avg_m = pe_avg_abs_diag(c, c->fp, c->M.p), avg_k = pe_avg_abs_diag(c, c->fp, c->K.p);
+    pe_condense_matrix(c, c->fp, c->M.p, c->Mc.p, false, avg_m);
+    pe_condense_matrix(c, c->fp, c->K.p, c->Kc.p, false, avg_k);
+  } else {
+    c->Mc.release();
+    c->Kc.release();
+  }
+  const double* m_proj = c->fp.hang.n ? c->Mc.p : c->M.p;
+  pe_extract_invdiag(c, c->fp, m_proj, c->invdiag_M.p);
+  c->eig_M = 1.1 * pe_estimate_eig_max(c, c->fp, m_proj, c->invdiag_M.p);
   c->jac_dt = -1;
   c->matrix_u_built = false;
   c->proj_matrix_ready = false;
@@ -377,7 +444,11 @@ int pe_pressure_assemble_residual(pe_ctx* c, double dt, double* l2) {
   PE_ENTER(c)
   PE_NEED_SETUP(c);
   require(dt > 0, PE_ERR_BAD_INPUT, "time step must be positive");
-  const double n = pe_pressure_residual(c, dt);
+  double n = pe_pressure_residual(c, dt);
+  if (c->fp.hang.n) {  // constraints.condense(residual), PS:153; FSS:364/405 take the norm afterwards
+    pe_condense_vector(c, c->fp, c->resid.p);
+    n = std::sqrt(pe_vec_dot(c, c->fp, c->resid.p, c->resid.p));
+  }
   if (l2) *l2 = n;
   if (std::isnan(n)) throw PeError(PE_ERR_NAN, "pressure residual is NaN");
   PE_LEAVE(c)
@@ -387,7 +458,9 @@ int pe_pressure_assemble_jacobian(pe_ctx* c, double dt) {
   PE_NEED_SETUP(c);
   require(dt > 0, PE_ERR_BAD_INPUT, "time step must be positive");
   if (c->jac_dt != dt) {  // J = M/(M_b dt) + (k/mu) K is constant while dt is (PS:162-167)
-    pe_vec_axpby_vals(c, c->fp.nnz, 1. / c->prm.m_modulus / dt, c->M.p, c->prm.perm_over_visc, c->K.p, c->J.p);
+    const double* Ms = c->fp.hang.n ? c->Mc.p : c->M.p;  // condensed copies on hanging-node meshes (PS:168)
+    const double* Ks = c->fp.hang.n ? c->Kc.p : c->K.p;
+    pe_vec_axpby_vals(c, c->fp.nnz, 1. / c->prm.m_modulus / dt, Ms, c->prm.perm_over_visc, Ks, c->J.p);
     pe_extract_invdiag(c, c->fp, c->J.p, c->invdiag_J.p);
     c->eig_J = 1.1 * pe_estimate_eig_max(c, c->fp, c->J.p, c->invdiag_J.p);
     c->st.eig_max_p = c->eig_J;
@@ -400,6 +473,7 @@ int pe_pressure_solve(pe_ctx* c, int* its, double* res) {
   PE_NEED_SETUP(c);
   require(c->jac_dt > 0, PE_ERR_STATE, "assemble_jacobian first");
   CgResult r = pe_cg_solve(c, c->fp, c->J.p, c->invdiag_J.p, c->eig_J, c->dp.p, c->resid.p, c->prm.cg_rel_tol_pressure, true, &c->st.spmv_launches_p);
+  pe_distribute_hanging(c, c->fp, c->dp.p);  // constraints.distribute(solution_update), PS:180
   c->st.cg_iterations_pressure += r.its;
   c->st.cg_solves_pressure++;
   if (its) *its = r.its;
@@ -425,7 +499,23 @@ int pe_displacement_assemble(pe_ctx* c) {
   PE_ENTER(c)
   PE_NEED_SETUP(c);
   if (!c->matrix_u_built) {  // rebuild_system_matrix (DS:137, DS:280-290)
+    c->fu.bsr.B = 0;
     pe_assemble_elasticity(c);
+    if (c->fu.hang.n) {
+      // The cell kernel treated hanging dofs as free.  Lines that carry an inhomogeneity (a hanging node with a parent on
+      // a Dirichlet face) are eliminated like Dirichlet values: b_const -= A g~ with g~ = g_h on hanging dofs; then the
+      // matrix is condensed (constrained diagonal = the assembled one = sum of the cells' |a_hh|, DS:281-283).
+      if (c->fu.hang.any_g) {
+        pe_scatter_hanging_inhomogeneity(c, c->fu, c->w_d.p);
+        pe_spmv_plain(c, c->fu, c->A.p, c->w_d.p, c->w_h.p);
+        pe_vec_axpy(c, c->fu.n_owned, -1.0, c->w_h.p, c->b_const.p);
+      }
+      DBuf<double> uncondensed;
+      uncondensed.alloc((size_t)c->fu.nnz);
+      PE_CUDA(cudaMemcpyAsync(uncondensed.p, c->A.p, c->fu.nnz * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      pe_condense_matrix(c, c->fu, uncondensed.p, c->A.p, true, 0.0);
+      PE_CUDA(cudaStreamSynchronize(c->stream));
+    }
     pe_extract_invdiag(c, c->fu, c->A.p, c->invdiag_A.p);
     {
       const char* fmt = std::getenv("PE_FORMAT");
@@ -444,6 +534,7 @@ int pe_displacement_assemble(pe_ctx* c) {
     c->matrix_u_built = true;
   }
   pe_assemble_u_rhs(c);
+  pe_condense_vector(c, c->fu, c->b.p);  // rows of hanging dofs go to their masters (DS:281-286); no-op on uniform meshes
   PE_LEAVE(c)
 }
 int pe_displacement_solve(pe_ctx* c, int* its, double* res) {
@@ -452,6 +543,7 @@ int pe_displacement_solve(pe_ctx* c, int* its, double* res) {
   require(c->matrix_u_built, PE_ERR_STATE, "displacement_assemble first");
   CgResult r = pe_cg_solve(c, c->fu, c->A.p, c->invdiag_A.p, c->eig_A, c->u.p, c->b.p, c->prm.cg_abs_tol_displacement, false, &c->st.spmv_launches_u);
   pe_distribute(c, c->fu, c->u.p);  // constraints.distribute(solution), DS:306
+  pe_distribute_hanging(c, c->fu, c->u.p);
   c->st.cg_iterations_displacement += r.its;
   c->st.cg_solves_displacement++;
   if (its) *its = r.its;
@@ -476,6 +568,7 @@ int pe_project_assemble_rhs(pe_ctx* c, int n_comp, const int32_t* comps) {
     entries[k] = sym_entry(c->dim, comps[k]);
   }
   pe_assemble_projection_rhs(c, n_comp, comps, entries);
+  for (int k = 0; k < n_comp; ++k) pe_condense_vector(c, c->fp, c->proj_rhs[entries[k]].p);  // SP:193-194
   PE_LEAVE(c)
 }
 int pe_project_solve(pe_ctx* c, int entry, int* its) {
@@ -484,7 +577,9 @@ int pe_project_solve(pe_ctx* c, int entry, int* its) {
   require(c->proj_matrix_ready, PE_ERR_STATE, "project_assemble_matrix first");
   require(entry >= 0 && entry < c->n_stress, PE_ERR_BAD_INPUT, "rhs entry out of range");
   int64_t dummy = 0;
-  CgResult r = pe_cg_solve(c, c->fp, c->M.p, c->invdiag_M.p, c->eig_M, c->strains[entry].p, c->proj_rhs[entry].p, c->prm.cg_rel_tol_projection, true, &dummy);
+  const double* m_proj = c->fp.hang.n ? c->Mc.p : c->M.p;  // SP:104-105: the condensed mass matrix
+  CgResult r = pe_cg_solve(c, c->fp, m_proj, c->invdiag_M.p, c->eig_M, c->strains[entry].p, c->proj_rhs[entry].p, c->prm.cg_rel_tol_projection, true, &dummy);
+  pe_distribute_hanging(c, c->fp, c->strains[entry].p);  // SP:215
   c->st.spmv_launches_p += dummy;
   c->st.cg_iterations_projection += r.its;
   c->st.cg_solves_projection++;

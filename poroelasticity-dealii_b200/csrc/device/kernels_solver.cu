@@ -796,6 +796,18 @@ double pe_linfty(pe_ctx* c, Field& F, const double* v) {
   return m;
 }
 
+double pe_vec_dot(pe_ctx* c, Field& F, const double* a, const double* b) {
+  const int64_t n = F.n_owned;
+  RedArgs R = red_args(c);
+  k_dot<<<std::min(vec_grid(c, n), PE_MAX_RED_BLOCKS), VEC_T, 0, c->stream>>>(n, nullptr, a, b, R, 0);
+  c->st.kernel_launches++;
+  pe_allreduce_sum(c, c->red.out.p, 1);
+  PE_CUDA(cudaMemcpyAsync(c->h_scalars, c->red.out.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PE_CUDA(cudaStreamSynchronize(c->stream));
+  PE_CUDA(cudaGetLastError());
+  return c->h_scalars[0];
+}
+
 void pe_stress_kernel(pe_ctx* c) {
   const int64_t n = c->fp.n_owned;
   auto E = [&](int i) { return i < c->n_stress ? c->strains[i].p : nullptr; };

@@ -101,6 +101,25 @@ struct Field {
   DBuf<int32_t> cline;     // n_local: line index or -1
   DBuf<int32_t> line_dof;  // n_lines
   DBuf<double> line_g;     // n_lines
+  // Hanging-node lines x_h = sum_m w_hm x_m + g_h (adaptive meshes, PS:74-77 / DS:112-114); masters are free dofs.
+  // The cell kernels treat hanging dofs like free ones; kernels_constraints.cu condenses matrices / vectors afterwards.
+  struct Hanging {
+    int64_t n = 0, n_entries = 0, n_masters = 0;
+    bool any_g = false;
+    std::vector<int32_t> h_dof, h_ptr, h_edof;  // host copies (lines sorted by dof; ptr has n+1 entries)
+    std::vector<double> h_w, h_g;
+    DBuf<int32_t> hline;                         // n_local: hanging line of a dof or -1
+    DBuf<int32_t> dof, ptr, edof;
+    DBuf<double> w, g;
+    DBuf<int32_t> tline_of;                      // n_local: slot in the transposed table or -1
+    DBuf<int32_t> t_master, t_ptr, t_line;       // per master: the hanging lines that refer to it ...
+    DBuf<double> t_w;                            // ... and their weights
+    void clear() {
+      n = n_entries = n_masters = 0;
+      any_g = false;
+      h_dof.clear(); h_ptr.clear(); h_edof.clear(); h_w.clear(); h_g.clear();
+    }
+  } hang;
   // CSR pattern of the owned rows, columns ascending (local ids)
   DBuf<int32_t> rowptr, col;
   int64_t nnz = 0;
@@ -196,6 +215,7 @@ struct pe_ctx {
 
   // matrices (values on the field patterns) and inverse diagonals
   DBuf<double> M, K, J, A;
+  DBuf<double> Mc, Kc;  // ConstraintMatrix::condense of M and K (hanging-node meshes only): J = Mc/(M_b dt) + (k/mu) Kc, projection matrix = Mc
   DBuf<double> invdiag_M, invdiag_J, invdiag_A;
   double jac_dt = -1;
   bool matrix_u_built = false, proj_matrix_ready = false;
@@ -242,6 +262,15 @@ void pe_build_pattern(pe_ctx* c, Field& F);
 bool pe_build_bsr(pe_ctx* c, Field& F, const double* csr_val);  // false when the matrix has no block structure
 int64_t pe_exclusive_scan_i32(pe_ctx* c, int32_t* data, int64_t n);  // in place, n+1 entries written (last = total)
 
+// ---- kernels_constraints.cu (hanging-node lines; active only when a field has lines with entries)
+void pe_hanging_upload(pe_ctx* c, Field& F);
+void pe_build_pattern_lists(pe_ctx* c, Field& F);  // pattern of cell lists extended by the masters of hanging dofs
+void pe_condense_matrix(pe_ctx* c, Field& F, const double* src, double* dst, bool keep_diag, double hang_diag);
+void pe_condense_vector(pe_ctx* c, Field& F, double* v);
+void pe_distribute_hanging(pe_ctx* c, Field& F, double* v);
+void pe_scatter_hanging_inhomogeneity(pe_ctx* c, Field& F, double* v);  // v = 0 except g_h on hanging dofs
+double pe_avg_abs_diag(pe_ctx* c, Field& F, const double* val);
+
 // ---- kernels_assembly.cu
 void pe_build_tables(pe_ctx* c);
 void pe_color_cells(pe_ctx* c);
@@ -269,6 +298,7 @@ void pe_distribute(pe_ctx* c, Field& F, double* v);  // constrained dofs <- inho
 double pe_linfty(pe_ctx* c, Field& F, const double* v);
 void pe_stress_kernel(pe_ctx* c);
 void pe_allreduce_sum(pe_ctx* c, double* dev, int count, bool in_solve = false);
+double pe_vec_dot(pe_ctx* c, Field& F, const double* a, const double* b);  // global dot product over owned entries
 // ---- kernels_comm.cu
 void pe_comm_setup(pe_ctx* c, size_t n_work);  // allocates the region (+ IPC exchange when nranks > 1)
 void pe_comm_release(pe_ctx* c);

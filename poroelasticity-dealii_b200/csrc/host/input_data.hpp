@@ -89,7 +89,7 @@ class InputDataPoroel {
   int chebyshev_degree = 4;
   double chebyshev_eig_ratio = 30.0;
   int cg_max_iterations = 1000;     // PS:175, DS:299, SP:209
-  int refine_every = 0;             // reference: 5 (FSS:333); AMR is out of scope => 0 = never
+  int refine_every = 0;             // reference: 5 (FSS:333); 0 = never (uniform-mesh benchmarks, partitioned runs)
   int couple_volumetric_strain = 0; // 1 re-enables FSS:399
   int write_vtk = 0;                // FSS:411
   int max_time_steps = 0;           // 0 = until t_max

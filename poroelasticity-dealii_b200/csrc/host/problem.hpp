@@ -7,7 +7,9 @@
 //   * mechanics -> flow feedback off unless `Couple volumetric strain = 1` (FSS:399 is commented out);
 //   * the initial volumetric strain is the reference state for all steps (FSS:317, PS:122-124);
 //   * create_mesh() is the default, read_mesh() optional (FSS:297-298).
-// AMR (FSS:333-340) is out of scope: `Refine every` must be 0.
+// Adaptive refinement (FSS:333-340, refine_mesh FSS:447-498) runs every `Refine every` steps (reference: 5; default 0 =
+// never, the configuration of the BASELINE benchmarks) on one rank: amr.hpp provides the refinement forest, the Kelly
+// estimator, the marking and the solution transfer; hanging-node constraints go to the device as general lines.
 #pragma once
 #include <cstdio>
 #include <memory>
@@ -16,6 +18,7 @@
 #include <vector>
 
 #include "../../../include/poroel.h"
+#include "amr.hpp"
 #include "dofs.hpp"
 #include "input_data.hpp"
 #include "mesh.hpp"
@@ -82,44 +85,64 @@ class PoroElasticProblem {
     if (rc != 0) throw std::runtime_error(std::string(what) + ": " + pe_last_error(ctx) + " (status " + std::to_string(rc) + ")");
   }
 
-  // FSS:297-317
-  void initialize(bool verbose) {
-    if (data.refine_every != 0) throw std::runtime_error("adaptive refinement (FSS:333-340) is out of scope: set 'Refine every = 0'");
-    // create_mesh() / read_mesh()
-    if (data.mesh_from_file) global_mesh = mesh::read_msh(data.mesh_file, dim);
-    else if (data.cells_per_axis[0] > 0) global_mesh = mesh::create_subdivided(dim, data.domain_size.data(), data.cells_per_axis);
-    else global_mesh = mesh::create_hyper_rectangle(dim, data.domain_size.data(), data.initial_refinement_level);
-    // setup_dofs(): distribute_dofs for both handlers (PS:73, DS:110)
-    dofs::DofMap dp = dofs::distribute_dofs(global_mesh, 1, 1);
-    dofs::DofMap du = dofs::distribute_dofs(global_mesh, data.displacement_degree, dim);
+  // setup_dofs() (FSS:131-151) on the current mesh + upload + pe_setup
+  void setup_dofs() {
+    const bool adaptive = data.refine_every != 0;
+    // distribute_dofs for both handlers (PS:73, DS:110)
+    dofs::NodeMaps maps_p, maps_u;
+    dofs_p = dofs::distribute_dofs(global_mesh, 1, 1, adaptive ? &maps_p : nullptr);
+    dofs::DofMap du = dofs::distribute_dofs(global_mesh, data.displacement_degree, dim, adaptive ? &maps_u : nullptr);
+    const dofs::DofMap& dp = dofs_p;
     n_global_p = dp.n_dofs;
     n_global_u = du.n_dofs;
-    // displacement_solver.set_boundary_conditions (FSS:300-306) -> Dirichlet lines (DS:117-135)
-    dofs::Constraints cons = dofs::make_dirichlet(global_mesh, du, data.displacement_boundary_labels,
-                                                  data.displacement_boundary_components, data.displacement_boundary_values);
     pe_params prm = params_from_input(data);
     check(pe_set_params(ctx, &prm), "pe_set_params");
     const mesh::Mesh* lm = &global_mesh;
     const int32_t *cdp = dp.cell_dofs.data(), *cdu = du.cell_dofs.data();
     int64_t nlp = dp.n_dofs, nlu = du.n_dofs;
-    std::vector<int32_t> line_dof = cons.line_dof;
-    std::vector<double> line_g = cons.inhomogeneity;
+    std::vector<int32_t> line_dof, entry_dof, p_line_dof, p_entry_dof;
+    std::vector<int64_t> entry_ptr, p_entry_ptr;
+    std::vector<double> line_g, entry_w, p_line_g, p_entry_w;
+    if (adaptive) {
+      // hanging-node lines first, then the Dirichlet values on dofs that are still free, then close (PS:71-78, DS:109-137)
+      dofs::ConstraintTable tp, tu;
+      tp.init(dp.n_dofs);
+      amr::hanging_node_constraints(forest, global_mesh, dp, maps_p, tp);
+      tp.close();
+      tp.flatten(p_line_dof, p_entry_ptr, p_entry_dof, p_entry_w, p_line_g);
+      tu.init(du.n_dofs);
+      amr::hanging_node_constraints(forest, global_mesh, du, maps_u, tu);
+      dofs::add_dirichlet(tu, global_mesh, du, data.displacement_boundary_labels, data.displacement_boundary_components,
+                          data.displacement_boundary_values);
+      tu.close();
+      tu.flatten(line_dof, entry_ptr, entry_dof, entry_w, line_g);
+      n_hanging_p = (int64_t)p_line_dof.size();
+    } else {
+      // displacement_solver.set_boundary_conditions (FSS:300-306) -> Dirichlet lines (DS:117-135)
+      dofs::Constraints cons = dofs::make_dirichlet(global_mesh, du, data.displacement_boundary_labels,
+                                                    data.displacement_boundary_components, data.displacement_boundary_values);
+      line_dof = cons.line_dof;
+      line_g = cons.inhomogeneity;
+      if (nranks > 1) {
+        part = partition::make_part(global_mesh, dp, du, rank, nranks);
+        lm = &part.mesh;
+        cdp = part.field[0].cell_dofs.data();
+        cdu = part.field[1].cell_dofs.data();
+        nlp = part.field[0].n_local;
+        nlu = part.field[1].n_local;
+        std::vector<int32_t> g2l(du.n_dofs, -1);
+        for (int64_t i = 0; i < nlu; ++i) g2l[part.field[1].local_to_global[i]] = (int32_t)i;
+        line_dof.clear();
+        line_g.clear();
+        std::vector<std::pair<int32_t, double>> ll;
+        for (size_t i = 0; i < cons.line_dof.size(); ++i)
+          if (g2l[cons.line_dof[i]] >= 0) ll.push_back({g2l[cons.line_dof[i]], cons.inhomogeneity[i]});
+        std::sort(ll.begin(), ll.end());
+        for (auto& e : ll) { line_dof.push_back(e.first); line_g.push_back(e.second); }
+      }
+      entry_ptr.assign(line_dof.size() + 1, 0);
+    }
     if (nranks > 1) {
-      part = partition::make_part(global_mesh, dp, du, rank, nranks);
-      lm = &part.mesh;
-      cdp = part.field[0].cell_dofs.data();
-      cdu = part.field[1].cell_dofs.data();
-      nlp = part.field[0].n_local;
-      nlu = part.field[1].n_local;
-      std::vector<int32_t> g2l(du.n_dofs, -1);
-      for (int64_t i = 0; i < nlu; ++i) g2l[part.field[1].local_to_global[i]] = (int32_t)i;
-      line_dof.clear();
-      line_g.clear();
-      std::vector<std::pair<int32_t, double>> ll;
-      for (size_t i = 0; i < cons.line_dof.size(); ++i)
-        if (g2l[cons.line_dof[i]] >= 0) ll.push_back({g2l[cons.line_dof[i]], cons.inhomogeneity[i]});
-      std::sort(ll.begin(), ll.end());
-      for (auto& e : ll) { line_dof.push_back(e.first); line_g.push_back(e.second); }
       global_ids[0] = std::vector<int64_t>(part.field[0].local_to_global.begin(), part.field[0].local_to_global.begin() + part.field[0].n_owned);
       global_ids[1] = std::vector<int64_t>(part.field[1].local_to_global.begin(), part.field[1].local_to_global.begin() + part.field[1].n_owned);
     } else {
@@ -132,9 +155,11 @@ class PoroElasticProblem {
                          lm->bface_cell.data(), lm->bface_local.data(), lm->bface_id.data()), "pe_upload_mesh");
     check(pe_upload_dofs(ctx, PE_FIELD_PRESSURE, nlp, cdp), "pe_upload_dofs(p)");
     check(pe_upload_dofs(ctx, PE_FIELD_DISPLACEMENT, nlu, cdu), "pe_upload_dofs(u)");
-    std::vector<int64_t> eptr(line_dof.size() + 1, 0);
-    check(pe_upload_constraints(ctx, PE_FIELD_DISPLACEMENT, (int64_t)line_dof.size(), line_dof.data(), eptr.data(), nullptr, nullptr, line_g.data()),
-          "pe_upload_constraints");
+    if (adaptive)
+      check(pe_upload_constraints(ctx, PE_FIELD_PRESSURE, (int64_t)p_line_dof.size(), p_line_dof.data(), p_entry_ptr.data(), p_entry_dof.data(),
+                                  p_entry_w.data(), p_line_g.data()), "pe_upload_constraints(p)");
+    check(pe_upload_constraints(ctx, PE_FIELD_DISPLACEMENT, (int64_t)line_dof.size(), line_dof.data(), entry_ptr.data(), entry_dof.data(),
+                                entry_w.data(), line_g.data()), "pe_upload_constraints(u)");
     std::vector<int32_t> nl(data.stress_boundary_labels.begin(), data.stress_boundary_labels.end()),
         ncmp(data.stress_boundary_components.begin(), data.stress_boundary_components.end());
     check(pe_upload_neumann(ctx, (int)nl.size(), nl.data(), ncmp.data(), data.stress_boundary_values.data()), "pe_upload_neumann");
@@ -146,7 +171,25 @@ class PoroElasticProblem {
       }
     local_mesh = lm;
     check(pe_setup(ctx), "pe_setup");
-    if (nranks == 1) { /* keep the global mesh for output */ }
+  }
+
+  // FSS:297-317
+  void initialize(bool verbose) {
+    if (data.refine_every < 0) throw std::runtime_error("'Refine every' must be >= 0");
+    if (data.refine_every != 0 && nranks != 1)
+      throw std::runtime_error("adaptive refinement (FSS:333-340) runs on one rank: set 'Refine every = 0' for partitioned runs");
+    // create_mesh() / read_mesh()
+    if (data.mesh_from_file) global_mesh = mesh::read_msh(data.mesh_file, dim);
+    else if (data.cells_per_axis[0] > 0) global_mesh = mesh::create_subdivided(dim, data.domain_size.data(), data.cells_per_axis);
+    else global_mesh = mesh::create_hyper_rectangle(dim, data.domain_size.data(), data.initial_refinement_level);
+    if (data.refine_every != 0) {
+      // the cells of the initial mesh are the roots of the refinement forest; for create_mesh() they sit at level
+      // `Initial refinement level`, which FSS:335 also passes as the coarsest level the estimator may go back to
+      const bool refined_box = !data.mesh_from_file && data.cells_per_axis[0] <= 0;
+      forest = amr::Forest::from_mesh(global_mesh, refined_box ? data.initial_refinement_level : 0);
+      global_mesh = forest.active_mesh();
+    }
+    setup_dofs();
 
     // Initialize reservoir (FSS:310-317)
     check(pe_pressure_set_uniform(ctx, data.p_init), "pressure_set_uniform");
@@ -161,6 +204,35 @@ class PoroElasticProblem {
     get_volumetric_strain(/*as_initial=*/true);
     time = 0;
     time_step_number = 0;
+  }
+
+  // refine_mesh (FSS:447-498)
+  void refine_mesh(int min_grid_level, int max_grid_level) {
+    const int64_t n_old = n_global_p;
+    std::vector<double> p(n_old), ev(n_old), ev0(n_old);
+    check(pe_get_vector(ctx, PE_VEC_P, p.data(), n_old), "get p");
+    check(pe_get_vector(ctx, PE_VEC_VOL_STRAIN, ev.data(), n_old), "get volumetric_strain");
+    check(pe_get_vector(ctx, PE_VEC_VOL_STRAIN0, ev0.data(), n_old), "get initial_volumetric_strain");
+    // KellyErrorEstimator on the pressure solution (FSS:452-458)
+    std::vector<double> vertex_value(forest.n_vertices(), 0.0);
+    const int vpc = global_mesh.vpc();
+    for (int64_t c = 0; c < global_mesh.n_cells(); ++c)
+      for (int k = 0; k < vpc; ++k) vertex_value[global_mesh.cell_vertices[c * vpc + k]] = p[dofs_p.cell_dofs[c * vpc + k]];
+    std::vector<float> estimated_error_per_cell = amr::kelly_estimate(forest, vertex_value);
+    amr::mark_fixed_fraction(forest, estimated_error_per_cell, 0.6, 0.4, min_grid_level, max_grid_level);  // FSS:460-472
+    // SolutionTransfer of {pressure, volumetric strain, initial volumetric strain} (FSS:475-497)
+    const double* in[3] = {p.data(), ev.data(), ev0.data()};
+    forest.store_vertex_values(global_mesh, dofs_p, 3, in);
+    auto counts = forest.execute();  // prepare_coarsening_and_refinement + execute_coarsening_and_refinement
+    last_refinement = counts;
+    global_mesh = forest.active_mesh();
+    setup_dofs();
+    std::vector<double> q(n_global_p), qv(n_global_p), qv0(n_global_p);
+    double* out[3] = {q.data(), qv.data(), qv0.data()};
+    forest.fetch_vertex_values(global_mesh, dofs_p, 3, out);
+    check(pe_set_vector(ctx, PE_VEC_P, q.data(), n_global_p), "set p");
+    check(pe_set_vector(ctx, PE_VEC_VOL_STRAIN, qv.data(), n_global_p), "set volumetric_strain");
+    check(pe_set_vector(ctx, PE_VEC_VOL_STRAIN0, qv0.data(), n_global_p), "set initial_volumetric_strain");
   }
 
   // FSS:153-164
@@ -200,6 +272,15 @@ class PoroElasticProblem {
     R.time_step_number = time_step_number;
     const bool out = verbose && rank == 0;
     if (out) std::printf("Time: %g\n", time);
+    if (data.refine_every > 0 && time_step_number % data.refine_every == 0) {  // FSS:333-340
+      if (out) std::printf("Refining mesh\n");
+      refine_mesh(data.initial_refinement_level, data.initial_refinement_level + data.max_refinement_level);
+      check(pe_displacement_assemble(ctx), "displacement_assemble");
+      check(pe_project_assemble_matrix(ctx), "project_assemble_matrix");
+      if (out)
+        std::printf("    %lld active cells, %lld pressure dofs (%lld hanging), %d families coarsened, %d cells refined\n",
+                    (long long)global_mesh.n_cells(), (long long)n_global_p, (long long)n_hanging_p, last_refinement.first, last_refinement.second);
+    }
     check(pe_pressure_begin_step(ctx), "begin_step");  // FSS:342
     double pressure_error = data.pressure_tol * 2;      // FSS:345
     int fss_iteration = 0;
@@ -265,7 +346,7 @@ class PoroElasticProblem {
   void output_results(unsigned int n) {
     if (nranks != 1 || data.displacement_degree != 1) return;  // Q2 displacement would need interpolation to vertices
     const mesh::Mesh& m = global_mesh;
-    dofs::DofMap dp = dofs::distribute_dofs(m, 1, 1);
+    const dofs::DofMap& dp = dofs_p;
     std::vector<double> p(n_global_p), u(n_global_u);
     check(pe_get_vector(ctx, PE_VEC_P, p.data(), n_global_p), "get p");
     check(pe_get_vector(ctx, PE_VEC_U, u.data(), n_global_u), "get u");
@@ -312,6 +393,10 @@ class PoroElasticProblem {
   input_data::InputDataPoroel data;
   int dim = 2, rank = 0, nranks = 1;
   mesh::Mesh global_mesh;
+  amr::Forest forest;          // refinement tree of the adaptive time loop (empty unless 'Refine every' > 0)
+  dofs::DofMap dofs_p;         // pressure handler of the current mesh
+  int64_t n_hanging_p = 0;
+  std::pair<int, int> last_refinement{0, 0};
   const mesh::Mesh* local_mesh = nullptr;
   partition::Part part;
   std::vector<int64_t> global_ids[2];

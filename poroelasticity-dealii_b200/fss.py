@@ -127,3 +127,54 @@ def rel_l2(a, b):
     b = np.asarray(b)
     nb = np.linalg.norm(b)
     return float(np.linalg.norm(a - b) / (nb if nb > 0 else 1.0))
+
+
+# ---- adaptive time loop (FSS:333-340, refine_mesh FSS:447-498) ---------------------------------------------------------
+def make_forest(inp: capi.InputData, mesh: capi.HostMesh):
+    """The initial mesh's cells become the roots of the refinement forest (csrc/host/problem.hpp::initialize)."""
+    refined_box = not inp.mesh_from_file and inp.cells_per_axis[0] <= 0
+    return capi.Forest(mesh, inp.initial_refinement_level if refined_box else 0)
+
+
+def refine_mesh(b: capi.OperatorBackend, inp: capi.InputData, forest: capi.Forest, mesh: capi.HostMesh, dofs_p: capi.HostDofs,
+                top_fraction=0.6, bottom_fraction=0.4):
+    """refine_mesh(initial, initial + max) of FSS:335-337 followed by setup_dofs and the solution transfer; returns the new
+    (mesh, dofs_p, dofs_u, report).  The caller re-assembles (FSS:338-339)."""
+    p, ev, ev0 = b.get_vector(capi.VEC_P), b.get_vector(capi.VEC_VOL_STRAIN), b.get_vector(capi.VEC_VOL_STRAIN0)
+    eta = forest.kelly(mesh, dofs_p, p)  # FSS:452-458
+    forest.mark_fixed_fraction(eta, top_fraction, bottom_fraction, inp.initial_refinement_level,
+                               inp.initial_refinement_level + inp.max_refinement_level)  # FSS:460-472
+    forest.store(mesh, dofs_p, [p, ev, ev0])  # FSS:475-479
+    n_coarsened, n_refined = forest.execute()  # FSS:481-483
+    new_mesh = forest.active_mesh()
+    new_p, new_u, (Lp, Lu) = upload_problem(b, inp, new_mesh, forest=forest)  # setup_dofs(), FSS:485
+    vals = forest.fetch(new_mesh, new_p, 3)  # FSS:488-497
+    b.set_vector(capi.VEC_P, vals[0])
+    b.set_vector(capi.VEC_VOL_STRAIN, vals[1])
+    b.set_vector(capi.VEC_VOL_STRAIN0, vals[2])
+    report = {"n_cells": new_mesh.arrays.n_cells, "n_dofs_p": new_p.n_dofs, "n_dofs_u": new_u.n_dofs, "n_hanging_p": Lp.n_lines,
+              "n_coarsened_families": n_coarsened, "n_refined_cells": n_refined, "eta_max": float(eta.max()), "levels": forest.levels()}
+    return new_mesh, new_p, new_u, report
+
+
+def run_adaptive(b: capi.OperatorBackend, inp: capi.InputData, n_steps, refine_every, on_step=None):
+    """PoroElasticProblem::run (FSS:294-415) with the reference's every-n-th-step refinement; returns the final
+    (forest, mesh, dofs_p, dofs_u) and the per-step reports."""
+    mesh0 = make_mesh(inp)
+    forest = make_forest(inp, mesh0)
+    mesh = forest.active_mesh()
+    dofs_p, dofs_u, _ = upload_problem(b, inp, mesh, forest=forest)
+    initialize(b, inp)
+    reports = []
+    for step in range(1, n_steps + 1):
+        amr = None
+        if refine_every > 0 and step % refine_every == 0:  # FSS:333
+            mesh, dofs_p, dofs_u, amr = refine_mesh(b, inp, forest, mesh, dofs_p)
+            b.displacement_assemble()    # FSS:338
+            b.project_assemble_matrix()  # FSS:339
+        rep = time_step(b, inp)
+        rep["amr"] = amr
+        reports.append(rep)
+        if on_step:
+            on_step(step, rep, mesh, dofs_p, dofs_u)
+    return forest, mesh, dofs_p, dofs_u, reports

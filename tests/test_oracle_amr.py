@@ -166,3 +166,75 @@ def test_uniform_mesh_through_the_constraint_path_equals_the_plain_path():
         out.append((b.get_vector(capi.VEC_P), b.get_vector(capi.VEC_U), rep["inner_counts"], rep["cg_its_displacement"]))
         b.close()
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2:] == out[1][2:]
+
+
+def test_adaptive_time_loop_of_the_shipped_case():
+    """input.data as shipped with the reference's every-5th-step refinement (FSS:333-340): 17 steps, AMR at 5, 10, 15."""
+    inp = capi.InputData(text=H.SHIPPED_INPUT + "\nsubsection GPU\n  set Refine every = 5\nend\n")
+    assert inp.refine_every == 5
+    b = H.create_oracle_backend()
+    seen = {}
+
+    state = {}
+
+    def on_step(step, rep, mesh, dp, du):
+        if rep["amr"]:
+            seen[step] = rep["amr"]
+            state["L"] = capi.make_constraints(state["F"], mesh, dp)
+        assert rep["fss_iterations"] == 1 and rep["pressure_error"] < inp.fss_tol
+        if "L" in state and rep["cg_its_pressure"] > 0:  # every pressure update is distributed (PS:180) -> conforming
+            L, dpv = state["L"], b.get_vector(capi.VEC_P_UPDATE)
+            assert np.abs(dpv).max() > 0
+            for i in range(L.n_lines):
+                d, ed, ew, _ = L.line(i)
+                assert abs(dpv[d] - dpv[ed] @ ew) <= 1e-12 * np.abs(dpv).max()
+
+    _make_forest = fss.make_forest
+
+    def spy(inp_, mesh_):
+        state["F"] = _make_forest(inp_, mesh_)
+        return state["F"]
+
+    fss.make_forest = spy
+    try:
+        F, mesh, dp, du, reps = fss.run_adaptive(b, inp, 17, inp.refine_every, on_step)
+    finally:
+        fss.make_forest = _make_forest
+
+    assert sorted(seen) == [5, 10, 15]
+    lo_level, hi_level = inp.initial_refinement_level, inp.initial_refinement_level + inp.max_refinement_level
+    n_prev = 256
+    for step in (5, 10, 15):
+        a = seen[step]
+        assert a["n_refined_cells"] > 0 and a["n_hanging_p"] > 0
+        assert a["levels"].min() >= lo_level and a["levels"].max() <= hi_level
+        assert a["levels"].max() == lo_level + step // 5  # one more level per pass
+        assert a["n_cells"] == n_prev + 3 * a["n_refined_cells"] - 3 * a["n_coarsened_families"]
+        n_prev = a["n_cells"]
+    # the estimator sends the refinement to the well (r_well = 1 around the origin, input.data:33)
+    m = mesh.arrays
+    ctr = m.xyz[m.cell_vertices].mean(axis=1)
+    lv = F.levels()
+    r = np.linalg.norm(ctr, axis=1)
+    assert r[lv == lv.max()].max() < 3.0 and lv[r > 4.5].max() < lv.max()
+    # As-is quirk kept: SolutionTransfer leaves a node that BECOMES hanging through coarsening at its old value and the
+    # reference never distributes the transferred pressure (FSS:488-497), so p itself may be slightly non-conforming
+    # there; the offsets are of the size of the interpolation error.
+    Lp = capi.make_constraints(F, mesh, dp)
+    p = b.get_vector(capi.VEC_P)
+    gap = max(abs(p[Lp.line(i)[0]] - p[Lp.line(i)[1]] @ Lp.line(i)[2]) for i in range(Lp.n_lines))
+    assert gap <= 1e-2 * (p.max() - p.min())
+    b2 = H.create_oracle_backend()
+    mesh0 = fss.make_mesh(inp)
+    dp0, _, _ = fss.upload_problem(b2, inp, mesh0)
+    fss.initialize(b2, inp)
+    for _ in range(17):
+        fss.time_step(b2, inp)
+    p0 = b2.get_vector(capi.VEC_P)
+    x0, x1 = dp0.support_points(), dp.support_points()
+    common = {key(x): i for i, x in enumerate(x1)}
+    idx = np.array([common[key(x)] for x in x0])  # every vertex of the initial mesh is still a vertex
+    assert np.abs(p[idx] - p0).max() <= 2e-3 * (p0.max() - p0.min())
+    assert abs(p.max() - p0.max()) <= 1e-3 * p0.max()
+    b.close()
+    b2.close()
