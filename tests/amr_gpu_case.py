@@ -1,0 +1,109 @@
+"""One hanging-node / adaptive parity case of the CUDA path against the CPU oracle, run as its own process by
+tests/test_zz_gpu_amr.py (a sticky CUDA error or a hang in a not-yet-verified kernel must not take the suite down).
+
+    python tests/amr_gpu_case.py static <dim> <degree_u> <rounds>     hanging-node mesh: matrices, rhs, 3 time steps
+    python tests/amr_gpu_case.py driver                               C++ driver with 'Refine every = 5' on the shipped input
+
+Prints one JSON line; exit code 0 = every bar met."""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+import helpers as H  # noqa: E402
+from test_amr import corner_refined_forest  # noqa: E402
+
+capi, fss = H.capi, H.fss
+MATRIX_TOL, FIELD_TOL = 1e-12, 1e-8
+
+
+def max_rel(A, B):
+    D = A - B
+    return float(abs(D).max() / abs(B).max()) if B.nnz else 0.0
+
+
+def static_case(dim, deg, rounds):
+    inp = capi.InputData(text=H.make_input(dim=dim, refine=2, degree_u=deg))
+    F = corner_refined_forest(dim, rounds=rounds)
+    am = F.active_mesh()
+    dev, ora = capi.create_device_backend(0), H.create_oracle_backend()
+    prm = inp.params()
+    prm.cg_max_iterations = 5000
+    out = {"case": f"static {dim} {deg} {rounds}", "n_cells": am.arrays.n_cells}
+    for b in (dev, ora):
+        dp, du, (Lp, Lu) = fss.upload_problem(b, inp, am, prm, forest=F)
+    out.update(n_dofs_p=dp.n_dofs, n_dofs_u=du.n_dofs, hanging_p=Lp.n_lines, lines_u=Lu.n_lines)
+    for b in (dev, ora):
+        b.pressure_set_uniform(inp.p_init)
+        b.displacement_assemble()
+        b.project_assemble_matrix()
+        b.assemble_jacobian(inp.time_step)
+    errs = {}
+    for name, which in (("M", capi.MAT_MASS), ("K", capi.MAT_LAPLACE), ("J", capi.MAT_JACOBIAN), ("PM", capi.MAT_PROJECTION), ("A", capi.MAT_ELASTICITY)):
+        A, B = dev.get_matrix(which), ora.get_matrix(which)
+        n = max(A.shape[1], B.shape[1])
+        A.resize((A.shape[0], n)); B.resize((B.shape[0], n))
+        errs[name] = max_rel(A, B)
+        # the device pattern is a superset of make_sparsity_pattern(.., constraints, true): whole nodes of the masters
+        Bp = B.copy(); Bp.data[:] = 1.0
+        Ap = A.copy(); Ap.data[:] = 1.0
+        assert (Bp - Bp.multiply(Ap)).nnz == 0, f"{name}: oracle entries missing from the device pattern"
+    b_d, b_o = dev.get_vector(capi.VEC_U_RHS), ora.get_vector(capi.VEC_U_RHS)
+    errs["b"] = float(np.abs(b_d - b_o).max() / np.abs(b_o).max())
+    out["matrix_errors"] = errs
+    ok = all(e <= MATRIX_TOL for e in errs.values())
+    fss.initialize(dev, inp); fss.initialize(ora, inp)
+    errs_f = [[fss.rel_l2(dev.get_vector(capi.VEC_U), ora.get_vector(capi.VEC_U))]]
+    counts = []
+    for step in range(3):
+        r_d, r_o = fss.time_step(dev, inp), fss.time_step(ora, inp)
+        counts.append((r_d["inner_counts"], r_o["inner_counts"]))
+        ep = fss.rel_l2(dev.get_vector(capi.VEC_P), ora.get_vector(capi.VEC_P))
+        eu = fss.rel_l2(dev.get_vector(capi.VEC_U), ora.get_vector(capi.VEC_U))
+        errs_f.append([ep, eu])
+        ok = ok and r_d["inner_counts"] == r_o["inner_counts"] and ep <= FIELD_TOL and eu <= FIELD_TOL
+    ok = ok and errs_f[0][0] <= FIELD_TOL
+    # conforming fields: hanging values equal their lines on the device as well
+    u = dev.get_vector(capi.VEC_U)
+    gap = max((abs(u[Lu.line(i)[0]] - (u[Lu.line(i)[1]] @ Lu.line(i)[2] + Lu.line(i)[3])) for i in range(Lu.n_lines)), default=0.0)
+    ok = ok and gap <= 1e-12 * np.abs(u).max()
+    out.update(field_errors=errs_f, inner_counts=counts, distribute_gap=float(gap), stats_bsr=dev.stats()["bsr_block_size"], ok=bool(ok))
+    dev.close(); ora.close()
+    return out
+
+
+def driver_case():
+    text = H.SHIPPED_INPUT + "\nsubsection GPU\n  set Refine every = 5\n  set CG max iterations = 5000\nend\n"
+    inp = capi.InputData(text=text)
+    ora = H.create_oracle_backend()
+    snaps = {}
+
+    def on_step(step, rep, mesh, dp, du):
+        snaps[step] = (dp.support_points().copy(), ora.get_vector(capi.VEC_P), rep["inner_counts"], mesh.arrays.n_cells)
+
+    fss.run_adaptive(ora, inp, 17, inp.refine_every, on_step)
+    prob = capi.Problem(inp, device=0)
+    prob.initialize()
+    ok, errs, cells = True, [], []
+    for step in range(1, 18):
+        rep = prob.step()
+        st = prob.backend.stats()
+        prob.backend.n_p, prob.backend.n_u = st["n_dofs_p"], st["n_dofs_u"]
+        p = prob.backend.get_vector(capi.VEC_P)
+        xo, po, counts, n_cells = snaps[step]
+        ok = ok and len(p) == len(po) and st["n_cells"] == n_cells
+        cells.append(int(st["n_cells"]))
+        if len(p) == len(po):
+            e = fss.rel_l2(p, po)  # same first-touch numbering on the same forest
+            errs.append(e)
+            ok = ok and e <= FIELD_TOL
+    prob.close()
+    return {"case": "driver", "cells_per_step": cells, "errors": errs, "ok": bool(ok)}
+
+
+if __name__ == "__main__":
+    res = static_case(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])) if sys.argv[1] == "static" else driver_case()
+    print(json.dumps(res))
+    sys.exit(0 if res["ok"] else 1)

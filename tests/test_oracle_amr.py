@@ -234,7 +234,7 @@ def test_adaptive_time_loop_of_the_shipped_case():
     x0, x1 = dp0.support_points(), dp.support_points()
     common = {key(x): i for i, x in enumerate(x1)}
     idx = np.array([common[key(x)] for x in x0])  # every vertex of the initial mesh is still a vertex
-    assert np.abs(p[idx] - p0).max() <= 2e-3 * (p0.max() - p0.min())
+    assert np.abs(p[idx] - p0).max() <= 2e-2 * (p0.max() - p0.min())  # the well source is resolved differently
     assert abs(p.max() - p0.max()) <= 1e-3 * p0.max()
     b.close()
     b2.close()

@@ -1,0 +1,37 @@
+"""GPU parity of the hanging-node / adaptive path against the CPU oracle.
+
+STATUS: the device kernels of csrc/device/kernels_constraints.cu were written after this round's GPU budget was spent;
+they compile for sm_100a and the algorithm they implement (E^T A E on assembled objects) is verified on the CPU against
+the oracle by tests/test_oracle_amr.py, but they have NOT run on a GPU yet.  The cases are therefore expected to pass
+but marked xfail(strict=False), run last (file name) and each in its own process with a timeout, so that an unverified
+path can neither hide behind nor take down the verified suite.  Remove the marker once a GPU run is green.
+"""
+import json
+import subprocess
+import sys
+
+import pytest
+
+import helpers as H
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="hanging-node kernels not yet executed on a GPU (round-1 budget spent)")]
+
+
+def run_case(*args):
+    r = subprocess.run([sys.executable, str(H.ROOT / "tests" / "amr_gpu_case.py"), *map(str, args)], capture_output=True, text=True, timeout=900)
+    line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "{}"
+    print(line)
+    print(r.stderr[-2000:])
+    assert r.returncode == 0, (r.returncode, line, r.stderr[-2000:])
+    return json.loads(line)
+
+
+@pytest.mark.parametrize("dim,deg,rounds", [(2, 1, 3), (2, 2, 3), (3, 1, 2), (3, 2, 1)])
+def test_hanging_node_mesh_matches_oracle(dim, deg, rounds):
+    res = run_case("static", dim, deg, rounds)
+    assert res["ok"] and res["hanging_p"] > 0
+
+
+def test_adaptive_driver_matches_the_oracle_mirror():
+    res = run_case("driver")
+    assert res["ok"] and max(res["cells_per_step"]) > 256
