@@ -60,6 +60,9 @@ typedef struct peh_mesh_view {
 peh_mesh* peh_mesh_create_rectangle(int dim, const double* size, int refine_level);  /* FSS:418-435 */
 peh_mesh* peh_mesh_create_subdivided(int dim, const double* size, const int32_t* n);
 peh_mesh* peh_mesh_read_msh(const char* path, int dim);                              /* FSS:438-445 */
+/* Morton order of the cell centroids: contiguous cell ranges become compact subdomains (partitioned unstructured meshes) */
+int  peh_mesh_reorder_sfc(peh_mesh*, int64_t* perm_new_to_old_or_null);
+int  peh_mesh_permute_cells(peh_mesh*, const int64_t* perm_new_to_old);
 void peh_mesh_destroy(peh_mesh*);
 int  peh_mesh_view_get(const peh_mesh*, peh_mesh_view* out);
 

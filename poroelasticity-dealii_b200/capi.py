@@ -128,7 +128,7 @@ DEVICE_SYMBOLS = [
 ]
 HOST_SYMBOLS = [
     "peh_last_error", "peh_input_create", "peh_input_destroy", "peh_input_read_file", "peh_input_read_string", "peh_input_view_get",
-    "peh_input_to_params", "peh_mesh_create_rectangle", "peh_mesh_create_subdivided", "peh_mesh_read_msh", "peh_mesh_destroy",
+    "peh_input_to_params", "peh_mesh_create_rectangle", "peh_mesh_create_subdivided", "peh_mesh_read_msh", "peh_mesh_reorder_sfc", "peh_mesh_permute_cells", "peh_mesh_destroy",
     "peh_mesh_view_get", "peh_dofs_distribute", "peh_dofs_destroy", "peh_dofs_view_get", "peh_dofs_support_points", "peh_make_dirichlet",
     "peh_forest_create", "peh_forest_destroy", "peh_forest_active_mesh", "peh_forest_active_levels", "peh_forest_set_flags",
     "peh_forest_get_flags", "peh_forest_prepare", "peh_forest_execute", "peh_forest_kelly", "peh_forest_mark_fixed_fraction",
@@ -238,6 +238,8 @@ def load_host():
     lib.peh_mesh_create_subdivided.restype = P
     lib.peh_mesh_read_msh.argtypes = [C.c_char_p, C.c_int]
     lib.peh_mesh_read_msh.restype = P
+    lib.peh_mesh_reorder_sfc.argtypes = [P, i64p]
+    lib.peh_mesh_permute_cells.argtypes = [P, i64p]
     lib.peh_mesh_destroy.argtypes = [P]
     lib.peh_mesh_view_get.argtypes = [P, C.POINTER(MeshView)]
     lib.peh_dofs_distribute.argtypes = [P, C.c_int, C.c_int]
@@ -333,6 +335,25 @@ class HostMesh:
         v = MeshView()
         load_host().peh_mesh_view_get(handle, C.byref(v))
         self.arrays = Mesh(v)
+
+    def _refresh(self):
+        v = MeshView()
+        load_host().peh_mesh_view_get(self.h, C.byref(v))
+        self.arrays = Mesh(v)
+
+    def reorder_sfc(self):
+        """Morton order of the cell centroids (mesh.hpp::reorder_cells_sfc); returns the permutation new -> old."""
+        perm = np.zeros(self.arrays.n_cells, dtype=np.int64)
+        if load_host().peh_mesh_reorder_sfc(self.h, _p(perm, C.c_int64)) != 0:
+            raise HostError(load_host().peh_last_error().decode())
+        self._refresh()
+        return perm
+
+    def permute_cells(self, perm_new_to_old):
+        perm = np.ascontiguousarray(perm_new_to_old, dtype=np.int64)
+        if load_host().peh_mesh_permute_cells(self.h, _p(perm, C.c_int64)) != 0:
+            raise HostError(load_host().peh_last_error().decode())
+        self._refresh()
 
     def __del__(self):
         if getattr(self, "h", None):

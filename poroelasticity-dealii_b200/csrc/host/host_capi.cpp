@@ -136,6 +136,32 @@ peh_mesh* peh_mesh_read_msh(const char* path, int dim) {
   return m;
   PEH_CATCH(nullptr)
 }
+int peh_mesh_reorder_sfc(peh_mesh* m, int64_t* perm_new_to_old) {
+  PEH_TRY
+  std::vector<int64_t> p = mesh::reorder_cells_sfc(m->m);
+  if (perm_new_to_old) std::memcpy(perm_new_to_old, p.data(), p.size() * sizeof(int64_t));
+  return 0;
+  PEH_CATCH(PE_ERR_BAD_INPUT)
+}
+int peh_mesh_permute_cells(peh_mesh* m, const int64_t* perm_new_to_old) {  // test hook: an arbitrary cell order
+  PEH_TRY
+  mesh::Mesh& M = m->m;
+  const int vpc = M.vpc();
+  const int64_t nc = M.n_cells();
+  std::vector<int64_t> inv((size_t)nc, -1);
+  for (int64_t i = 0; i < nc; ++i) {
+    if (perm_new_to_old[i] < 0 || perm_new_to_old[i] >= nc || inv[perm_new_to_old[i]] >= 0) throw std::runtime_error("not a permutation");
+    inv[perm_new_to_old[i]] = i;
+  }
+  std::vector<int32_t> cv((size_t)nc * vpc);
+  for (int64_t i = 0; i < nc; ++i)
+    for (int v = 0; v < vpc; ++v) cv[i * vpc + v] = M.cell_vertices[perm_new_to_old[i] * vpc + v];
+  M.cell_vertices.swap(cv);
+  for (auto& c : M.bface_cell) c = (int32_t)inv[c];
+  M.morton = false;
+  return 0;
+  PEH_CATCH(PE_ERR_BAD_INPUT)
+}
 void peh_mesh_destroy(peh_mesh* m) { delete m; }
 int peh_mesh_view_get(const peh_mesh* m, peh_mesh_view* v) { fill_mesh_view(m->m, v); return 0; }
 

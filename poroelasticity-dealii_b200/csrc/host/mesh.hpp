@@ -194,4 +194,52 @@ inline Mesh read_msh(const std::string& path, int dim) {
   return m;
 }
 
+// Space-filling-curve cell order for unstructured meshes: cells are sorted by the Morton key of
+// their centroid inside the mesh's bounding box, so that the contiguous cell ranges partition.hpp hands to the ranks are
+// compact subdomains (the same idea as the Z-order of refine_global() on the box) and neighbouring cells are close in
+// memory.  Boundary faces follow their cells.  Returns the permutation new -> old.
+inline std::vector<int64_t> reorder_cells_sfc(Mesh& m) {
+  const int dim = m.dim, vpc = m.vpc();
+  const int64_t nc = m.n_cells();
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  std::vector<double> ctr((size_t)nc * dim, 0.0);
+  for (int64_t c = 0; c < nc; ++c)
+    for (int a = 0; a < dim; ++a) {
+      double s = 0;
+      for (int v = 0; v < vpc; ++v) s += m.xyz[(int64_t)m.cell_vertices[c * vpc + v] * dim + a];
+      s /= vpc;
+      ctr[c * dim + a] = s;
+      lo[a] = std::min(lo[a], s);
+      hi[a] = std::max(hi[a], s);
+    }
+  const int bits = dim == 2 ? 31 : 21;
+  double ext = 0;
+  for (int a = 0; a < dim; ++a) ext = std::max(ext, hi[a] - lo[a]);
+  if (ext <= 0) ext = 1;
+  std::vector<std::pair<uint64_t, int64_t>> keyed((size_t)nc);
+  for (int64_t c = 0; c < nc; ++c) {
+    uint64_t key = 0;
+    for (int a = 0; a < dim; ++a) {
+      // one cube for all axes keeps the curve's cells isotropic
+      const double t = (ctr[c * dim + a] - lo[a]) / ext;
+      uint64_t q = (uint64_t)(t * (double)(((uint64_t)1 << bits) - 1));
+      for (int b = 0; b < bits; ++b) key |= ((q >> b) & 1u) << (b * dim + a);
+    }
+    keyed[c] = {key, c};
+  }
+  std::sort(keyed.begin(), keyed.end());
+  std::vector<int64_t> perm((size_t)nc), inv((size_t)nc);
+  for (int64_t i = 0; i < nc; ++i) { perm[i] = keyed[i].second; inv[keyed[i].second] = i; }
+  std::vector<int32_t> cv((size_t)nc * vpc);
+  for (int64_t i = 0; i < nc; ++i)
+    for (int v = 0; v < vpc; ++v) cv[i * vpc + v] = m.cell_vertices[perm[i] * vpc + v];
+  m.cell_vertices.swap(cv);
+  std::vector<std::array<int32_t, 3>> bf((size_t)m.n_bfaces());
+  for (int64_t b = 0; b < m.n_bfaces(); ++b) bf[b] = {(int32_t)inv[m.bface_cell[b]], (int32_t)m.bface_local[b], m.bface_id[b]};
+  std::sort(bf.begin(), bf.end());
+  for (int64_t b = 0; b < m.n_bfaces(); ++b) { m.bface_cell[b] = bf[b][0]; m.bface_local[b] = (int8_t)bf[b][1]; m.bface_id[b] = bf[b][2]; }
+  m.morton = false;
+  return perm;
+}
+
 }  // namespace mesh

@@ -179,8 +179,12 @@ class PoroElasticProblem {
     if (data.refine_every != 0 && nranks != 1)
       throw std::runtime_error("adaptive refinement (FSS:333-340) runs on one rank: set 'Refine every = 0' for partitioned runs");
     // create_mesh() / read_mesh()
-    if (data.mesh_from_file) global_mesh = mesh::read_msh(data.mesh_file, dim);
-    else if (data.cells_per_axis[0] > 0) global_mesh = mesh::create_subdivided(dim, data.domain_size.data(), data.cells_per_axis);
+    if (data.mesh_from_file) {
+      global_mesh = mesh::read_msh(data.mesh_file, dim);
+      // partitioned runs on unstructured meshes: contiguous cell ranges of a space-filling-curve order are compact
+      // subdomains (every rank computes the same order); single-rank runs keep the file order of GridIn::read_msh
+      if (nranks > 1) mesh::reorder_cells_sfc(global_mesh);
+    } else if (data.cells_per_axis[0] > 0) global_mesh = mesh::create_subdivided(dim, data.domain_size.data(), data.cells_per_axis);
     else global_mesh = mesh::create_hyper_rectangle(dim, data.domain_size.data(), data.initial_refinement_level);
     if (data.refine_every != 0) {
       // the cells of the initial mesh are the roots of the refinement forest; for create_mesh() they sit at level

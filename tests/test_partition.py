@@ -38,7 +38,21 @@ class Part:
         capi.load_host().peh_part_destroy(self.h)
 
 
+def scrambled_box(dim, refine, seed=7):
+    """A structured box whose cells come in random order — the situation of a mesh file written by a mesh generator."""
+    m = capi.mesh_rectangle(dim, [10.0] * dim, refine)
+    rng = np.random.default_rng(seed)
+    m.permute_cells(rng.permutation(m.arrays.n_cells))
+    return m
+
+
 def meshes():
+    sfc = scrambled_box(3, 2)
+    sfc.reorder_sfc()
+    yield "scrambled 4^3 in space-filling-curve order", sfc, 1
+    gm = capi.mesh_read_msh(H.ROOT / "tests" / "golden" / "distorted_hex4.msh", 3)
+    gm.reorder_sfc()
+    yield "distorted Gmsh hexes in space-filling-curve order", gm, 2
     yield "morton 4^3", capi.mesh_rectangle(3, [10, 10, 10], 2), 1
     yield "lexi 5x3x4 Q2", capi.mesh_subdivided(3, [10, 10, 10], [5, 3, 4]), 2
     yield "2d 8x8 Q2", capi.mesh_rectangle(2, [10, 10], 3), 2
@@ -89,6 +103,33 @@ def test_partition_invariants(nranks):
         # boundary faces of the local meshes are domain-boundary faces only
         nb = sum(len(p.mesh.bface_cell) for p in parts)
         assert nb >= len(mesh.arrays.bface_cell)
+
+
+@pytest.mark.parametrize("dim,refine", [(2, 4), (3, 3)])
+def test_space_filling_curve_order_makes_contiguous_ranges_compact(dim, refine):
+    """SURVEY §8f row 4: partitioned unstructured meshes.  mesh.hpp::reorder_cells_sfc must (i) only permute cells (same
+    geometry, same boundary faces), (ii) recover the locality of the Morton order a scrambled mesh has lost: the halo of
+    the partition shrinks from 'nearly everything' to within 1.5x of the structured Morton partition."""
+    ref = capi.mesh_rectangle(dim, [10.0] * dim, refine)
+    bad = scrambled_box(dim, refine)
+    fixed = scrambled_box(dim, refine)
+    perm = fixed.reorder_sfc()
+    a, b = bad.arrays, fixed.arrays
+    assert sorted(perm.tolist()) == list(range(a.n_cells))
+    assert np.array_equal(b.cell_vertices, a.cell_vertices[perm])
+    faces = lambda m: sorted((tuple(sorted(m.cell_vertices[c][[v for v in range(1 << dim) if ((v >> (f // 2)) & 1) == f % 2]])), i)
+                             for c, f, i in zip(m.bface_cell, m.bface_local, m.bface_id))
+    assert faces(a) == faces(b) == faces(ref.arrays)
+    ctr = b.xyz[b.cell_vertices].mean(axis=1)
+    assert np.abs(np.diff(ctr, axis=0)).max(axis=1).mean() < 2.0 * 10.0 / 2 ** refine  # consecutive cells are neighbours on average
+    nranks = 4
+    ghosts = {}
+    for name, mesh in (("morton", ref), ("scrambled", bad), ("sfc", fixed)):
+        dp, du = capi.HostDofs(mesh, 1, 1), capi.HostDofs(mesh, 1, dim)
+        parts = [Part(mesh, dp, du, r, nranks) for r in range(nranks)]
+        ghosts[name] = sum(p.field[1]["n_local"] - p.field[1]["n_owned"] for p in parts)
+    assert ghosts["sfc"] <= 1.5 * ghosts["morton"]
+    assert ghosts["scrambled"] > 2 * ghosts["sfc"]
 
 
 def _worker(rank, world, port, q):
