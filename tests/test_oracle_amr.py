@@ -238,3 +238,79 @@ def test_adaptive_time_loop_of_the_shipped_case():
     assert abs(p.max() - p0.max()) <= 1e-3 * p0.max()
     b.close()
     b2.close()
+
+
+@pytest.mark.parametrize("dim,deg,rounds", [(2, 1, 3), (2, 2, 2), (3, 1, 2), (3, 2, 1)])
+def test_two_phase_algorithm_of_the_device_equals_cellwise_constraints(dim, deg, rounds):
+    """csrc/device/kernels_constraints.cu does not resolve constraints cell by cell.  Phase 1 = the cell kernels as on
+    uniform meshes: Dirichlet lines eliminated, hanging dofs assembled like free ones (that is the oracle's plain path,
+    which the GPU parity suite pins).  Phase 2 acts on the assembled objects:
+        b_const -= A1 g~ ;  A^ = E^T A1 E (hanging diagonal kept) ;  b^ = E^T b (hanging rows zeroed) ;  x_h = sum w x_m + g_h
+    with E built from the hanging lines only.  Restated here with scipy and compared with the cell-wise oracle."""
+    import scipy.sparse as sp
+    # non-zero values on the faces the refined corner touches, so that hanging lines with inhomogeneities occur
+    vals = [2e-5, -1e-5, 3e-5, -1e-5, -4e-5, -1e-5][: 2 * dim]
+    inp, F, am, full, dp, du, Lp, Lu = adaptive_oracle(dim, deg, rounds, dirichlet=(list(range(2 * dim)), [i // 2 for i in range(2 * dim)], vals))
+    hang = [i for i in range(Lu.n_lines) if len(Lu.line(i)[1]) > 0]
+    diri = [i for i in range(Lu.n_lines) if len(Lu.line(i)[1]) == 0]
+    assert hang and diri and any(Lu.line(i)[3] != 0 for i in hang)  # inhomogeneous hanging lines occur on this mesh
+    # phase 1 on the plain path: Dirichlet-type lines only
+    plain = H.create_oracle_backend()
+    prm = inp.params()
+    plain.set_params(prm)
+    plain.upload_mesh(am.arrays)
+    plain.upload_dofs(capi.FIELD_PRESSURE, dp.n_dofs, dp.cell_dofs)
+    plain.upload_dofs(capi.FIELD_DISPLACEMENT, du.n_dofs, du.cell_dofs)
+    plain.upload_constraints(capi.FIELD_DISPLACEMENT, Lu.line_dof[diri], Lu.inhomogeneity[diri])
+    plain.upload_neumann([], [], [])
+    plain.setup()
+    n = du.n_dofs
+    for b in (plain, full):
+        b.pressure_set_uniform(inp.p_init)
+        b.displacement_assemble()
+    A1 = plain.get_matrix(capi.MAT_ELASTICITY)
+    A1.resize((n, n))
+    b1 = plain.get_vector(capi.VEC_U_RHS)
+    # phase 2
+    rows, cols, vals = [], [], []
+    g_tilde = np.zeros(n)
+    is_h = np.zeros(n, bool)
+    for i in hang:
+        d, ed, ew, g = Lu.line(i)
+        is_h[d] = True
+        g_tilde[d] = g
+        rows += [d] * len(ed); cols += ed.tolist(); vals += ew.tolist()
+    keep = np.nonzero(~is_h)[0]
+    E = sp.csr_matrix((vals + [1.0] * len(keep), (rows + keep.tolist(), cols + keep.tolist())), shape=(n, n))
+    bb = b1 - A1 @ g_tilde
+    b_hat = E.T @ bb
+    b_hat[is_h] = 0.0
+    A_hat = (E.T @ A1 @ E).tolil()
+    d1 = A1.diagonal()
+    for d in np.nonzero(is_h)[0]:
+        A_hat[d, d] = d1[d]
+    A_hat = A_hat.tocsr()
+    A = full.get_matrix(capi.MAT_ELASTICITY)
+    A.resize((n, n))
+    assert abs(A_hat - A).max() <= 1e-13 * abs(A).max()
+    b_full = full.get_vector(capi.VEC_U_RHS)
+    assert np.abs(b_hat - b_full).max() <= 1e-12 * np.abs(b_full).max()
+    # pressure side: condensed M with the average |diagonal| on hanging rows; condensed residual
+    np_ = dp.n_dofs
+    rows, cols, vals = [], [], []
+    is_hp = np.zeros(np_, bool)
+    for i in range(Lp.n_lines):
+        d, ed, ew, _ = Lp.line(i)
+        is_hp[d] = True
+        rows += [d] * len(ed); cols += ed.tolist(); vals += ew.tolist()
+    keep = np.nonzero(~is_hp)[0]
+    Ep = sp.csr_matrix((vals + [1.0] * len(keep), (rows + keep.tolist(), cols + keep.tolist())), shape=(np_, np_))
+    full.project_assemble_matrix()
+    M = full.get_matrix(capi.MAT_MASS)
+    Mc = (Ep.T @ M @ Ep).tolil()
+    for d in np.nonzero(is_hp)[0]:
+        Mc[d, d] = np.abs(M.diagonal()).mean()
+    PM = full.get_matrix(capi.MAT_PROJECTION)
+    assert abs(Mc.tocsr() - PM).max() <= 1e-13 * abs(PM).max()
+    plain.close()
+    full.close()
