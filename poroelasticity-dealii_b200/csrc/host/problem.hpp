@@ -346,41 +346,51 @@ class PoroElasticProblem {
     }
   }
 
-  // FSS:227-291 — minimal legacy-VTK writer (Q1 patches of the local mesh; single rank only)
+  // FSS:227-291 — minimal legacy-VTK writer (Q1 patches of the active mesh, vertex values of every field; single rank only)
   void output_results(unsigned int n) {
-    if (nranks != 1 || data.displacement_degree != 1) return;  // Q2 displacement would need interpolation to vertices
+    if (nranks != 1) return;
     const mesh::Mesh& m = global_mesh;
     const dofs::DofMap& dp = dofs_p;
     std::vector<double> p(n_global_p), u(n_global_u);
     check(pe_get_vector(ctx, PE_VEC_P, p.data(), n_global_p), "get p");
     check(pe_get_vector(ctx, PE_VEC_U, u.data(), n_global_u), "get u");
-    std::vector<int32_t> v2d(m.n_vertices(), -1);
+    std::vector<int32_t> v2d(m.n_vertices(), -1), v2u(m.n_vertices(), -1);
     const int vpc = m.vpc();
+    // the first 2^dim scalar nodes of FE_Q(k) are the vertices, so the vertex values of u are dofs for k = 1 and k = 2
+    dofs::DofMap du = dofs::distribute_dofs(m, data.displacement_degree, dim);
     for (int64_t c = 0; c < m.n_cells(); ++c)
-      for (int v = 0; v < vpc; ++v) v2d[m.cell_vertices[c * vpc + v]] = dp.cell_dofs[c * vpc + v];
+      for (int v = 0; v < vpc; ++v) {
+        v2d[m.cell_vertices[c * vpc + v]] = dp.cell_dofs[c * vpc + v];
+        v2u[m.cell_vertices[c * vpc + v]] = du.cell_dofs[c * du.n_loc + v * dim];
+      }
+    // the forest keeps vertices of coarsened cells: write only the ones in use
+    std::vector<int32_t> vnew(m.n_vertices(), -1);
+    std::vector<int64_t> used;
+    for (int64_t v = 0; v < m.n_vertices(); ++v)
+      if (v2d[v] >= 0) { vnew[v] = (int32_t)used.size(); used.push_back(v); }
     char name[256];
     std::snprintf(name, sizeof name, "./solution/solution-%04u.vtk", n);
     FILE* f = std::fopen(name, "w");
     if (!f) return;
-    std::fprintf(f, "# vtk DataFile Version 3.0\nporoelasticity fixed-stress\nASCII\nDATASET UNSTRUCTURED_GRID\nPOINTS %lld double\n", (long long)m.n_vertices());
-    for (int64_t v = 0; v < m.n_vertices(); ++v)
-      std::fprintf(f, "%.12g %.12g %.12g\n", m.xyz[v * dim], m.xyz[v * dim + 1], dim == 3 ? m.xyz[v * dim + 2] : 0.0);
+    const long long nv = (long long)used.size();
+    std::fprintf(f, "# vtk DataFile Version 3.0\nporoelasticity fixed-stress\nASCII\nDATASET UNSTRUCTURED_GRID\nPOINTS %lld double\n", nv);
+    for (int64_t v : used) std::fprintf(f, "%.12g %.12g %.12g\n", m.xyz[v * dim], m.xyz[v * dim + 1], dim == 3 ? m.xyz[v * dim + 2] : 0.0);
     std::fprintf(f, "CELLS %lld %lld\n", (long long)m.n_cells(), (long long)(m.n_cells() * (vpc + 1)));
     static const int vtk2[4] = {0, 1, 3, 2}, vtk3[8] = {0, 1, 3, 2, 4, 5, 7, 6};
     for (int64_t c = 0; c < m.n_cells(); ++c) {
       std::fprintf(f, "%d", vpc);
-      for (int v = 0; v < vpc; ++v) std::fprintf(f, " %d", m.cell_vertices[c * vpc + (dim == 2 ? vtk2[v] : vtk3[v])]);
+      for (int v = 0; v < vpc; ++v) std::fprintf(f, " %d", vnew[m.cell_vertices[c * vpc + (dim == 2 ? vtk2[v] : vtk3[v])]]);
       std::fprintf(f, "\n");
     }
     std::fprintf(f, "CELL_TYPES %lld\n", (long long)m.n_cells());
     for (int64_t c = 0; c < m.n_cells(); ++c) std::fprintf(f, "%d\n", dim == 2 ? 9 : 12);
-    std::fprintf(f, "POINT_DATA %lld\nVECTORS u double\n", (long long)m.n_vertices());
-    for (int64_t v = 0; v < m.n_vertices(); ++v) {
-      int64_t d0 = (int64_t)v2d[v] * dim;  // vertex dofs of both handlers are numbered in the same first-touch order
+    std::fprintf(f, "POINT_DATA %lld\nVECTORS u double\n", nv);
+    for (int64_t v : used) {
+      const int64_t d0 = v2u[v];
       std::fprintf(f, "%.12g %.12g %.12g\n", u[d0], u[d0 + 1], dim == 3 ? u[d0 + 2] : 0.0);
     }
     std::fprintf(f, "SCALARS p double 1\nLOOKUP_TABLE default\n");
-    for (int64_t v = 0; v < m.n_vertices(); ++v) std::fprintf(f, "%.12g\n", p[v2d[v]]);
+    for (int64_t v : used) std::fprintf(f, "%.12g\n", p[v2d[v]]);
     static const char* names2[3] = {"xx", "xy", "yy"};
     static const char* names3[6] = {"xx", "xy", "xz", "yy", "yz", "zz"};
     std::vector<double> s(n_global_p);
@@ -388,7 +398,7 @@ class PoroElasticProblem {
       for (int e = 0; e < n_stress_components; ++e) {
         check(pe_get_vector(ctx, (pass == 0 ? PE_VEC_STRAIN0 : PE_VEC_STRESS0) + e, s.data(), n_global_p), "get strain/stress");
         std::fprintf(f, "SCALARS %s_%s double 1\nLOOKUP_TABLE default\n", pass == 0 ? "eps" : "sigma", dim == 2 ? names2[e] : names3[e]);
-        for (int64_t v = 0; v < m.n_vertices(); ++v) std::fprintf(f, "%.12g\n", s[v2d[v]]);
+        for (int64_t v : used) std::fprintf(f, "%.12g\n", s[v2d[v]]);
       }
     std::fclose(f);
   }
