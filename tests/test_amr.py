@@ -394,3 +394,142 @@ def test_solution_transfer_keeps_old_values_and_interpolates_new_vertices(dim):
         d, ed, ew, _ = L2.line(i)
         if x2[d].sum() < -2.0 * dim - 2.5:
             assert np.isclose(out[1][d], out[1][ed] @ ew, atol=1e-12)
+
+
+# ---- unstructured coarse meshes with mixed cell orientations (read_mesh(), FSS:438-445) --------------------------------
+def _hex_rotations():
+    """node permutations of a Gmsh hexahedron under the 24 proper rotations of the cube"""
+    pos = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]])
+    perms = set()
+    for axes in itertools.permutations(range(3)):
+        for flips in itertools.product([0, 1], repeat=3):
+            R = np.zeros((3, 3))
+            for a in range(3):
+                R[a, axes[a]] = -1.0 if flips[a] else 1.0
+            if np.linalg.det(R) < 0:
+                continue
+            img = (pos - 0.5) @ R.T + 0.5
+            perms.add(tuple(int(np.argmin(np.abs(pos - p).sum(axis=1))) for p in img))
+    return sorted(perms)
+
+
+def rotated_msh(src, dst, dim, seed):
+    """Copy of a Gmsh 2.2 file in which every cell's node list is replaced by a randomly rotated, equally oriented one."""
+    rng = np.random.default_rng(seed)
+    rots = _hex_rotations()
+    assert len(rots) == 24
+    out, in_elems, count_line = [], False, False
+    for line in open(src).read().splitlines():
+        if line.startswith("$Elements"):
+            in_elems, count_line = True, True
+        elif line.startswith("$EndElements"):
+            in_elems = False
+        elif in_elems and count_line:
+            count_line = False
+        elif in_elems:
+            t = line.split()
+            etype, ntags = int(t[1]), int(t[2])
+            head, nodes = t[: 3 + ntags], t[3 + ntags:]
+            if dim == 2 and etype == 3:
+                k = int(rng.integers(4))
+                nodes = nodes[k:] + nodes[:k]
+            elif dim == 3 and etype == 5:
+                perm = rots[int(rng.integers(24))]
+                nodes = [nodes[i] for i in perm]
+            line = " ".join(head + nodes)
+        out.append(line)
+    open(dst, "w").write("\n".join(out) + "\n")
+
+
+@pytest.mark.parametrize("dim,fname,degree", [(2, "distorted_quad8.msh", 1), (2, "distorted_quad8.msh", 2), (3, "distorted_hex4.msh", 1), (3, "distorted_hex4.msh", 2)])
+def test_refinement_of_unstructured_meshes_does_not_depend_on_cell_orientation(dim, fname, degree, tmp_path):
+    """Lines, quads and hanging nodes are identified by vertex numbers, never by local indices of a neighbour, so a mesh
+    whose cells are rotated at random (what a mesh generator may produce) must give the same refined mesh, the same
+    constraint lines and the same error indicators as the consistently oriented one."""
+    src = H.ROOT / "tests" / "golden" / fname
+    rot = tmp_path / "rotated.msh"
+    rotated_msh(src, rot, dim, seed=11)
+    results = []
+    for path in (src, rot):
+        mesh = capi.mesh_read_msh(path, dim)
+        F = capi.Forest(mesh, 0)
+        for rnd in range(2):
+            m = F.active_mesh().arrays
+            ctr = m.xyz[m.cell_vertices].mean(axis=1)
+            # flags from the geometry only, so both meshes refine the same cells
+            F.set_flags(refine=(np.sin(3.1 * ctr[:, 0] + rnd) * np.cos(2.3 * ctr[:, dim - 1]) > 0.35).astype(np.int8))
+            F.execute()
+        am = F.active_mesh()
+        d = capi.HostDofs(am, degree, 1)
+        L = capi.make_constraints(F, am, d)
+        sp = d.support_points()
+        kk = lambda x: tuple(np.round(x, 8))
+        lines = {}
+        for i in range(L.n_lines):
+            dof, ed, ew, g = L.line(i)
+            if len(ed) == 1 and kk(sp[ed[0]]) == kk(sp[dof]):
+                continue  # FE_Q(2) identity line of a duplicated midpoint dof: both dofs share the coordinates
+            lines[kk(sp[dof])] = sorted((kk(sp[e]), round(float(w), 12)) for e, w in zip(ed, ew))
+        dp = capi.HostDofs(am, 1, 1)
+        xp = dp.support_points()
+        p = np.sin(0.4 * xp[:, 0]) + 0.03 * xp[:, dim - 1] ** 2 + 0.1 * xp[:, 0] * xp[:, 1]
+        Lp = capi.make_constraints(F, am, dp)
+        for i in range(Lp.n_lines):
+            dof, ed, ew, _ = Lp.line(i)
+            p[dof] = p[ed] @ ew
+        eta = F.kelly(am, dp, p)
+        a = am.arrays
+        ctr = a.xyz[a.cell_vertices].mean(axis=1)
+        results.append((a.n_cells, lines, {kk(c): float(e) for c, e in zip(ctr, eta)}, sorted(F.levels().tolist())))
+    (n0, l0, e0, lv0), (n1, l1, e1, lv1) = results
+    assert n0 == n1 and lv0 == lv1 and max(lv0) == 2 and len(l0) > 0
+    assert l0 == l1
+    assert set(e0) == set(e1)
+    assert max(abs(e0[k] - e1[k]) for k in e0) <= 1e-6 * max(e0.values())
+
+
+@pytest.mark.parametrize("dim,seed", [(2, 0), (2, 1), (3, 2)])
+def test_random_refine_coarsen_sequences_keep_every_invariant(dim, seed):
+    """Six rounds of random refine / coarsen flags: after every round the active cells tile the box, levels across shared
+    lines differ by at most one, the constrained FE_Q(2) space is continuous, the transfer reproduces a linear field, and
+    flags requested on cells that may legally change are honoured (refinement always, coarsening for whole families whose
+    neighbours allow it)."""
+    rng = np.random.default_rng(seed)
+    m0 = capi.mesh_rectangle(dim, [10.0] * dim, 1)
+    F = capi.Forest(m0, 1)
+    lin = lambda x: 1.5 + x @ np.arange(1, dim + 1)
+    for rnd in range(6 if dim == 2 else 3):
+        am = F.active_mesh()
+        dp = capi.HostDofs(am, 1, 1)
+        F.store(am, dp, [lin(dp.support_points())])
+        lv = F.levels()
+        re = (rng.random(len(lv)) < 0.2) & (lv < 4)
+        co = (rng.random(len(lv)) < 0.5) & ~re
+        F.set_flags(refine=re.astype(np.int8), coarsen=co.astype(np.int8))
+        F.prepare()
+        r2, c2 = F.get_flags()
+        assert (r2 | ~re).all()          # prepare never drops a refine flag
+        assert not (c2 & ~co).any()      # and never invents a coarsen flag
+        n_before = len(lv)
+        nc, nr = F.execute()
+        assert nr == r2.sum()
+        am = F.active_mesh()
+        m = am.arrays
+        lv = F.levels()
+        assert len(lv) == n_before + ((1 << dim) - 1) * (nr - nc)
+        lo, hi = cell_boxes(m)
+        assert np.isclose(np.prod(hi - lo, axis=1).sum(), 10.0 ** dim)
+        for i, j in touching_pairs(m, 1):
+            assert abs(int(lv[i]) - int(lv[j])) <= 1
+        dp = capi.HostDofs(am, 1, 1)
+        assert np.allclose(F.fetch(am, dp, 1)[0], lin(dp.support_points()), atol=1e-12)
+        if len(lv) > (600 if dim == 2 else 80):
+            continue  # the lattice check below is a python loop over cells x lattice points x nodes
+        d2 = capi.HostDofs(am, 2, 1)
+        L = capi.make_constraints(F, am, d2)
+        v = rng.standard_normal(d2.n_dofs)
+        for i in range(L.n_lines):
+            d, ed, ew, g = L.line(i)
+            v[d] = v[ed] @ ew
+        samples = fe_eval_on_lattice(m, d2, v, 2)
+        assert max(max(vals) - min(vals) for vals in samples.values()) < 1e-12

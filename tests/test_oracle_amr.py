@@ -314,3 +314,34 @@ def test_two_phase_algorithm_of_the_device_equals_cellwise_constraints(dim, deg,
     assert abs(Mc.tocsr() - PM).max() <= 1e-13 * abs(PM).max()
     plain.close()
     full.close()
+
+
+@pytest.mark.parametrize("dim,fname,deg", [(2, "distorted_quad8.msh", 1), (2, "distorted_quad8.msh", 2), (3, "distorted_hex4.msh", 1), (3, "distorted_hex4.msh", 2)])
+def test_patch_test_on_refined_unstructured_meshes(dim, fname, deg, tmp_path):
+    """read_mesh() (FSS:438-445) + refinement: distorted Gmsh cells in random orientations, refined twice.  The children
+    of a bi/trilinear cell tile it exactly and the constraints are the traces of the coarse basis, so the linear exact
+    solution must come out to round-off."""
+    from test_amr import rotated_msh
+    rot = tmp_path / "rotated.msh"
+    rotated_msh(H.ROOT / "tests" / "golden" / fname, rot, dim, seed=5)
+    inp = capi.InputData(text=H.make_input(dim=dim, refine=2, degree_u=deg))
+    mesh = capi.mesh_read_msh(rot, dim)
+    F = capi.Forest(mesh, 0)
+    rng = np.random.default_rng(1)
+    for _ in range(2):
+        F.set_flags(refine=(rng.random(len(F.levels())) < 0.25).astype(np.int8))
+        F.execute()
+    am = F.active_mesh()
+    b = H.create_oracle_backend()
+    dp, du, (Lp, Lu) = fss.upload_problem(b, inp, am, forest=F)
+    assert Lp.n_lines > 0 and F.levels().max() == 2
+    fss.initialize(b, inp)
+    assert b.get_matrix(capi.MAT_MASS).sum() == pytest.approx(10.0 ** dim, rel=1e-12)
+    u = b.get_vector(capi.VEC_U)
+    sp = du.support_points()
+    exact = -1e-5 * (sp[np.arange(du.n_dofs), components(du, dim)] + 5.0) / 10.0
+    assert np.abs(u - exact).max() <= 1e-14
+    assert np.allclose(b.get_vector(capi.VEC_VOL_STRAIN0), -1e-6 * dim, rtol=1e-6)
+    rep = fss.time_step(b, inp)
+    assert rep["fss_iterations"] == 1
+    b.close()
