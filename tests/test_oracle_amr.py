@@ -345,3 +345,155 @@ def test_patch_test_on_refined_unstructured_meshes(dim, fname, deg, tmp_path):
     rep = fss.time_step(b, inp)
     assert rep["fss_iterations"] == 1
     b.close()
+
+
+# ---- the device's constraint kernels, executed on the CPU ------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    """tests/emu_constraints.cpp: csrc/device/constraints_dev.cuh + constraint_tables.hpp compiled for the host."""
+    import ctypes as C
+    import subprocess
+    out = tmp_path_factory.mktemp("emu") / "libemu.so"
+    subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-o", str(out),
+                           str(H.ROOT / "tests" / "emu_constraints.cpp")])
+    lib = C.CDLL(str(out))
+    i32, f64, i64 = C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int64)
+    lib.emu_pattern.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int64, i32, C.c_int64, i32, i32, i32, i32, i32, i64, C.c_int]
+    lib.emu_pattern.restype = C.c_int64
+    lib.emu_avg_abs_diag.argtypes = [C.c_int64, i32, i32, f64]
+    lib.emu_avg_abs_diag.restype = C.c_double
+    lib.emu_condense_matrix.argtypes = [C.c_int64, i32, i32, f64, f64, C.c_int64, i32, i32, i32, f64, C.c_int, C.c_double]
+    lib.emu_condense_vector.argtypes = [C.c_int64, C.c_int64, i32, i32, i32, f64, f64]
+    lib.emu_distribute.argtypes = [C.c_int64, C.c_int64, i32, i32, i32, f64, f64, f64]
+    lib.emu_scatter_inhomogeneity.argtypes = [C.c_int64, C.c_int64, i32, f64, f64]
+    return lib
+
+
+def _ptr(a, ct):
+    import ctypes as C
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+class DeviceLines:
+    """the split pe_upload_constraints makes: Dirichlet-type lines stay with the cell kernels, hanging lines go to the
+    constraint kernels (int32 entry pointers as on the device)"""
+
+    def __init__(self, L):
+        hang = [i for i in range(L.n_lines) if L.entry_ptr[i + 1] > L.entry_ptr[i]]
+        self.diri = [i for i in range(L.n_lines) if L.entry_ptr[i + 1] == L.entry_ptr[i]]
+        self.dof = np.ascontiguousarray(L.line_dof[hang], dtype=np.int32)
+        self.g = np.ascontiguousarray(L.inhomogeneity[hang], dtype=np.float64)
+        ptr, edof, w = [0], [], []
+        for i in hang:
+            _, ed, ew, _ = L.line(i)
+            edof += ed.tolist(); w += ew.tolist(); ptr.append(len(edof))
+        self.ptr = np.array(ptr, dtype=np.int32)
+        self.edof = np.array(edof, dtype=np.int32)
+        self.w = np.array(w, dtype=np.float64)
+        self.n = len(hang)
+
+
+def device_pattern(emu, n_cells, d, DL, use_kernels=1):
+    """pe_build_pattern_lists: with use_kernels the CUDA pattern kernels run on the CPU (one OS thread per lane)"""
+    import ctypes as C
+    cd = np.ascontiguousarray(d.cell_dofs, dtype=np.int32)
+    rowptr = np.zeros(d.n_dofs + 1, dtype=np.int32)
+    maxc = C.c_int64()
+    args = (n_cells, d.n_loc, d.n_comp, d.n_dofs, _ptr(cd, C.c_int32), DL.n, _ptr(DL.dof, C.c_int32), _ptr(DL.ptr, C.c_int32), _ptr(DL.edof, C.c_int32))
+    nnz = emu.emu_pattern(*args, _ptr(rowptr, C.c_int32), None, C.byref(maxc), use_kernels)
+    assert nnz > 0, nnz
+    col = np.full(nnz, -1, dtype=np.int32)
+    assert emu.emu_pattern(*args, _ptr(rowptr, C.c_int32), _ptr(col, C.c_int32), C.byref(maxc), use_kernels) == nnz
+    return rowptr, col, maxc.value
+
+
+def values_on_pattern(A, rowptr, col):
+    """values of scipy matrix A on a (superset) CSR pattern"""
+    import scipy.sparse as sp
+    n = len(rowptr) - 1
+    P = sp.csr_matrix((np.ones(len(col)), col, rowptr), shape=(n, n))
+    assert abs(A - A.multiply(P)).sum() == 0, "matrix has entries outside the pattern"
+    A = A.tocsr()
+    out = np.zeros(len(col))
+    for r in range(n):
+        cols = col[rowptr[r]:rowptr[r + 1]]
+        out[rowptr[r]:rowptr[r + 1]] = np.asarray(A[r, cols].todense()).ravel()
+    return out
+
+
+@pytest.mark.parametrize("dim,deg,rounds", [(2, 1, 3), (2, 2, 2), (3, 1, 2), (3, 2, 1)])
+def test_device_constraint_kernels_executed_on_the_cpu_match_the_oracle(emu, dim, deg, rounds):
+    """The source of k_condense_matrix / k_condense_vector_gather / k_zero_lines / k_distribute_hanging / k_scatter_lines and the
+    host-side tables of libporoel.so, run thread by thread on the CPU, fed with what the (GPU-verified) cell kernels
+    produce on this mesh — the oracle's plain path — and compared with the oracle's cell-wise constraint handling."""
+    import ctypes as C
+    import scipy.sparse as sp
+    vals = [2e-5, -1e-5, 3e-5, -1e-5, -4e-5, -1e-5][: 2 * dim]
+    inp, F, am, full, dp, du, Lp, Lu = adaptive_oracle(dim, deg, rounds, dirichlet=(list(range(2 * dim)), [i // 2 for i in range(2 * dim)], vals))
+    DLu, DLp = DeviceLines(Lu), DeviceLines(Lp)
+    assert DLu.n > 0 and DLp.n == Lp.n_lines and np.any(DLu.g != 0)
+    plain = H.create_oracle_backend()
+    plain.set_params(inp.params())
+    plain.upload_mesh(am.arrays)
+    plain.upload_dofs(capi.FIELD_PRESSURE, dp.n_dofs, dp.cell_dofs)
+    plain.upload_dofs(capi.FIELD_DISPLACEMENT, du.n_dofs, du.cell_dofs)
+    plain.upload_constraints(capi.FIELD_DISPLACEMENT, Lu.line_dof[DLu.diri], Lu.inhomogeneity[DLu.diri])
+    plain.upload_neumann([], [], [])
+    plain.setup()
+    for b in (plain, full):
+        b.pressure_set_uniform(inp.p_init)
+        b.displacement_assemble()
+        b.project_assemble_matrix()
+    n = du.n_dofs
+    # ---- displacement matrix
+    rowptr, col, maxc = device_pattern(emu, am.arrays.n_cells, du, DLu)
+    rp2, col2, _ = device_pattern(emu, am.arrays.n_cells, du, DLu, use_kernels=0)
+    assert np.array_equal(rowptr, rp2) and np.array_equal(col, col2)  # kernels == sorted union of the lists around each row
+    cap = 32
+    while cap < maxc:
+        cap *= 2
+    assert cap * 4 * 4 <= 200 * 1024  # fits the row-pattern kernel's shared memory
+    lens = np.diff(rowptr).reshape(-1, dim)
+    assert (lens == lens[:, :1]).all() and (lens % dim == 0).all()  # dim x dim block structure survives (block-CSR copy)
+    A1 = plain.get_matrix(capi.MAT_ELASTICITY); A1.resize((n, n))
+    src = values_on_pattern(A1, rowptr, col)
+    dst = np.full_like(src, np.nan)
+    emu.emu_condense_matrix(n, _ptr(rowptr, C.c_int32), _ptr(col, C.c_int32), _ptr(src, C.c_double), _ptr(dst, C.c_double), DLu.n,
+                            _ptr(DLu.dof, C.c_int32), _ptr(DLu.ptr, C.c_int32), _ptr(DLu.edof, C.c_int32), _ptr(DLu.w, C.c_double), 1, 0.0)
+    assert not np.isnan(dst).any()
+    A_dev = sp.csr_matrix((dst, col, rowptr), shape=(n, n))
+    A = full.get_matrix(capi.MAT_ELASTICITY); A.resize((n, n))
+    assert abs(A_dev - A).max() <= 1e-13 * abs(A).max()
+    # ---- displacement right-hand side: b_const -= A1 g~ ; condense
+    gt = np.zeros(n)
+    emu.emu_scatter_inhomogeneity(n, DLu.n, _ptr(DLu.dof, C.c_int32), _ptr(DLu.g, C.c_double), _ptr(gt, C.c_double))
+    bvec = plain.get_vector(capi.VEC_U_RHS) - sp.csr_matrix((src, col, rowptr), shape=(n, n)) @ gt
+    emu.emu_condense_vector(n, DLu.n, _ptr(DLu.dof, C.c_int32), _ptr(DLu.ptr, C.c_int32), _ptr(DLu.edof, C.c_int32), _ptr(DLu.w, C.c_double),
+                            _ptr(bvec, C.c_double))
+    b_full = full.get_vector(capi.VEC_U_RHS)
+    assert np.abs(bvec - b_full).max() <= 1e-12 * np.abs(b_full).max()
+    # ---- distribute
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(n)
+    y = x.copy()
+    emu.emu_distribute(n, DLu.n, _ptr(DLu.dof, C.c_int32), _ptr(DLu.ptr, C.c_int32), _ptr(DLu.edof, C.c_int32), _ptr(DLu.w, C.c_double),
+                       _ptr(DLu.g, C.c_double), _ptr(y, C.c_double))
+    for k in range(DLu.n):
+        e = slice(DLu.ptr[k], DLu.ptr[k + 1])
+        assert y[DLu.dof[k]] == pytest.approx(x[DLu.edof[e]] @ DLu.w[e] + DLu.g[k], rel=1e-14, abs=1e-300)
+    untouched = np.ones(n, bool); untouched[DLu.dof] = False
+    assert np.array_equal(y[untouched], x[untouched])
+    # ---- pressure: condensed mass matrix with the average |diagonal| (what pe_setup stores in Mc)
+    npd = dp.n_dofs
+    rp, cp, _ = device_pattern(emu, am.arrays.n_cells, dp, DLp)
+    M = full.get_matrix(capi.MAT_MASS)
+    msrc = values_on_pattern(M, rp, cp)
+    mdst = np.zeros_like(msrc)
+    avg = emu.emu_avg_abs_diag(npd, _ptr(rp, C.c_int32), _ptr(cp, C.c_int32), _ptr(msrc, C.c_double))  # k_sum_abs_diag
+    assert avg == pytest.approx(np.abs(M.diagonal()).mean(), rel=1e-14)
+    emu.emu_condense_matrix(npd, _ptr(rp, C.c_int32), _ptr(cp, C.c_int32), _ptr(msrc, C.c_double), _ptr(mdst, C.c_double), DLp.n,
+                            _ptr(DLp.dof, C.c_int32), _ptr(DLp.ptr, C.c_int32), _ptr(DLp.edof, C.c_int32), _ptr(DLp.w, C.c_double), 0, avg)
+    PM = full.get_matrix(capi.MAT_PROJECTION)
+    assert abs(sp.csr_matrix((mdst, cp, rp), shape=(npd, npd)) - PM).max() <= 1e-13 * abs(PM).max()
+    plain.close()
+    full.close()
