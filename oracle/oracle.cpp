@@ -5,7 +5,9 @@
 // (CMakeLists.txt:3), which is neither vendored nor installed here.  This file therefore restates
 // the reference's own headers plus the published deal.II 8.4 algorithms they call; it is pinned
 // only by the known-answer tests in tests/ (derived moduli, element matrices vs closed forms,
-// patch test, contraction factor, an independent numpy/scipy restatement in oracle/oracle_np.py).
+// patch test, contraction factor, an independent numpy/scipy restatement in oracle/oracle_np.py) and by ONE
+// external anchor: the CG iteration counts deal.II's tutorial step-4 publishes (26 in 2D / 30 in 3D), which the
+// Laplace assembly + cg_solve below reproduce (tests/test_oracle.py T10).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // load this library.  The product (libporoel.so) never links or calls it.
@@ -390,7 +392,7 @@ void jacobi_apply(const Pattern& P, const Vec& val, const Vec& src, Vec& dst) {
 struct CgResult { int its = 0; double res = 0; bool ok = true; };
 
 // SolverCG<>::solve (deal.II 8.4) with SolverControl(max_steps, tol)
-// precond: omega > 0 -> SSOR(omega); omega == 0 -> Jacobi (debug aid, not the reference)
+// precond: omega > 0 -> SSOR(omega); omega == 0 -> Jacobi (debug aid, not the reference); omega < 0 -> PreconditionIdentity
 CgResult cg_solve(const Pattern& P, const Vec& A, Vec& x, const Vec& b, double omega, int max_steps, double tol) {
   const int64_t n = P.n;
   Vec g(n), h(n), d(n);
@@ -413,7 +415,9 @@ CgResult cg_solve(const Pattern& P, const Vec& A, Vec& x, const Vec& b, double o
   int conv = check(0, res);
   if (conv != 0) { R.ok = conv > 0; return R; }
   auto precond = [&](const Vec& s, Vec& t) {
-    if (omega > 0) ssor_apply(P, A, omega, s, t); else jacobi_apply(P, A, s, t);
+    if (omega > 0) ssor_apply(P, A, omega, s, t);
+    else if (omega == 0) jacobi_apply(P, A, s, t);
+    else t = s;
   };
   precond(g, h);
   for (int64_t i = 0; i < n; ++i) d[i] = -h[i];
@@ -1141,6 +1145,39 @@ int po_reset_stats(Ctx* c) {
   c->st = pe_stats{};
   c->st.n_cells = k.n_cells; c->st.n_dofs_p = k.n_dofs_p; c->st.n_dofs_u = k.n_dofs_u; c->st.nnz_p = k.nnz_p; c->st.nnz_u = k.nnz_u;
   return 0;
+}
+
+// SolverCG on a caller-supplied CSR matrix (columns ascending): lets the tests pin cg_solve / ssor_apply against published
+// deal.II results (tutorial step-4).  omega > 0 SSOR, == 0 Jacobi, < 0 identity.
+int po_cg_csr(int64_t n, const int64_t* rowptr, const int32_t* col, const double* val, double* x, const double* b, double omega, int max_steps,
+              double tol, int* its, double* res) {
+  Pattern P;
+  P.n = n;
+  P.rowptr.assign(rowptr, rowptr + n + 1);
+  P.col.resize(rowptr[n]);
+  P.right_of_diag.resize(n);
+  Vec A(rowptr[n]);
+  for (int64_t r = 0; r < n; ++r) {  // deal.II layout: diagonal first, then ascending
+    int64_t p = rowptr[r] + 1;
+    bool have_diag = false;
+    P.right_of_diag[r] = rowptr[r + 1];
+    bool found = false;
+    for (int64_t j = rowptr[r]; j < rowptr[r + 1]; ++j) {
+      if (col[j] == r) { P.col[rowptr[r]] = (int32_t)r; A[rowptr[r]] = val[j]; have_diag = true; continue; }
+      if (p >= rowptr[r + 1] && !have_diag) return PE_ERR_BAD_INPUT;
+      if (!found && col[j] > r) { P.right_of_diag[r] = p; found = true; }
+      P.col[p] = col[j];
+      A[p] = val[j];
+      ++p;
+    }
+    if (!have_diag) return PE_ERR_BAD_INPUT;
+  }
+  Vec xv(x, x + n), bv(b, b + n);
+  CgResult R = cg_solve(P, A, xv, bv, omega, max_steps, tol);
+  std::memcpy(x, xv.data(), n * sizeof(double));
+  if (its) *its = R.its;
+  if (res) *res = R.res;
+  return R.ok ? 0 : PE_ERR_NO_CONVERGENCE;
 }
 
 // timing helpers for the CPU baseline: n repetitions of one operator on the assembled matrices

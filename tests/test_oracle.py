@@ -325,3 +325,57 @@ def test_t6_elasticity_element_matrix_against_sympy(dim, deg):
         worst = max(worst, abs(A[i, j] - exact) / scale, abs(A[j, i] - exact) / scale)
     assert worst <= 1e-12, worst
     b.close()
+
+
+@pytest.mark.parametrize("dim,n_cells,n_dofs,cg_iterations", [(2, 256, 289, 26), (3, 4096, 4913, 30)])
+def test_t10_dealii_step4_published_iteration_counts(dim, n_cells, n_dofs, cg_iterations):
+    """EXTERNAL PIN.  The "Results" section of deal.II's tutorial step-4 prints, for -Laplace u = 4 sum_a x_a^4 on [-1,1]^dim
+    (hyper_cube + refine_global(4), FE_Q(1), QGauss(2), u = |x|^2 on the boundary through interpolate_boundary_values +
+    MatrixTools::apply_boundary_values, SolverCG with PreconditionIdentity and SolverControl(1000, 1e-12)):
+
+        2D: 256 active cells, 289 degrees of freedom, "26 CG iterations needed to obtain convergence."
+        3D: 4096 active cells, 4913 degrees of freedom, "30 CG iterations needed to obtain convergence."
+
+    (quoted from the published tutorial output; deal.II itself cannot be installed here).  Reproducing both numbers pins
+    the oracle's refine_global mesh, its create_laplace_matrix restatement (PS:99-101), the QGauss(2) tables, and the
+    SolverCG recurrence / SolverControl stopping rule used at PS:175-179, DS:299-305, SP:209-214."""
+    import itertools
+    inp = capi.InputData(text=H.make_input(dim=dim, refine=4, degree_u=1))
+    mesh = capi.mesh_rectangle(dim, [2.0] * dim, 4)
+    b = H.create_oracle_backend()
+    dp, _, _ = fss.upload_problem(b, inp, mesh)
+    assert mesh.arrays.n_cells == n_cells and dp.n_dofs == n_dofs
+    K = b.get_matrix(capi.MAT_LAPLACE).tocsr()
+    x = dp.support_points()
+    # VectorTools::create_right_hand_side with QGauss(2) on the affine cells
+    m = mesh.arrays
+    a = 0.5 / np.sqrt(3.0)
+    g1 = np.array([0.5 - a, 0.5 + a])
+    f = np.zeros(n_dofs)
+    X = m.xyz[m.cell_vertices]
+    lo, h = X.min(axis=1), X.max(axis=1) - X.min(axis=1)
+    for q in itertools.product(range(2), repeat=dim):
+        xi = g1[list(q)]
+        pts = lo + xi * h
+        fq = 4.0 * (pts ** 4).sum(axis=1) * np.prod(h, axis=1) / 2 ** dim
+        for k in range(1 << dim):
+            N = np.prod([xi[d] if (k >> d) & 1 else 1 - xi[d] for d in range(dim)])
+            np.add.at(f, dp.cell_dofs[:, k], fq * N)
+    # MatrixTools::apply_boundary_values: symmetric elimination, rhs_i = a_ii g_i, solution_i = g_i
+    bnd = np.isclose(np.abs(x).max(axis=1), 1.0)
+    g = np.where(bnd, (x ** 2).sum(axis=1), 0.0)
+    rhs = f - K @ g
+    D = K.diagonal()
+    keep = sp_diag(~bnd)
+    A = keep @ K @ keep + sp_diag(bnd) @ sp_diag(D)
+    rhs[bnd] = D[bnd] * g[bnd]
+    rc, u, its, res = H.oracle_cg(A, rhs, x0=g, omega=-1.0, max_steps=1000, tol=1e-12)
+    assert rc == 0 and res <= 1e-12
+    assert its == cg_iterations
+    assert np.linalg.norm(A @ u - rhs) <= 1e-11 and np.array_equal(u[bnd], g[bnd])
+    b.close()
+
+
+def sp_diag(v):
+    import scipy.sparse as sp
+    return sp.diags(np.asarray(v, dtype=float)).tocsr()
