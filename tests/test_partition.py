@@ -58,8 +58,10 @@ def meshes():
     yield "2d 8x8 Q2", capi.mesh_rectangle(2, [10, 10], 3), 2
 
 
+@pytest.mark.parametrize("balanced", [False, True])
 @pytest.mark.parametrize("nranks", [2, 3, 4, 8])
-def test_partition_invariants(nranks):
+def test_partition_invariants(nranks, balanced, monkeypatch):
+    monkeypatch.setenv("PE_BALANCED_OWNERSHIP", "1" if balanced else "0")
     for name, mesh, deg in meshes():
         dim = mesh.arrays.dim
         dp, du = capi.HostDofs(mesh, 1, 1), capi.HostDofs(mesh, deg, dim)
@@ -132,6 +134,26 @@ def test_space_filling_curve_order_makes_contiguous_ranges_compact(dim, refine):
     assert ghosts["scrambled"] > 2 * ghosts["sfc"]
 
 
+def test_balanced_ownership_evens_out_the_rows(monkeypatch):
+    """PE_BALANCED_OWNERSHIP=1: interface nodes are dealt out among the ranks that touch them instead of all going to the
+    lowest rank; whole nodes move (block rows stay intact) and the spread of owned rows over 8 octants shrinks."""
+    mesh = capi.mesh_rectangle(3, [10, 10, 10], 4)  # 16^3 cells, 8 octants of 8^3
+    dp, du = capi.HostDofs(mesh, 1, 1), capi.HostDofs(mesh, 1, 3)
+    spread = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PE_BALANCED_OWNERSHIP", mode)
+        parts = [Part(mesh, dp, du, r, 8) for r in range(8)]
+        rows = np.array([p.field[1]["n_owned"] for p in parts])
+        assert rows.sum() == du.n_dofs and (rows % 3 == 0).all()
+        for p in parts:
+            o = p.field[1]["l2g"][: p.field[1]["n_owned"]]
+            assert (o.reshape(-1, 3) // 3 == (o[::3] // 3)[:, None]).all() or set((o // 3).tolist()) == set((o[::3] // 3).tolist())
+        spread[mode] = rows.max() / rows.mean()
+    assert spread["0"] > 1.15          # 9^3 nodes on the corner octant against a mean of 17^3 / 8: 1.19 at this small size
+    assert spread["1"] < 1.08
+    assert spread["1"] < spread["0"]
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, str(H.ROOT / "tests"))
@@ -179,11 +201,13 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_halo_plan_with_two_gloo_ranks():
+@pytest.mark.parametrize("balanced", ["0", "1"])
+def test_halo_plan_with_two_gloo_ranks(balanced, monkeypatch):
     import torch.multiprocessing as mp
+    monkeypatch.setenv("PE_BALANCED_OWNERSHIP", balanced)  # inherited by the spawned ranks
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
+    port = 29500 + os.getpid() % 2000 + int(balanced)
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
