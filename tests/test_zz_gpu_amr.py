@@ -18,7 +18,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="hanging-n
 
 
 def run_case(*args):
-    r = subprocess.run([sys.executable, str(H.ROOT / "tests" / "amr_gpu_case.py"), *map(str, args)], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, str(H.ROOT / "tests" / "amr_gpu_case.py"), *map(str, args)], capture_output=True, text=True, timeout=300)
     line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "{}"
     print(line)
     print(r.stderr[-2000:])
