@@ -215,15 +215,8 @@ def load_device():
     return lib
 
 
-def load_host():
-    global _host
-    if _host is not None:
-        return _host
-    load_device()  # libporoel_host.so links against libporoel.so
-    path = LIB_DIR / "libporoel_host.so"
-    if not path.exists():
-        raise RuntimeError(f"{path} is missing: run __graft_entry__.build()")
-    lib = C.CDLL(str(path))
+def _declare_host_api(lib):
+    """ctypes signatures of include/poroel_host.h (also applied to the oracle-backed driver build of the tests)."""
     P = C.c_void_p
     lib.peh_last_error.restype = C.c_char_p
     lib.peh_input_create.restype = P
@@ -284,6 +277,18 @@ def load_host():
     lib.peh_problem_mesh.argtypes = [P]
     lib.peh_problem_mesh.restype = P
     lib.peh_problem_global_ids.argtypes = [P, C.c_int, i64p]
+
+
+def load_host():
+    global _host
+    if _host is not None:
+        return _host
+    load_device()  # libporoel_host.so links against libporoel.so
+    path = LIB_DIR / "libporoel_host.so"
+    if not path.exists():
+        raise RuntimeError(f"{path} is missing: run __graft_entry__.build()")
+    lib = C.CDLL(str(path))
+    _declare_host_api(lib)
     _host = lib
     return lib
 
@@ -770,23 +775,34 @@ class Problem:
         self._inp = inp
         self.backend = None
 
+    def _attach_backend(self):
+        dev = load_device()
+        self.backend = OperatorBackend(dev, "pe_", C.c_void_p(self.lib.peh_problem_ctx(self.h)))
+        self.refresh_sizes()
+
+    def refresh_sizes(self):
+        """dof counts of the current mesh (they change when the adaptive loop refines, FSS:333-340)"""
+        st = self.backend.stats()
+        self.backend.n_p, self.backend.n_u = st["n_dofs_p"], st["n_dofs_u"]
+        return st
+
     def initialize(self, verbose=False):
         if self.lib.peh_problem_initialize(self.h, int(verbose)) != 0:
             raise HostError(self.lib.peh_last_error().decode())
-        dev = load_device()
-        self.backend = OperatorBackend(dev, "pe_", C.c_void_p(self.lib.peh_problem_ctx(self.h)))
-        st = self.backend.stats()
-        self.backend.n_p, self.backend.n_u = st["n_dofs_p"], st["n_dofs_u"]
+        self._attach_backend()
 
     def step(self, verbose=False):
         r = StepReport()
         if self.lib.peh_problem_step(self.h, int(verbose), C.byref(r)) != 0:
             raise HostError(self.lib.peh_last_error().decode())
+        if self._inp.refine_every:
+            self.refresh_sizes()
         return r.as_dict()
 
     def run(self, verbose=True):
         if self.lib.peh_problem_run(self.h, int(verbose)) != 0:
             raise HostError(self.lib.peh_last_error().decode())
+        self._attach_backend()
 
     def global_ids(self, field):
         n = self.backend.n_p if field == FIELD_PRESSURE else self.backend.n_u

@@ -90,7 +90,6 @@ def driver_case():
     for step in range(1, 18):
         rep = prob.step()
         st = prob.backend.stats()
-        prob.backend.n_p, prob.backend.n_u = st["n_dofs_p"], st["n_dofs_u"]
         p = prob.backend.get_vector(capi.VEC_P)
         xo, po, counts, n_cells = snaps[step]
         ok = ok and len(p) == len(po) and st["n_cells"] == n_cells
