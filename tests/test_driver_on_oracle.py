@@ -168,3 +168,27 @@ def test_fss_poroel_executable_runs_the_shipped_input_with_refinement(tmp_path):
         assert lines[i + 1] == "Refining mesh" and "active cells" in lines[i + 2]
     no_file = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert no_file.returncode == 1 and "specify the file name" in no_file.stdout
+
+
+def test_cpp_driver_reads_domain_msh_and_refines_it(on_oracle, tmp_path, monkeypatch):
+    """read_mesh() (FSS:438-445: "domain.msh" in the working directory) as the coarse mesh of the adaptive loop; the Gmsh
+    file uses the boundary ids of the reference's domain.geo:22-25 (0 bottom, 1 right, 2 top, 3 left)."""
+    import shutil
+    monkeypatch.chdir(tmp_path)
+    shutil.copy(H.ROOT / "tests" / "golden" / "square10.msh", tmp_path / "domain.msh")
+    text = H.make_input(dim=2, refine=2, degree_u=2, dirichlet=([3, 1, 0, 2], [0, 0, 1, 1], [0, -1e-5, 0, -1e-5]),
+                        extra_gpu="  set Read mesh file = 1\n  set Refine every = 2\n")
+    inp = capi.InputData(text=text)
+    ora = H.create_oracle_backend()
+    snaps = {}
+    fss.run_adaptive(ora, inp, 4, inp.refine_every, lambda s, r, m, dp, du: snaps.__setitem__(s, (ora.get_vector(capi.VEC_P), m.arrays.n_cells)))
+    prob = capi.Problem(capi.InputData(text=text), device=0)
+    prob.initialize()
+    for step in range(1, 5):
+        prob.step()
+        p, n_cells = snaps[step]
+        assert prob.backend.stats()["n_cells"] == n_cells
+        assert np.array_equal(prob.backend.get_vector(capi.VEC_P), p)
+    assert snaps[1][1] == 100 and snaps[2][1] > 100 and snaps[4][1] > snaps[2][1]
+    prob.close()
+    ora.close()
