@@ -524,8 +524,10 @@ int pe_displacement_assemble(pe_ctx* c) {
         const Field::Bsr& S = c->fu.bsr;
         c->st.spmv_bytes_u = (double)S.nnzb * (S.B * S.B * 8.0 + 4.0) + (double)S.n_brows * 4.0 + (double)c->fu.n_owned * 16.0;
         c->st.bsr_block_size = S.B;
+        pe_build_bsr_fp32(c, c->fu);
       } else {
         c->fu.bsr.B = 0;
+        c->fu.bsr.bval32.release();
         c->st.bsr_block_size = 0;
       }
     }

@@ -141,6 +141,11 @@ __device__ __forceinline__ double ld_stream(const double* p) {
   asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ int ld_stream(const int* p) {
   int v;
   asm volatile("ld.global.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -426,6 +431,128 @@ __global__ void __launch_bounds__(SPMV_T) k_spmv_bsr(SpmvArgs a, BsrArgs m) {
   if (EPI == EPI_DOT || EPI == EPI_RESID) grid_reduce<1>(acc, a.red, a.slot);
 }
 
+// ---- Chebyshev inner pass with the FP32 copy of the block values (opt-in, PE_CHEB_FP32=1) -------------------------------
+// Same warp-blocked scheme as k_spmv_bsr, but the nine values of a block arrive as floats (36 + 4 B per block instead of
+// 72 + 4) and are widened to double before the multiply: all arithmetic and all vectors stay FP64.  Used only for the
+// passes INSIDE the polynomial preconditioner, never for CG's own h = A d or the residual, so the solve still converges to
+// the solution of the FP64 system (the preconditioner is a fixed SPD operator; measured in numpy on the assembled 64^3
+// matrix: identical iteration counts, |x - x_fp64| / |x| = 1e-15).
+template <int B>
+struct BlockRowF {
+  int c, nb, j;
+  bool p;
+  float v[B * B];
+  size_t vbase;
+  __device__ __forceinline__ void issue(const BsrArgs& m, int base, int nb_, int lane) {
+    nb = nb_;
+    j = lane;
+    p = j < nb;
+    vbase = (size_t)base * B * B;
+    c = 0;
+    if (p) c = ld_stream(m.bcol + base + j);
+  }
+  __device__ __forceinline__ void issue_vals(const float* __restrict__ bval32) {
+#pragma unroll
+    for (int k = 0; k < B * B; ++k) {
+      v[k] = 0.f;
+      if (p) v[k] = ld_stream(bval32 + vbase + (size_t)k * nb + j);
+    }
+  }
+  __device__ __forceinline__ void finish(const BsrArgs& m, const float* __restrict__ bval32, const double* __restrict__ x, int base, double (&s)[B]) {
+    double xv[B];
+#pragma unroll
+    for (int cc = 0; cc < B; ++cc) {
+      xv[cc] = 0.0;
+      if (p) xv[cc] = ld_gather(x + (size_t)c * B + cc);
+    }
+#pragma unroll
+    for (int r = 0; r < B; ++r) {
+      double t = 0.0;
+#pragma unroll
+      for (int cc = 0; cc < B; ++cc) t += (double)v[r * B + cc] * xv[cc];
+      s[r] = t;
+    }
+    for (int jj = j + 32; jj < nb; jj += 32) {
+      const int c2 = ld_stream(m.bcol + base + jj);
+      double x2[B];
+#pragma unroll
+      for (int cc = 0; cc < B; ++cc) x2[cc] = ld_gather(x + (size_t)c2 * B + cc);
+#pragma unroll
+      for (int r = 0; r < B; ++r)
+#pragma unroll
+        for (int cc = 0; cc < B; ++cc) s[r] += (double)ld_stream(bval32 + vbase + (size_t)(r * B + cc) * nb + jj) * x2[cc];
+    }
+  }
+};
+
+template <int B>
+__device__ __forceinline__ void warp_block_brows_f32(const BsrArgs& m, const float* __restrict__ bval32, const double* __restrict__ x, int64_t wb,
+                                                     int lane, double (&mine)[B]) {
+  const int64_t brow = (wb << 5) + lane;
+  const int64_t blo = brow < m.n_brows ? brow : m.n_brows, bhi = brow + 1 < m.n_brows ? brow + 1 : m.n_brows;
+  const int ptr_lo = m.bptr[blo], ptr_hi = m.bptr[bhi];
+#pragma unroll
+  for (int r = 0; r < B; ++r) mine[r] = 0.0;
+  for (int t = 0; t < 32; t += 2) {
+    const int sa = __shfl_sync(0xffffffffu, ptr_lo, t), ea = __shfl_sync(0xffffffffu, ptr_hi, t);
+    const int sb = __shfl_sync(0xffffffffu, ptr_lo, t + 1), eb = __shfl_sync(0xffffffffu, ptr_hi, t + 1);
+    BlockRowF<B> RA, RB;
+    RA.issue(m, sa, ea - sa, lane);
+    RB.issue(m, sb, eb - sb, lane);
+    RA.issue_vals(bval32);
+    RB.issue_vals(bval32);
+    __syncwarp();  // scheduling fence, see k_spmv
+    double s_a[B], s_b[B];
+    RA.finish(m, bval32, x, sa, s_a);
+    RB.finish(m, bval32, x, sb, s_b);
+#pragma unroll
+    for (int r = 0; r < B; ++r) {
+      double va = s_a[r], vb = s_b[r];
+      for (int o = 16; o > 0; o >>= 1) {
+        va += __shfl_xor_sync(0xffffffffu, va, o);
+        vb += __shfl_xor_sync(0xffffffffu, vb, o);
+      }
+      if (lane == t) mine[r] = va;
+      if (lane == t + 1) mine[r] = vb;
+    }
+  }
+}
+
+// r -= A~ d ; d' = c1 d + c2 D^-1 r ; z += d'   (the EPI_CHEB epilogue of k_spmv_bsr)
+template <int B>
+__global__ void __launch_bounds__(SPMV_T) k_spmv_bsr_cheb_f32(SpmvArgs a, BsrArgs m, const float* __restrict__ bval32) {
+  if (a.state && a.state->done) return;
+  if (a.ctl) {
+    bool ok = true;
+    if ((int)threadIdx.x < a.n_neigh) ok = pe_wait_flag(&a.ctl->halo_flag[a.field][a.neigh_rank[threadIdx.x]], a.halo_epoch);
+    if (!ok && a.state) { CgState* st = const_cast<CgState*>(a.state); st->pad = 1; st->done = -1; }
+    __threadfence_system();
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n_wb = (m.n_brows + 31) >> 5;
+  for (int64_t wb = (int64_t)blockIdx.x * (SPMV_T / 32) + warp; wb < n_wb; wb += (int64_t)gridDim.x * (SPMV_T / 32)) {
+    const int64_t brow = (wb << 5) + lane;
+    double mine[B];
+    warp_block_brows_f32<B>(m, bval32, a.x, wb, lane, mine);
+    if (brow < m.n_brows) {
+#pragma unroll
+      for (int r = 0; r < B; ++r) {
+        const int64_t row = brow * B + r;
+        const double rn = a.r[row] - mine[r];
+        a.r[row] = rn;
+        const double dn = a.c1 * a.x[row] + a.c2 * a.invdiag[row] * rn;
+        a.d_out[row] = dn;
+        a.z[row] += dn;
+      }
+    }
+  }
+}
+
+__global__ void k_to_float(int64_t n, const double* __restrict__ in, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (float)in[i];
+}
+
 // pressure residual (PS:113-155): r = -( M t1 + kappa K p + f ), ||r||^2 -> slot
 template <int LPR>
 __global__ void __launch_bounds__(SPMV_T)
@@ -695,6 +822,13 @@ void launch_spmv(pe_ctx* c, Field& F, SpmvArgs& a) {
   if (F.bsr.B && a.val == c->A.p && a.row0 == 0 && a.n == F.n_owned) {  // the displacement matrix has a block-CSR copy
     BsrArgs m{F.bsr.bptr.p, F.bsr.bcol.p, F.bsr.bval.p, F.bsr.n_brows};
     const int bgrid = spmv_grid(c, F.bsr.n_brows, 32);
+    if (EPI == EPI_CHEB && F.bsr.bval32.p) {  // PE_CHEB_FP32=1: the polynomial preconditioner reads the FP32 copy of the values
+      if (F.bsr.B == 3) k_spmv_bsr_cheb_f32<3><<<bgrid, SPMV_T, 0, c->stream>>>(a, m, F.bsr.bval32.p);
+      else k_spmv_bsr_cheb_f32<2><<<bgrid, SPMV_T, 0, c->stream>>>(a, m, F.bsr.bval32.p);
+      if (c->profiling && !c->prof_hold) pe_prof_end(c);
+      c->st.kernel_launches++;
+      return;
+    }
     if (F.bsr.B == 3) k_spmv_bsr<3, EPI><<<bgrid, SPMV_T, 0, c->stream>>>(a, m);
     else k_spmv_bsr<2, EPI><<<bgrid, SPMV_T, 0, c->stream>>>(a, m);
     if (c->profiling && !c->prof_hold) pe_prof_end(c);
@@ -794,6 +928,18 @@ double pe_linfty(pe_ctx* c, Field& F, const double* v) {
     PE_CUDA(cudaStreamSynchronize(c->stream));
   }
   return m;
+}
+
+// FP32 copy of the block values for the Chebyshev preconditioner (opt-in: PE_CHEB_FP32=1 and a Chebyshev preconditioner)
+void pe_build_bsr_fp32(pe_ctx* c, Field& F) {
+  F.bsr.bval32.release();
+  static const bool want = std::getenv("PE_CHEB_FP32") && std::string(std::getenv("PE_CHEB_FP32")) == "1";
+  if (!want || !F.bsr.B || c->prm.preconditioner != PE_PRECOND_CHEBYSHEV) return;
+  const int64_t nv = F.bsr.nnzb * F.bsr.B * F.bsr.B;
+  F.bsr.bval32.alloc((size_t)nv);
+  k_to_float<<<vec_grid(c, nv), VEC_T, 0, c->stream>>>(nv, F.bsr.bval.p, F.bsr.bval32.p);
+  c->st.kernel_launches++;
+  PE_CUDA(cudaGetLastError());
 }
 
 double pe_vec_dot(pe_ctx* c, Field& F, const double* a, const double* b) {

@@ -3,6 +3,7 @@ tests/test_zz_gpu_amr.py (a sticky CUDA error or a hang in a not-yet-verified ke
 
     python tests/amr_gpu_case.py static <dim> <degree_u> <rounds>     hanging-node mesh: matrices, rhs, 3 time steps
     python tests/amr_gpu_case.py driver                               C++ driver with 'Refine every = 5' on the shipped input
+    python tests/amr_gpu_case.py chebfp32                             PE_CHEB_FP32=1 (set by the caller): Chebyshev(3) with FP32 inner passes
 
 Prints one JSON line; exit code 0 = every bar met."""
 import json
@@ -102,7 +103,39 @@ def driver_case():
     return {"case": "driver", "cells_per_step": cells, "errors": errs, "ok": bool(ok)}
 
 
+def cheb_fp32_case():
+    """3D Q1 16^3, Chebyshev(3)-Jacobi CG.  With PE_CHEB_FP32=1 in the environment the polynomial's matrix passes read the FP32
+    copy of the block values; fields must still match the oracle to 1e-8 and the iteration counts those of the prototype."""
+    import os
+    inp = capi.InputData(text=H.make_input(dim=3, refine=4, degree_u=1))
+    mesh = fss.make_mesh(inp)
+    dev, ora = capi.create_device_backend(0), H.create_oracle_backend()
+    prm = inp.params()
+    prm.preconditioner = capi.PRECOND_CHEBYSHEV
+    prm.chebyshev_degree = 3
+    prm.cg_max_iterations = 5000
+    for b in (dev, ora):
+        fss.upload_problem(b, inp, mesh, prm)
+    i_d, i_o = fss.initialize(dev, inp), fss.initialize(ora, inp)
+    errs, ok = [], True
+    for step in range(3):
+        r_d, r_o = fss.time_step(dev, inp), fss.time_step(ora, inp)
+        ep = fss.rel_l2(dev.get_vector(capi.VEC_P), ora.get_vector(capi.VEC_P))
+        eu = fss.rel_l2(dev.get_vector(capi.VEC_U), ora.get_vector(capi.VEC_U))
+        errs.append([ep, eu])
+        ok = ok and r_d["inner_counts"] == r_o["inner_counts"] and ep <= FIELD_TOL and eu <= FIELD_TOL
+    out = {"case": "chebfp32", "env": os.environ.get("PE_CHEB_FP32", "0"), "initial_cg_its_displacement": i_d["cg_its_displacement"],
+           "field_errors": errs, "ok": bool(ok and 15 <= i_d["cg_its_displacement"] <= 40)}  # prototype: 24 iterations at 16^3
+    dev.close(); ora.close()
+    return out
+
+
 if __name__ == "__main__":
-    res = static_case(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])) if sys.argv[1] == "static" else driver_case()
+    if sys.argv[1] == "static":
+        res = static_case(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
+    elif sys.argv[1] == "chebfp32":
+        res = cheb_fp32_case()
+    else:
+        res = driver_case()
     print(json.dumps(res))
     sys.exit(0 if res["ok"] else 1)
