@@ -218,25 +218,59 @@ struct Forest {
   // pairs of active cells that share a line or half a line (2D: faces; 3D: faces and edges)
   std::vector<std::pair<int32_t, int32_t>> line_adjacency() const {
     dofs::RefElement ref = dofs::make_ref_element(dim, 1);
-    std::unordered_map<dofs::EntityKey, std::vector<int32_t>, dofs::PairHash> by_line;
-    for (size_t i = 0; i < cells.size(); ++i) {
-      const Cell& c = cells[i];
-      if (!c.active || c.dead) continue;
-      for (auto& l : ref.lines) by_line[dofs::edge_key(c.v[l[0]], c.v[l[1]])].push_back((int32_t)i);
+    const int nl = (int)ref.lines.size();
+    // line table in CSR form: id per distinct line, the active cells that have it as a full line
+    dofs::FlatMap<int32_t> line_id;
+    std::vector<int32_t> act;
+    for (size_t i = 0; i < cells.size(); ++i)
+      if (cells[i].active && !cells[i].dead) act.push_back((int32_t)i);
+    line_id.reserve(act.size() * (dim == 2 ? 2 : 3) + 16);
+    std::vector<int32_t> cell_line(act.size() * nl), count;
+    std::vector<dofs::EntityKey> keys;
+    for (size_t i = 0; i < act.size(); ++i) {
+      const Cell& c = cells[act[i]];
+      for (int l = 0; l < nl; ++l) {
+        const dofs::EntityKey k = dofs::edge_key(c.v[ref.lines[l][0]], c.v[ref.lines[l][1]]);
+        auto it = line_id.find(k);
+        int32_t id;
+        if (it == line_id.end()) {
+          id = (int32_t)keys.size();
+          line_id[k] = id;
+          keys.push_back(k);
+          count.push_back(0);
+        } else
+          id = it->second;
+        cell_line[i * nl + l] = id;
+        count[id]++;
+      }
     }
+    std::vector<int32_t> ptr(keys.size() + 1, 0);
+    for (size_t l = 0; l < keys.size(); ++l) ptr[l + 1] = ptr[l] + count[l];
+    std::vector<int32_t> members(ptr.back()), fill(ptr.begin(), ptr.end() - 1);
+    for (size_t i = 0; i < act.size(); ++i)
+      for (int l = 0; l < nl; ++l) members[fill[cell_line[i * nl + l]]++] = act[i];
+    // a line can only have a used midpoint when a finer cell touches one of its ends
+    std::vector<int8_t> vmax(n_vertices(), -1);
+    for (int32_t ci : act)
+      for (int k = 0; k < vpc(); ++k) vmax[cells[ci].v[k]] = std::max<int8_t>(vmax[cells[ci].v[k]], (int8_t)cells[ci].level);
     std::vector<std::pair<int32_t, int32_t>> pairs;
-    for (auto& kv : by_line) {
-      const auto& g = kv.second;
-      for (size_t i = 0; i < g.size(); ++i)
-        for (size_t j = i + 1; j < g.size(); ++j) pairs.push_back({g[i], g[j]});
-      auto mid = edge_mid.find(kv.first);
+    pairs.reserve(members.size() * 2);
+    for (size_t l = 0; l < keys.size(); ++l) {
+      const int32_t* g = &members[ptr[l]];
+      const int n = ptr[l + 1] - ptr[l];
+      for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j) pairs.push_back(g[i] < g[j] ? std::make_pair(g[i], g[j]) : std::make_pair(g[j], g[i]));
+      const int lev = cells[g[0]].level;
+      const int64_t ends[2] = {keys[l].first, keys[l].second};
+      if (vmax[ends[0]] <= lev && vmax[ends[1]] <= lev) continue;
+      auto mid = edge_mid.find(keys[l]);
       if (mid == edge_mid.end()) continue;
-      const int64_t ends[2] = {kv.first.first, kv.first.second};
       for (int e = 0; e < 2; ++e) {
-        auto half = by_line.find(dofs::edge_key(ends[e], mid->second));
-        if (half == by_line.end()) continue;
-        for (int32_t x : g)
-          for (int32_t y : half->second) pairs.push_back({x, y});
+        auto half = line_id.find(dofs::edge_key(ends[e], mid->second));
+        if (half == line_id.end()) continue;
+        for (int i = 0; i < n; ++i)
+          for (int32_t q = ptr[half->second]; q < ptr[half->second + 1]; ++q)
+            pairs.push_back(g[i] < members[q] ? std::make_pair(g[i], members[q]) : std::make_pair(members[q], g[i]));
       }
     }
     std::sort(pairs.begin(), pairs.end());
@@ -349,6 +383,17 @@ inline void hanging_node_constraints(const Forest& F, const mesh::Mesh& m, const
   std::vector<uint8_t> used(F.n_vertices(), 0);
   for (int64_t c = 0; c < m.n_cells(); ++c)
     for (int k = 0; k < vpc; ++k) used[m.cell_vertices[c * vpc + k]] = 1;
+  // Smallest active cell around every vertex (by its longest line).  The midpoint of a line / quad of cell c can only be
+  // in use when a smaller cell touches one of its corners (the refined neighbour's children do), so entities whose corners
+  // see nothing smaller than c are skipped without a hash look-up — on mostly uniform meshes that is nearly all of them.
+  std::vector<int32_t> cell_level(m.n_cells());
+  {
+    std::vector<int32_t> act = F.active_cells();
+    for (int64_t c = 0; c < m.n_cells(); ++c) cell_level[c] = F.cells[act[c]].level;
+  }
+  std::vector<int8_t> vmax(F.n_vertices(), -1);
+  for (int64_t c = 0; c < m.n_cells(); ++c)
+    for (int k = 0; k < vpc; ++k) vmax[m.cell_vertices[c * vpc + k]] = std::max<int8_t>(vmax[m.cell_vertices[c * vpc + k]], (int8_t)cell_level[c]);
   auto line_dof = [&](int64_t a, int64_t b) {
     auto it = maps.line_dof.find(dofs::edge_key(a, b));
     return it == maps.line_dof.end() ? -1 : it->second;
@@ -365,8 +410,10 @@ inline void hanging_node_constraints(const Forest& F, const mesh::Mesh& m, const
   for (int64_t c = 0; c < m.n_cells(); ++c) {
     const int32_t* cv = &m.cell_vertices[c * vpc];
     // lines of the cell whose midpoint is a vertex of finer active cells
+    const int lev = cell_level[c];
     for (auto& l : ref.lines) {
       const int32_t a = cv[l[0]], b = cv[l[1]];
+      if (vmax[a] <= lev && vmax[b] <= lev) continue;
       auto it = F.edge_mid.find(dofs::edge_key(a, b));
       if (it == F.edge_mid.end() || !used[it->second]) continue;
       const int32_t mv = it->second;
@@ -383,6 +430,7 @@ inline void hanging_node_constraints(const Forest& F, const mesh::Mesh& m, const
     // quads of the cell that are refined on the other side
     for (auto& q : ref.quads) {
       const int32_t f[4] = {cv[q[0]], cv[q[1]], cv[q[2]], cv[q[3]]};  // lexicographic in the face frame
+      if (vmax[f[0]] <= lev && vmax[f[1]] <= lev && vmax[f[2]] <= lev && vmax[f[3]] <= lev) continue;
       auto it = F.face_mid.find(dofs::quad_key(f[0], f[1], f[2], f[3]));
       if (it == F.face_mid.end() || !used[it->second]) continue;
       const int32_t fc = it->second;
@@ -522,17 +570,29 @@ inline std::vector<float> kelly_estimate(const Forest& F, const std::vector<doub
     mesh::face_vertices(dim, f, fv);
     return dim == 2 ? dofs::edge_key(c.v[fv[0]], c.v[fv[1]]) : dofs::quad_key(c.v[fv[0]], c.v[fv[1]], c.v[fv[2]], c.v[fv[3]]);
   };
-  std::unordered_map<dofs::EntityKey, std::vector<std::pair<int32_t, int>>, dofs::PairHash> active_face;
+  struct FaceSides {  // an interior face of the active mesh has two sides, a boundary or coarse/fine face one
+    int32_t cell[2] = {-1, -1};
+    int8_t face[2] = {0, 0};
+    int8_t n = 0;
+  };
+  dofs::FlatMap<FaceSides> active_face;
+  active_face.reserve(act.size() * (size_t)dim + 16);
   for (int32_t c : act)
-    for (int f = 0; f < 2 * dim; ++f) active_face[face_key_of(F.cells[c], f)].push_back({c, f});
+    for (int f = 0; f < 2 * dim; ++f) {
+      FaceSides& s = active_face[face_key_of(F.cells[c], f)];
+      if (s.n >= 2) throw std::runtime_error("amr: a face with more than two cells");
+      s.cell[s.n] = c;
+      s.face[s.n] = (int8_t)f;
+      s.n++;
+    }
   // QGauss<dim-1>(2)
   const double ga = 0.5 - 0.5 / std::sqrt(3.0), gb = 0.5 + 0.5 / std::sqrt(3.0);
   std::vector<std::array<double, 2>> qp;
   std::vector<double> qw;
   if (dim == 2) { qp = {{ga, 0}, {gb, 0}}; qw = {0.5, 0.5}; }
   else { qp = {{ga, ga}, {gb, ga}, {ga, gb}, {gb, gb}}; qw = {0.25, 0.25, 0.25, 0.25}; }
-  std::vector<double> sum(act.size(), 0.0);
-  auto integrate = [&](int32_t k, int f, int32_t n, int fn) {  // face f of K is (a part of) face fn of N
+  // face integral of the squared jump; face f of K is (a part of) face fn of N
+  auto integrate = [&](int32_t k, int f, int32_t n, int fn) -> double {
     const Cell& K = F.cells[k];
     const Cell& N = F.cells[n];
     int fv[4];
@@ -561,26 +621,55 @@ inline std::vector<float> kelly_estimate(const Forest& F, const std::vector<doub
       for (int a = 0; a < dim; ++a) jump += (gK[a] - gN[a]) * nv[a] / nn;
       integral += jump * jump * std::fabs(det) * nn * qw[q];
     }
-    sum[pos[k]] += integral;
-    sum[pos[n]] += integral;
+    return integral;
   };
-  for (int32_t k : act) {
+  // Pass 1 (threads): every interior face is integrated once — by the lower-numbered cell of a regular face, by the fine
+  // cell of a coarse/fine face — into its own slot.  Pass 2 (sequential, fixed order): the slots are added to the two
+  // cells, so the sums do not depend on the number of threads.
+  const int nf = 2 * dim;
+  const int64_t na = (int64_t)act.size();
+  std::vector<double> face_int((size_t)na * nf, 0.0);
+  std::vector<int32_t> partner((size_t)na * nf, -1);
+  int failed = 0;
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int64_t i = 0; i < na; ++i) {
+    const int32_t k = act[i];
     const Cell& K = F.cells[k];
-    for (int f = 0; f < 2 * dim; ++f) {
+    for (int f = 0; f < nf; ++f) {
       if (K.bid[f] >= 0) continue;  // no Neumann function map at FSS:456: boundary faces contribute nothing
-      bool done = false;
-      for (auto& e : active_face[face_key_of(K, f)])
-        if (e.first != k) {
-          if (k < e.first) integrate(k, f, e.first, e.second);
-          done = true;
-        }
-      if (done || K.parent < 0) continue;
-      if (((K.child_index >> (f / 2)) & 1) != (f % 2)) continue;  // interior face of the parent
-      auto it = active_face.find(face_key_of(F.cells[K.parent], f));
-      if (it == active_face.end()) continue;
-      for (auto& e : it->second) integrate(k, f, e.first, e.second);  // coarser neighbour: sub-face integral
+      int32_t n = -1;
+      int fn = 0;
+      bool regular = false;
+      const auto same = active_face.find(face_key_of(K, f));
+      for (int e = 0; same != active_face.end() && e < same->second.n; ++e)
+        if (same->second.cell[e] != k) { n = same->second.cell[e]; fn = same->second.face[e]; regular = true; }
+      if (regular) {
+        if (!(k < n)) continue;  // the other side integrates this face
+      } else {
+        if (K.parent < 0 || ((K.child_index >> (f / 2)) & 1) != (f % 2)) continue;  // interior face of the parent / finer neighbour
+        const auto it = active_face.find(face_key_of(F.cells[K.parent], f));
+        if (it == active_face.end() || it->second.n == 0) continue;  // the neighbour is finer: integrated from its side
+        n = it->second.cell[0];
+        fn = it->second.face[0];
+      }
+      try {
+        face_int[(size_t)i * nf + f] = integrate(k, f, n, fn);
+        partner[(size_t)i * nf + f] = n;
+      } catch (const std::exception&) {
+#pragma omp atomic write
+        failed = 1;
+      }
     }
   }
+  if (failed) throw std::runtime_error("amr: faces do not match (mesh not 2:1 balanced?)");
+  std::vector<double> sum(act.size(), 0.0);
+  for (int64_t i = 0; i < na; ++i)
+    for (int f = 0; f < nf; ++f) {
+      const int32_t n = partner[(size_t)i * nf + f];
+      if (n < 0) continue;
+      sum[i] += face_int[(size_t)i * nf + f];
+      sum[pos[n]] += face_int[(size_t)i * nf + f];
+    }
   std::vector<float> eta(act.size());
   for (size_t i = 0; i < act.size(); ++i) {
     const Cell& K = F.cells[act[i]];

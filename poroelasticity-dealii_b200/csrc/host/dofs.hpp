@@ -68,7 +68,87 @@ struct PairHash {
   }
 };
 typedef std::pair<int64_t, int64_t> EntityKey;
-typedef std::unordered_map<EntityKey, int32_t, PairHash> EntityMap;
+
+// Open-addressing hash map for entity keys (lines, quads): no per-node allocation, linear probing, never erased.  The
+// refinement forest does tens of millions of look-ups per pass (amr.hpp); std::unordered_map made those 5-10x slower.
+// Interface: the subset of std::unordered_map the callers use (find / end / operator[] / at / size / swap).
+template <class V>
+class FlatMap {
+ public:
+  struct Slot { EntityKey first; V second; };
+  typedef Slot* iterator;
+  typedef const Slot* const_iterator;
+  FlatMap() { rehash(16); }
+  size_t size() const { return count_; }
+  iterator end() { return nullptr; }
+  const_iterator end() const { return nullptr; }
+  const_iterator find(const EntityKey& k) const {
+    size_t i = hash(k) & mask_;
+    while (used_[i]) {
+      if (slots_[i].first == k) return &slots_[i];
+      i = (i + 1) & mask_;
+    }
+    return nullptr;
+  }
+  iterator find(const EntityKey& k) { return const_cast<iterator>(static_cast<const FlatMap*>(this)->find(k)); }
+  V& operator[](const EntityKey& k) {
+    if ((count_ + 1) * 2 > slots_.size()) rehash(slots_.size() * 2);
+    size_t i = hash(k) & mask_;
+    while (used_[i]) {
+      if (slots_[i].first == k) return slots_[i].second;
+      i = (i + 1) & mask_;
+    }
+    used_[i] = 1;
+    slots_[i].first = k;
+    slots_[i].second = V();
+    ++count_;
+    return slots_[i].second;
+  }
+  const V& at(const EntityKey& k) const {
+    const_iterator it = find(k);
+    if (!it) throw std::out_of_range("FlatMap::at");
+    return it->second;
+  }
+  void reserve(size_t n) {
+    size_t cap = 16;
+    while (cap < 2 * n) cap <<= 1;
+    if (cap > slots_.size()) rehash(cap);
+  }
+  void swap(FlatMap& o) {
+    slots_.swap(o.slots_);
+    used_.swap(o.used_);
+    std::swap(mask_, o.mask_);
+    std::swap(count_, o.count_);
+  }
+  template <class F>
+  void for_each(F&& f) const {
+    for (size_t i = 0; i < slots_.size(); ++i)
+      if (used_[i]) f(slots_[i].first, slots_[i].second);
+  }
+
+ private:
+  static size_t hash(const EntityKey& k) {
+    uint64_t h = (uint64_t)k.first * 0x9e3779b97f4a7c15ull ^ ((uint64_t)k.second + 0x7f4a7c159e3779b9ull) * 0xc2b2ae3d27d4eb4full;
+    h ^= h >> 32;
+    return (size_t)h;
+  }
+  void rehash(size_t cap) {
+    std::vector<Slot> old;
+    std::vector<uint8_t> old_used;
+    old.swap(slots_);
+    old_used.swap(used_);
+    slots_.resize(cap);
+    used_.assign(cap, 0);
+    mask_ = cap - 1;
+    count_ = 0;
+    for (size_t i = 0; i < old.size(); ++i)
+      if (old_used[i]) (*this)[old[i].first] = old[i].second;
+  }
+  std::vector<Slot> slots_;
+  std::vector<uint8_t> used_;
+  size_t mask_ = 0, count_ = 0;
+};
+typedef FlatMap<int32_t> EntityMap;
 
 // A line is identified by its two vertices, a quad by its four (orientation-free keys).
 inline EntityKey edge_key(int64_t a, int64_t b) { return a < b ? EntityKey{a, b} : EntityKey{b, a}; }
