@@ -215,11 +215,17 @@ struct Forest {
     return true;
   }
 
-  // pairs of active cells that share a line or half a line (2D: faces; 3D: faces and edges)
-  std::vector<std::pair<int32_t, int32_t>> line_adjacency() const {
+  // Lines of the active mesh in CSR form: the active cells that have the line as one of their own, and, where the line's
+  // midpoint exists and finer cells touch the line, its two halves (lines of the next level).  Two cells "share a line or
+  // half a line" (2D: a face; 3D: a face or an edge) iff they are members of one line, or of a line and one of its halves.
+  struct LineTable {
+    std::vector<int32_t> ptr, members;   // line -> active cells
+    std::vector<int32_t> half;           // 2 per line: id of the half line or -1
+    int64_t n_lines() const { return (int64_t)ptr.size() - 1; }
+  };
+  LineTable line_table() const {
     dofs::RefElement ref = dofs::make_ref_element(dim, 1);
     const int nl = (int)ref.lines.size();
-    // line table in CSR form: id per distinct line, the active cells that have it as a full line
     dofs::FlatMap<int32_t> line_id;
     std::vector<int32_t> act;
     for (size_t i = 0; i < cells.size(); ++i)
@@ -244,38 +250,30 @@ struct Forest {
         count[id]++;
       }
     }
-    std::vector<int32_t> ptr(keys.size() + 1, 0);
-    for (size_t l = 0; l < keys.size(); ++l) ptr[l + 1] = ptr[l] + count[l];
-    std::vector<int32_t> members(ptr.back()), fill(ptr.begin(), ptr.end() - 1);
+    LineTable T;
+    T.ptr.assign(keys.size() + 1, 0);
+    for (size_t l = 0; l < keys.size(); ++l) T.ptr[l + 1] = T.ptr[l] + count[l];
+    T.members.resize(T.ptr.back());
+    std::vector<int32_t> fill(T.ptr.begin(), T.ptr.end() - 1);
     for (size_t i = 0; i < act.size(); ++i)
-      for (int l = 0; l < nl; ++l) members[fill[cell_line[i * nl + l]]++] = act[i];
+      for (int l = 0; l < nl; ++l) T.members[fill[cell_line[i * nl + l]]++] = act[i];
     // a line can only have a used midpoint when a finer cell touches one of its ends
     std::vector<int8_t> vmax(n_vertices(), -1);
     for (int32_t ci : act)
       for (int k = 0; k < vpc(); ++k) vmax[cells[ci].v[k]] = std::max<int8_t>(vmax[cells[ci].v[k]], (int8_t)cells[ci].level);
-    std::vector<std::pair<int32_t, int32_t>> pairs;
-    pairs.reserve(members.size() * 2);
+    T.half.assign(2 * keys.size(), -1);
     for (size_t l = 0; l < keys.size(); ++l) {
-      const int32_t* g = &members[ptr[l]];
-      const int n = ptr[l + 1] - ptr[l];
-      for (int i = 0; i < n; ++i)
-        for (int j = i + 1; j < n; ++j) pairs.push_back(g[i] < g[j] ? std::make_pair(g[i], g[j]) : std::make_pair(g[j], g[i]));
-      const int lev = cells[g[0]].level;
+      const int lev = cells[T.members[T.ptr[l]]].level;
       const int64_t ends[2] = {keys[l].first, keys[l].second};
       if (vmax[ends[0]] <= lev && vmax[ends[1]] <= lev) continue;
       auto mid = edge_mid.find(keys[l]);
       if (mid == edge_mid.end()) continue;
       for (int e = 0; e < 2; ++e) {
-        auto half = line_id.find(dofs::edge_key(ends[e], mid->second));
-        if (half == line_id.end()) continue;
-        for (int i = 0; i < n; ++i)
-          for (int32_t q = ptr[half->second]; q < ptr[half->second + 1]; ++q)
-            pairs.push_back(g[i] < members[q] ? std::make_pair(g[i], members[q]) : std::make_pair(members[q], g[i]));
+        auto h = line_id.find(dofs::edge_key(ends[e], mid->second));
+        if (h != line_id.end()) T.half[2 * l + e] = h->second;
       }
     }
-    std::sort(pairs.begin(), pairs.end());
-    pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
-    return pairs;
+    return T;
   }
 
   void clear_family_coarsen(int32_t c) {
@@ -286,7 +284,7 @@ struct Forest {
 
   // Triangulation::prepare_coarsening_and_refinement (FSS:481)
   void prepare() {
-    auto pairs = line_adjacency();
+    const LineTable T = line_table();
     bool changed = true;
     while (changed) {
       changed = false;
@@ -310,15 +308,31 @@ struct Forest {
           changed = true;
         }
       }
+      // level difference <= 1 across every shared (half) line after the pass; refinement wins over coarsening
       auto future = [&](int32_t c) { return cells[c].level + (cells[c].refine_flag ? 1 : 0) - (cells[c].coarsen_flag ? 1 : 0); };
-      for (auto& pr : pairs)
-        for (int s = 0; s < 2; ++s) {
-          const int32_t hi = s ? pr.second : pr.first, lo = s ? pr.first : pr.second;
-          if (future(hi) - future(lo) <= 1) continue;
-          if (cells[lo].coarsen_flag) clear_family_coarsen(lo);
-          else cells[lo].refine_flag = true;
-          changed = true;
+      auto raise = [&](int32_t lo) {
+        if (cells[lo].coarsen_flag) clear_family_coarsen(lo);
+        else cells[lo].refine_flag = true;
+        changed = true;
+      };
+      for (int64_t l = 0; l < T.n_lines(); ++l) {
+        int top_own = -1000, top_half = -1000;
+        for (int32_t q = T.ptr[l]; q < T.ptr[l + 1]; ++q) top_own = std::max(top_own, future(T.members[q]));
+        for (int e = 0; e < 2; ++e) {
+          const int32_t h = T.half[2 * l + e];
+          if (h < 0) continue;
+          for (int32_t q = T.ptr[h]; q < T.ptr[h + 1]; ++q) top_half = std::max(top_half, future(T.members[q]));
         }
+        const int top = std::max(top_own, top_half);
+        for (int32_t q = T.ptr[l]; q < T.ptr[l + 1]; ++q)
+          if (top - future(T.members[q]) > 1) raise(T.members[q]);
+        for (int e = 0; e < 2; ++e) {
+          const int32_t h = T.half[2 * l + e];
+          if (h < 0) continue;
+          for (int32_t q = T.ptr[h]; q < T.ptr[h + 1]; ++q)
+            if (top_own - future(T.members[q]) > 1) raise(T.members[q]);
+        }
+      }
     }
   }
 
