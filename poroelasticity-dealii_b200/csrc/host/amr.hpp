@@ -589,16 +589,55 @@ inline std::vector<float> kelly_estimate(const Forest& F, const std::vector<doub
     int8_t face[2] = {0, 0};
     int8_t n = 0;
   };
-  dofs::FlatMap<FaceSides> active_face;
-  active_face.reserve(act.size() * (size_t)dim + 16);
-  for (int32_t c : act)
-    for (int f = 0; f < 2 * dim; ++f) {
-      FaceSides& s = active_face[face_key_of(F.cells[c], f)];
-      if (s.n >= 2) throw std::runtime_error("amr: a face with more than two cells");
-      s.cell[s.n] = c;
-      s.face[s.n] = (int8_t)f;
+  // The table is sharded by a hash of the key so that the threads can build it concurrently: the keys of all
+  // (cell, face) pairs are computed once, bucketed by shard with a counting sort (which keeps the cell order inside a
+  // shard, so the table does not depend on the number of threads), and every shard is filled by one thread.
+  constexpr int N_SHARDS = 64;
+  auto shard_of = [](const dofs::EntityKey& k) {
+    uint64_t h = (uint64_t)k.first * 0xd6e8feb86659fd93ull + (uint64_t)k.second * 0xa0761d6478bd642full;
+    return (int)((h >> 40) & (N_SHARDS - 1));
+  };
+  const int nf = 2 * dim;
+  const int64_t na = (int64_t)act.size(), nkeys = na * nf;
+  std::vector<dofs::EntityKey> keys((size_t)nkeys);
+  std::vector<uint8_t> key_shard((size_t)nkeys);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < na; ++i)
+    for (int f = 0; f < nf; ++f) {
+      keys[(size_t)i * nf + f] = face_key_of(F.cells[act[i]], f);
+      key_shard[(size_t)i * nf + f] = (uint8_t)shard_of(keys[(size_t)i * nf + f]);
+    }
+  std::vector<int64_t> bucket_ptr(N_SHARDS + 1, 0);
+  for (int64_t q = 0; q < nkeys; ++q) bucket_ptr[key_shard[q] + 1]++;
+  for (int sh = 0; sh < N_SHARDS; ++sh) bucket_ptr[sh + 1] += bucket_ptr[sh];
+  std::vector<int64_t> bucket((size_t)nkeys), fill_pos(bucket_ptr.begin(), bucket_ptr.end() - 1);
+  for (int64_t q = 0; q < nkeys; ++q) bucket[fill_pos[key_shard[q]]++] = q;
+  std::vector<dofs::FlatMap<FaceSides>> shards(N_SHARDS);
+  int too_many = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int sh = 0; sh < N_SHARDS; ++sh) {
+    dofs::FlatMap<FaceSides>& M = shards[sh];
+    M.reserve((size_t)(bucket_ptr[sh + 1] - bucket_ptr[sh]) / 2 + 64);
+    for (int64_t b = bucket_ptr[sh]; b < bucket_ptr[sh + 1]; ++b) {
+      const int64_t q = bucket[b];
+      FaceSides& s = M[keys[q]];
+      if (s.n >= 2) {
+#pragma omp atomic write
+        too_many = 1;
+        continue;
+      }
+      s.cell[s.n] = act[q / nf];
+      s.face[s.n] = (int8_t)(q % nf);
       s.n++;
     }
+  }
+  if (too_many) throw std::runtime_error("amr: a face with more than two cells");
+  struct ShardedFaces {
+    const std::vector<dofs::FlatMap<FaceSides>>& shards;
+    decltype(shard_of)& shard;
+    const dofs::FlatMap<FaceSides>::Slot* find(const dofs::EntityKey& k) const { return shards[shard(k)].find(k); }
+    const dofs::FlatMap<FaceSides>::Slot* end() const { return nullptr; }
+  } active_face{shards, shard_of};
   // QGauss<dim-1>(2)
   const double ga = 0.5 - 0.5 / std::sqrt(3.0), gb = 0.5 + 0.5 / std::sqrt(3.0);
   std::vector<std::array<double, 2>> qp;
@@ -640,8 +679,6 @@ inline std::vector<float> kelly_estimate(const Forest& F, const std::vector<doub
   // Pass 1 (threads): every interior face is integrated once — by the lower-numbered cell of a regular face, by the fine
   // cell of a coarse/fine face — into its own slot.  Pass 2 (sequential, fixed order): the slots are added to the two
   // cells, so the sums do not depend on the number of threads.
-  const int nf = 2 * dim;
-  const int64_t na = (int64_t)act.size();
   std::vector<double> face_int((size_t)na * nf, 0.0);
   std::vector<int32_t> partner((size_t)na * nf, -1);
   int failed = 0;
@@ -654,7 +691,7 @@ inline std::vector<float> kelly_estimate(const Forest& F, const std::vector<doub
       int32_t n = -1;
       int fn = 0;
       bool regular = false;
-      const auto same = active_face.find(face_key_of(K, f));
+      const auto same = active_face.find(keys[(size_t)i * nf + f]);
       for (int e = 0; same != active_face.end() && e < same->second.n; ++e)
         if (same->second.cell[e] != k) { n = same->second.cell[e]; fn = same->second.face[e]; regular = true; }
       if (regular) {
