@@ -497,3 +497,53 @@ def test_device_constraint_kernels_executed_on_the_cpu_match_the_oracle(emu, dim
     assert abs(sp.csr_matrix((mdst, cp, rp), shape=(npd, npd)) - PM).max() <= 1e-13 * abs(PM).max()
     plain.close()
     full.close()
+
+
+@pytest.mark.parametrize("dim,deg,rounds", [(2, 2, 3), (3, 1, 2)])
+def test_two_phase_algorithm_with_a_neumann_load_on_a_refined_face(dim, deg, rounds):
+    """Stress boundary (DS:249-277) on the faces the refined corner touches: in 3D their hanging nodes lie ON the loaded face.
+    Phase 1 adds the face term to hanging rows as if they were free, phase 2 hands those rows to the masters — the same
+    right-hand side as the cell-wise distribute_local_to_global of the oracle."""
+    import scipy.sparse as sp
+    labels = list(range(2, 2 * dim))  # rollers everywhere except the two x faces
+    dirichlet = (labels + [1], [l // 2 for l in labels] + [0], [0.0] * len(labels) + [-1e-5])
+    neumann = ([0], [0], [-3e6])      # traction on x-min, which the refined corner touches
+    inp, F, am, full, dp, du, Lp, Lu = adaptive_oracle(dim, deg, rounds, dirichlet=dirichlet, neumann=neumann)
+    DL = DeviceLines(Lu)
+    assert DL.n > 0
+    plain = H.create_oracle_backend()
+    plain.set_params(inp.params())
+    plain.upload_mesh(am.arrays)
+    plain.upload_dofs(capi.FIELD_PRESSURE, dp.n_dofs, dp.cell_dofs)
+    plain.upload_dofs(capi.FIELD_DISPLACEMENT, du.n_dofs, du.cell_dofs)
+    plain.upload_constraints(capi.FIELD_DISPLACEMENT, Lu.line_dof[DL.diri], Lu.inhomogeneity[DL.diri])
+    plain.upload_neumann(inp.stress_boundary_labels, inp.stress_boundary_components, inp.stress_boundary_values)
+    plain.setup()
+    for b in (plain, full):
+        b.pressure_set_uniform(inp.p_init)
+        b.displacement_assemble()
+    n = du.n_dofs
+    x = du.support_points()
+    on_face = np.isclose(x[:, 0], -5.0)
+    comp = components(du, dim)
+    if dim == 3:
+        assert (on_face[DL.dof] & (comp[DL.dof] == 0)).any()  # hanging nodes on the loaded face, loaded component
+    A1 = plain.get_matrix(capi.MAT_ELASTICITY); A1.resize((n, n))
+    g_t = np.zeros(n); g_t[DL.dof] = DL.g
+    b1 = plain.get_vector(capi.VEC_U_RHS) - A1 @ g_t
+    rows = np.repeat(DL.dof, np.diff(DL.ptr))
+    is_h = np.zeros(n, bool); is_h[DL.dof] = True
+    keep = np.nonzero(~is_h)[0]
+    E = sp.csr_matrix((np.concatenate([DL.w, np.ones(len(keep))]), (np.concatenate([rows, keep]), np.concatenate([DL.edof, keep]))), shape=(n, n))
+    b_hat = E.T @ b1
+    b_hat[is_h] = 0.0
+    b_full = full.get_vector(capi.VEC_U_RHS)
+    assert np.abs(b_full).max() > 0 and np.abs(b_hat - b_full).max() <= 1e-12 * np.abs(b_full).max()
+    # and the loaded problem still solves: the mean traction is balanced by the rollers' reactions, u stays conforming
+    fss.initialize(full, inp)
+    u = full.get_vector(capi.VEC_U)
+    for i in range(Lu.n_lines):
+        d, ed, ew, g = Lu.line(i)
+        assert abs(u[d] - (u[ed] @ ew + g)) <= 1e-12 * np.abs(u).max()
+    plain.close()
+    full.close()
