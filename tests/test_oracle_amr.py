@@ -547,3 +547,68 @@ def test_two_phase_algorithm_with_a_neumann_load_on_a_refined_face(dim, deg, rou
         assert abs(u[d] - (u[ed] @ ew + g)) <= 1e-12 * np.abs(u).max()
     plain.close()
     full.close()
+
+
+def random_forest(dim, seed, rounds):
+    rng = np.random.default_rng(seed)
+    F = capi.Forest(capi.mesh_rectangle(dim, [10.0] * dim, 1), 1)
+    for _ in range(rounds):
+        lv = F.levels()
+        re = (rng.random(len(lv)) < 0.3) & (lv < 4)
+        co = (rng.random(len(lv)) < 0.3) & ~re
+        F.set_flags(refine=re.astype(np.int8), coarsen=co.astype(np.int8))
+        F.execute()
+    return F
+
+
+@pytest.mark.parametrize("dim,deg,seed,rounds", [(2, 1, 0, 5), (2, 2, 1, 4), (2, 2, 2, 5), (3, 1, 3, 3), (3, 2, 4, 2)])
+def test_oracle_matches_numpy_on_randomly_refined_meshes(dim, deg, seed, rounds):
+    """Random refine / coarsen sequences produce level staircases, chains of hanging nodes (2D) and hanging nodes on Dirichlet
+    faces and edges; the tree-based constraint tables and the cell-wise condensed matrices must still equal the geometric
+    numpy restatement."""
+    F = random_forest(dim, seed, rounds)
+    am = F.active_mesh()
+    inp = capi.InputData(text=H.make_input(dim=dim, refine=2, degree_u=deg, dirichlet=(list(range(2 * dim)), [i // 2 for i in range(2 * dim)],
+                                                                                      [1e-5, -1e-5, 2e-5, -1e-5, -3e-5, -1e-5][: 2 * dim])))
+    b = H.create_oracle_backend()
+    dp, du, (Lp, Lu) = fss.upload_problem(b, inp, am, forest=F)
+    assert Lp.n_lines > 0 and F.levels().max() - F.levels().min() >= 1
+    prm = inp.params()
+    P = {k: getattr(prm, k) for k in ("lame_lambda", "shear_modulus", "bulk_modulus", "biot_coef", "m_modulus", "perm_over_visc", "well_radius", "flow_rate")}
+    lo, hi = cell_boxes(am.arrays)
+    R = AdaptiveNP(dim, lo, hi, deg, P)
+    R.assemble_displacement([(int(l), int(c), float(v)) for l, c, v in zip(inp.displacement_boundary_labels, inp.displacement_boundary_components,
+                                                                         inp.displacement_boundary_values)])
+    pp = perm_by_coords(R.xp, dp.support_points())
+    pu = perm_by_coords(R.xu, du.support_points()) * dim + components(du, dim)
+    assert {int(pp[d]) for d in Lp.line_dof} == set(R.lines_p)
+    for i in range(Lp.n_lines):
+        d, ed, ew, g = Lp.line(i)
+        ref = R.lines_p[int(pp[d])]
+        assert {int(pp[e]) for e in ed} == set(ref) and all(abs(ref[int(pp[e])] - w) < 1e-14 for e, w in zip(ed, ew))
+    seen = set()
+    for i in range(Lu.n_lines):
+        d, ed, ew, g = Lu.line(i)
+        if int(pu[d]) not in R.lines_u:
+            assert deg == 2 and len(ed) == 1 and ew[0] == 1.0 and g == 0.0 and pu[ed[0]] == pu[d]
+            continue
+        seen.add(int(pu[d]))
+        ref_w, ref_g = R.lines_u[int(pu[d])]
+        assert {int(pu[e]) for e in ed} == set(ref_w) and all(abs(ref_w[int(pu[e])] - w) < 1e-13 for e, w in zip(ed, ew))
+        assert abs(ref_g - g) <= 1e-19
+    assert seen == set(R.lines_u)
+    b.pressure_set_uniform(inp.p_init)
+    b.displacement_assemble()
+    b.project_assemble_matrix()
+    b.assemble_jacobian(inp.time_step)
+    rel = lambda X, Y: abs(X - Y).max() / abs(Y).max()
+    free_u = np.ones(du.n_dofs, bool)
+    free_u[Lu.line_dof] = False
+    fu = np.nonzero(free_u)[0]
+    assert rel(b.get_matrix(capi.MAT_ELASTICITY)[fu][:, fu], R.condensed_elasticity()[pu[fu]][:, pu[fu]]) <= 1e-13
+    assert rel(b.get_matrix(capi.MAT_PROJECTION), R.condensed(R.M)[pp][:, pp]) <= 1e-13
+    Jn = R.condensed(R.M * (1.0 / prm.m_modulus / inp.time_step) + prm.perm_over_visc * R.K)
+    assert rel(b.get_matrix(capi.MAT_JACOBIAN), Jn[pp][:, pp]) <= 1e-13
+    R.p = np.full(R.np_, float(inp.p_init))
+    assert fss.rel_l2(b.get_vector(capi.VEC_U_RHS)[fu], R.rhs_displacement(R.p)[pu[fu]]) <= 1e-12
+    b.close()
