@@ -69,7 +69,8 @@ def test_ctypes_struct_offsets_match_a_c_compile_of_the_header(tmp_path):
         return "\n".join(lines)
 
     mirrors = {"pe_params": capi.PeParams, "pe_stats": capi.PeStats, "peh_step_report": capi.StepReport, "peh_mesh_view": capi.MeshView,
-               "peh_dofs_view": capi.DofsView, "peh_input_view": capi.InputView, "peh_part_field_view": capi.PartFieldView, "peh_part_view": capi.PartView}
+               "peh_dofs_view": capi.DofsView, "peh_input_view": capi.InputView, "peh_part_field_view": capi.PartFieldView, "peh_part_view": capi.PartView,
+               "peh_constraints_view": capi.ConstraintsView}
     body = "\n".join(emit(name, name, [f for f, _ in cls._fields_]) for name, cls in mirrors.items())
     src = tmp_path / "offsets.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "poroel_host.h"\nint main(void) {\n' + body + "\n  return 0;\n}\n")
