@@ -45,6 +45,7 @@ struct Forest {
   std::vector<Cell> cells;
   dofs::EntityMap edge_mid, face_mid;  // line / quad (3D) -> midpoint vertex
   // vertex-keyed payload of the solution transfer (FSS:475-497)
+  static constexpr int MAX_TRANSFER = 8;
   int n_transfer = 0;
   std::vector<double> vval;     // n_vertices * n_transfer
   std::vector<uint8_t> vknown;  // vertex carried a dof of the old mesh
@@ -156,7 +157,7 @@ struct Forest {
     if (!cells[c].active || cells[c].dead) throw std::runtime_error("amr: refine of a non-active cell");
     const int nv = vpc();
     const int32_t first = (int32_t)cells.size();
-    std::vector<Cell> kids(nv);
+    Cell kids[8];
     for (int ci = 0; ci < nv; ++ci) {
       Cell& k = kids[ci];
       k.level = cells[c].level + 1;
@@ -176,7 +177,7 @@ struct Forest {
         const int32_t v = lattice_vertex(c, idx);
         if (vknown[v]) continue;
         int n = 0;
-        std::vector<double> acc(n_transfer, 0.0);
+        double acc[MAX_TRANSFER] = {0};
         for (int k = 0; k < nv; ++k) {
           bool ok = true;
           for (int a = 0; a < dim; ++a) {
@@ -192,7 +193,7 @@ struct Forest {
       }
     cells[c].active = false;
     cells[c].child0 = first;
-    for (auto& k : kids) cells.push_back(k);
+    for (int ci = 0; ci < nv; ++ci) cells.push_back(kids[ci]);
   }
 
   void coarsen_cell(int32_t p) {
@@ -358,6 +359,7 @@ struct Forest {
   // ---- solution transfer of FE_Q(1) fields keyed by vertex (FSS:475-497)
   void store_vertex_values(const mesh::Mesh& m, const dofs::DofMap& dp, int n_vec, const double* const* vec) {
     if (dp.degree != 1 || dp.n_comp != 1) throw std::runtime_error("amr: the transfer handles the FE_Q(1) pressure handler only (FSS:475)");
+    if (n_vec < 1 || n_vec > MAX_TRANSFER) throw std::runtime_error("amr: between 1 and 8 vectors can be transferred at once");
     n_transfer = n_vec;
     vval.assign((size_t)n_vertices() * n_vec, 0.0);
     vknown.assign(n_vertices(), 0);
