@@ -11,7 +11,7 @@ BIN = H.ROOT / "poroelasticity-dealii_b200" / "bin" / "fss-poroel"
 
 
 def test_fss_poroel_runs_the_shipped_case(tmp_path):
-    # input.data as shipped (2D, refine 4, Q2/Q1, dt 60, t_max 1e3 => 17 steps) + AMR off (out of scope)
+    # input.data as shipped (2D, refine 4, Q2/Q1, dt 60, t_max 1e3 => 17 steps) on the uniform mesh (the adaptive schedule: test_zz_gpu_amr.py)
     text = H.SHIPPED_INPUT + "\nsubsection GPU\n  set Refine every = 0\n  set CG max iterations = 5000\nend\n"
     f = tmp_path / "input.data"
     f.write_text(text)
