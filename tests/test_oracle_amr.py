@@ -612,3 +612,44 @@ def test_oracle_matches_numpy_on_randomly_refined_meshes(dim, deg, seed, rounds)
     R.p = np.full(R.np_, float(inp.p_init))
     assert fss.rel_l2(b.get_vector(capi.VEC_U_RHS)[fu], R.rhs_displacement(R.p)[pu[fu]]) <= 1e-12
     b.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_emulated_condense_kernel_on_random_constraint_tables(emu, seed):
+    """k_condense_matrix / k_condense_vector_gather on inputs that do not come from a mesh: random sparse symmetric matrix, random
+    closed constraint table (up to 9 masters per line, masters shared by many lines), pattern = union of A and E^T A E."""
+    import ctypes as C
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    n = 300
+    B = sp.random(n, n, density=0.03, random_state=int(seed), format="csr")
+    A = (B + B.T + sp.diags(rng.uniform(1, 2, n))).tocsr()
+    cons = rng.choice(n, size=60, replace=False)
+    free = np.setdiff1d(np.arange(n), cons)
+    dof = np.sort(cons).astype(np.int32)
+    ptr, edof, w = [0], [], []
+    for _ in dof:
+        k = int(rng.integers(1, 10))
+        m = np.sort(rng.choice(free[:40], size=k, replace=False))  # few masters -> long transposed lists
+        edof += m.tolist(); w += rng.uniform(-0.5, 1.0, k).tolist(); ptr.append(len(edof))
+    ptr, edof, w = np.array(ptr, np.int32), np.array(edof, np.int32), np.array(w)
+    rows = np.repeat(dof, np.diff(ptr))
+    E = sp.csr_matrix((np.concatenate([w, np.ones(len(free))]), (np.concatenate([rows, free]), np.concatenate([edof, free]))), shape=(n, n))
+    ref = (E.T @ A @ E).tolil()
+    for d in dof:
+        ref[d, d] = 7.5
+    ref = ref.tocsr()
+    P = (abs(A) + abs(ref) + sp.eye(n)).tocsr()
+    P.sort_indices()
+    rowptr, col = P.indptr.astype(np.int32), P.indices.astype(np.int32)
+    src = values_on_pattern(A, rowptr, col)
+    dst = np.full_like(src, np.nan)
+    emu.emu_condense_matrix(n, _ptr(rowptr, C.c_int32), _ptr(col, C.c_int32), _ptr(src, C.c_double), _ptr(dst, C.c_double), len(dof),
+                            _ptr(dof, C.c_int32), _ptr(ptr, C.c_int32), _ptr(edof, C.c_int32), _ptr(w, C.c_double), 0, 7.5)
+    got = sp.csr_matrix((dst, col, rowptr), shape=(n, n))
+    assert abs(got - ref).max() <= 1e-13 * abs(ref).max()
+    v = rng.standard_normal(n)
+    expect = E.T @ v
+    expect[dof] = 0.0
+    emu.emu_condense_vector(n, len(dof), _ptr(dof, C.c_int32), _ptr(ptr, C.c_int32), _ptr(edof, C.c_int32), _ptr(w, C.c_double), _ptr(v, C.c_double))
+    assert np.abs(v - expect).max() <= 1e-13 * np.abs(expect).max()
