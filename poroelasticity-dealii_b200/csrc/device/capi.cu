@@ -118,6 +118,8 @@ int pe_create(pe_ctx** out, int device, int rank, int nranks, const void* nccl_i
     c->pcg_timing.alloc_zero(10, c->stream);
     PE_CUDA(cudaMallocHost((void**)&c->h_state, 2 * sizeof(CgState)));
     PE_CUDA(cudaMallocHost((void**)&c->h_scalars, (PE_RED_SLOTS + 8) * sizeof(double)));
+    PE_CUDA(cudaHostAlloc((void**)&c->h_comm_err, sizeof(int), cudaHostAllocMapped));
+    *c->h_comm_err = 0;
     PE_CUDA(cudaEventCreateWithFlags(&c->ev_poll[0], cudaEventDisableTiming));
     PE_CUDA(cudaEventCreateWithFlags(&c->ev_poll[1], cudaEventDisableTiming));
     PE_CUDA(cudaStreamSynchronize(c->stream));
@@ -151,6 +153,7 @@ void pe_destroy(pe_ctx* c) {
   if (c->comm) ncclCommDestroy(c->comm);
   if (c->h_state) cudaFreeHost(c->h_state);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
+  if (c->h_comm_err) cudaFreeHost(c->h_comm_err);
   for (auto& e : c->ev_poll) if (e) cudaEventDestroy(e);
   for (auto& e : c->prof_ev) if (e) cudaEventDestroy(e);
   cudaStream_t s = c->stream;
@@ -342,6 +345,12 @@ int pe_setup(pe_ctx* c) {
   auto t0 = std::chrono::steady_clock::now();
   cudaStream_t s = c->stream;
   for (Field* F : {&c->fp, &c->fu}) {
+    for (SellMat& S : F->sell) {  // sliced copies belong to the previous mesh
+      S.B = 0;
+      S.src = nullptr;
+      S.panels.release();
+      S.slice_ptr.release();
+    }
     std::vector<int32_t> cl((size_t)F->n_local, -1);
     for (int64_t i = 0; i < F->n_lines; ++i) {
       require(cl[F->h_line_dof[i]] < 0, PE_ERR_BAD_INPUT, "dof constrained twice");
@@ -395,6 +404,7 @@ int pe_setup(pe_ctx* c) {
   }
   const double* m_proj = c->fp.hang.n ? c->Mc.p : c->M.p;
   pe_extract_invdiag(c, c->fp, m_proj, c->invdiag_M.p);
+  pe_build_sell(c, c->fp, 3, m_proj, false);  // the projection solves (SP:201-232) stream this copy
   c->eig_M = 1.1 * pe_estimate_eig_max(c, c->fp, m_proj, c->invdiag_M.p);
   c->jac_dt = -1;
   c->matrix_u_built = false;
@@ -462,6 +472,7 @@ int pe_pressure_assemble_jacobian(pe_ctx* c, double dt) {
     const double* Ks = c->fp.hang.n ? c->Kc.p : c->K.p;
     pe_vec_axpby_vals(c, c->fp.nnz, 1. / c->prm.m_modulus / dt, Ms, c->prm.perm_over_visc, Ks, c->J.p);
     pe_extract_invdiag(c, c->fp, c->J.p, c->invdiag_J.p);
+    pe_build_sell(c, c->fp, 2, c->J.p, false);
     c->eig_J = 1.1 * pe_estimate_eig_max(c, c->fp, c->J.p, c->invdiag_J.p);
     c->st.eig_max_p = c->eig_J;
     c->jac_dt = dt;
@@ -525,10 +536,18 @@ int pe_displacement_assemble(pe_ctx* c) {
         c->st.spmv_bytes_u = (double)S.nnzb * (S.B * S.B * 8.0 + 4.0) + (double)S.n_brows * 4.0 + (double)c->fu.n_owned * 16.0;
         c->st.bsr_block_size = S.B;
         pe_build_bsr_fp32(c, c->fu);
+        // TMA-fed sliced copy (+ its FP32 twin for the passes inside the Chebyshev polynomial unless PE_CHEB_FP32=0)
+        const bool have_sell = pe_build_sell(c, c->fu, 0, c->A.p, false);
+        const char* f32 = std::getenv("PE_CHEB_FP32");
+        if (have_sell && c->prm.preconditioner == PE_PRECOND_CHEBYSHEV && c->prm.chebyshev_degree > 1 && !(f32 && std::string(f32) == "0"))
+          pe_build_sell(c, c->fu, 1, c->A.p, true);
+        else
+          c->fu.sell[1].B = 0;
       } else {
         c->fu.bsr.B = 0;
         c->fu.bsr.bval32.release();
         c->st.bsr_block_size = 0;
+        c->fu.sell[0].B = c->fu.sell[1].B = 0;
       }
     }
     c->eig_A = 1.1 * pe_estimate_eig_max(c, c->fu, c->A.p, c->invdiag_A.p);
@@ -644,7 +663,7 @@ int pe_get_vector(pe_ctx* c, int which, double* host, int64_t n) {
   VecRef v = vec_by_id(c, which);
   require(host && n == v.F->n_owned, PE_ERR_BAD_INPUT, "size must equal the number of owned dofs");
   PE_CUDA(cudaMemcpyAsync(host, v.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  PE_CUDA(cudaStreamSynchronize(c->stream));
+  pe_sync_checked(c);
   PE_LEAVE(c)
 }
 int pe_set_vector(pe_ctx* c, int which, const double* host, int64_t n) {
@@ -712,7 +731,7 @@ int pe_reset_stats(pe_ctx* c) {
 }
 int pe_synchronize(pe_ctx* c) {
   PE_ENTER(c)
-  PE_CUDA(cudaStreamSynchronize(c->stream));
+  pe_sync_checked(c);
   PE_LEAVE(c)
 }
 void* pe_stream(pe_ctx* c) { return c ? (void*)c->stream : nullptr; }

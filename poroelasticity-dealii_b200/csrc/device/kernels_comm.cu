@@ -52,17 +52,21 @@ k_halo_send(int64_t n_send, const int32_t* __restrict__ send_idx, const int32_t*
 
 // Receiver side: returns once every neighbour's halo of this epoch has landed in my ghost segment.
 __global__ void k_halo_wait(const P2PControl* __restrict__ ctl, const int32_t* __restrict__ neigh_rank, int n_neigh, int field, int epoch,
-                            CgState* __restrict__ state) {
+                            CgState* __restrict__ state, int* __restrict__ comm_err) {
   if (state && state->done) return;
   bool ok = true;
   for (int k = threadIdx.x; k < n_neigh; k += blockDim.x) ok = pe_wait_flag(&ctl->halo_flag[field][neigh_rank[k]], epoch) && ok;
   __threadfence_system();
-  if (!ok && state) { state->pad = 1; state->done = -1; }
+  if (!ok) {  // a neighbour never delivered: the ghost values are stale.  Always reported (cold path: through the error word)
+    *comm_err = 1;
+    if (state) { state->pad = 1; state->done = -1; }
+    __threadfence_system();
+  }
 }
 
 // Allreduce(sum) of `count` doubles in place: post to every rank's mailbox, wait for everyone, sum in rank order.
 __global__ void k_allreduce_p2p(double* __restrict__ vals, int count, char* const* __restrict__ peer, int nranks, int me, int epoch,
-                                CgState* __restrict__ state) {
+                                CgState* __restrict__ state, int* __restrict__ comm_err) {
   if (state && state->done) return;
   const int r = threadIdx.x;
   const int par = epoch & 1;
@@ -77,8 +81,13 @@ __global__ void k_allreduce_p2p(double* __restrict__ vals, int count, char* cons
   if (r < nranks) ok = pe_wait_flag(&mine->red_flag[r], epoch);
   ok = __all_sync(0xffffffffu, ok);
   __threadfence_system();
-  if (!ok) {
-    if (r == 0 && state) { state->pad = 1; state->done = -1; }
+  if (!ok) {  // a peer never posted: never leave the rank-local partial behind as if it were the global sum
+    if (r < count) vals[r] = __longlong_as_double(0x7ff8000000000000LL);
+    if (r == 0) {
+      *comm_err = 2;
+      if (state) { state->pad = 1; state->done = -1; }
+      __threadfence_system();
+    }
     return;
   }
   if (r < count) {
@@ -104,11 +113,21 @@ void pe_pack_launch(pe_ctx* c, int64_t n, const int32_t* idx, const double* v, d
   c->st.kernel_launches++;
 }
 
+void pe_sync_checked(pe_ctx* c) {
+  PE_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->h_comm_err && *c->h_comm_err) {
+    const int code = *c->h_comm_err;
+    *c->h_comm_err = 0;
+    throw PeError(PE_ERR_NCCL, code == 1 ? "peer-memory halo exchange timed out (a neighbour rank never delivered its ghost values)"
+                                         : "peer-memory reduction timed out (a rank never posted its partial sum)");
+  }
+}
+
 void pe_allreduce_sum(pe_ctx* c, double* dev, int count, bool in_solve) {
   if (c->nranks <= 1) return;
   if (c->p2p.on && count <= 4) {
     const int epoch = (int)(++c->p2p.red_epoch);
-    k_allreduce_p2p<<<1, 32, 0, c->stream>>>(dev, count, c->p2p.d_peer.p, c->nranks, c->rank, epoch, in_solve ? c->cg_state.p : nullptr);
+    k_allreduce_p2p<<<1, 32, 0, c->stream>>>(dev, count, c->p2p.d_peer.p, c->nranks, c->rank, epoch, in_solve ? c->cg_state.p : nullptr, c->h_comm_err);
     c->st.kernel_launches++;
     return;
   }
@@ -134,7 +153,7 @@ void pe_halo_exchange(pe_ctx* c, Field& F, double* v, bool in_solve, int* fused_
       *fused_epoch = epoch;
       return;
     }
-    k_halo_wait<<<1, 32, 0, c->stream>>>(reinterpret_cast<const P2PControl*>(c->p2p.region), P.neigh_rank.p, H.n_neigh, fi, epoch, in_solve ? c->cg_state.p : nullptr);
+    k_halo_wait<<<1, 32, 0, c->stream>>>(reinterpret_cast<const P2PControl*>(c->p2p.region), P.neigh_rank.p, H.n_neigh, fi, epoch, in_solve ? c->cg_state.p : nullptr, c->h_comm_err);
     c->st.kernel_launches++;
     return;
   }

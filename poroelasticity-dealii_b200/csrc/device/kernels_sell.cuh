@@ -1,0 +1,278 @@
+// kernels_sell.cuh — the TMA-fed matrix stream of the CG kernels (included by kernels_solver.cu).
+//
+// Replaces SparseMatrix<double>::vmult as called by SolverCG at lib/include/PoroElasticPressureSolver.h:176-179,
+// PoroElasticDisplacementSolver.h:300-305 and StrainProjector.h:210-214.
+//
+// Format ("sliced block ELL", built once per matrix by kernels_sell.cu): 32 consecutive block rows form a SLICE; a
+// slice is stored as nb_max PANELS, panel j holding block j of each of the 32 block rows:
+//     int32 col[32] | T val[B*B][32]          (128 + B*B*32*sizeof(T) bytes, always a multiple of 128)
+// so a slice is ONE contiguous, 128-byte aligned byte range.  Rows shorter than the slice maximum are padded with
+// zero blocks that point at the row itself (+1.6 % bytes on the 128^3 Q1 mesh).  8 + 4/B^2 bytes per scalar
+// nonzero, as block CSR.
+//
+// Data movement: every warp owns a ring of NST shared-memory stages.  Lane 0 arms the stage's mbarrier with the
+// byte count and issues ONE cp.async.bulk (the 1-D TMA copy, SASS UBLKCP) for up to SJ panels; the bytes travel
+// DRAM -> L2 -> shared memory without passing through registers or the LSU issue slots, with an evict-first L2
+// policy so the matrix stream does not push the gathered vector out of L2.  The lanes then read "their" column
+// and values with conflict-free LDS (lane = block row), gather x, and accumulate in a fixed order — there is no
+// cross-lane reduction at all, every lane ends up with the B row sums of its block row, so the store and every
+// fused epilogue are coalesced.  Measured reason for this design: with per-lane global loads the FP32 copy of the
+// matrix was exactly as slow as the FP64 one (profiles/README.md, round 2) — the pass was bound by load
+// instructions / bytes in flight per warp, not by DRAM.
+//
+// Work distribution: slices are claimed dynamically (one atomic per 32 block rows, issued a whole stage ring ahead
+// of use) so slow SMs or ranks with uneven halos do not set the pace.  Dot products stay bitwise reproducible:
+// every slice writes its partial sums to a fixed slot; the warp that completes a group of 32 slices adds the
+// group's partials in a fixed order; the kernel's last CTA (or every CTA of the persistent kernel) adds the group
+// totals in a fixed order.  Who computed what never enters the result.
+#pragma once
+
+namespace sell {
+
+constexpr int WARPS = 8;          // per CTA; one CTA per SM (the rings take ~180 KB of shared memory)
+constexpr int THREADS = WARPS * 32;
+constexpr int NST = 3;            // stages per warp
+constexpr int STAGE_BYTES = 7680; // largest stage of any configuration
+constexpr int RING_BYTES = NST * STAGE_BYTES;
+constexpr int SMEM_BYTES = WARPS * RING_BYTES + WARPS * NST * 8 + 64;
+
+template <int B, typename T>
+struct Cfg {
+  static constexpr int PANEL = 128 + B * B * 32 * (int)sizeof(T);
+  static constexpr int SJ = (B == 1) ? 14 : (STAGE_BYTES / PANEL);  // panels per stage: (3,f64) 3, (3,f32) 6, (2,f64) 6, (2,f32) 12
+  static_assert(SJ >= 1 && SJ * PANEL <= STAGE_BYTES, "stage does not fit");
+};
+
+struct Mat {
+  const char* panels;
+  const int32_t* slice_ptr;  // n_slices + 1, in panels
+  int n_slices;
+  int first_boundary_slice;  // slices before this one reference no ghost column
+  int64_t n_brows;
+};
+
+// scratch of the deterministic reductions and of the dynamic distribution (per context)
+struct Work {
+  unsigned* claim;    // next unclaimed slice
+  double* spart;      // [NV][cap] per-slice partial sums
+  unsigned* gcnt;     // [groups] slices of the group that have reported
+  double* gpart;      // [NV][gcap] per-group sums
+  int cap, gcap;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar` (TMA engine; SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ int lds_i32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double lds_val(uint32_t addr, double) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double lds_val(uint32_t addr, float) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return (double)v;
+}
+
+// Per-warp state that survives between calls of stream() inside a persistent kernel: the mbarriers keep flipping.
+struct Ring {
+  uint32_t base;     // shared address of the warp's first stage
+  uint32_t bar;      // shared address of the warp's first mbarrier
+  uint32_t parity;   // bit s = parity the NEXT completion of stage s will have
+};
+
+__device__ __forceinline__ Ring ring_setup(char* smem, int warp, int lane) {
+  Ring r;
+  r.base = smem_addr(smem) + (uint32_t)warp * RING_BYTES;
+  r.bar = smem_addr(smem) + (uint32_t)WARPS * RING_BYTES + (uint32_t)warp * NST * 8;
+  r.parity = 0;
+  if (lane == 0) {
+    for (int s = 0; s < NST; ++s) mbar_init(r.bar + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  return r;
+}
+
+// Streams the slices this warp claims.  `before(slice)` runs once per slice ahead of its first gather (halo wait of
+// boundary slices); `done(slice, acc)` receives the B row sums of block row 32*slice + lane.  x is gathered with plain
+// cached loads.  All control flow is warp-uniform.
+template <int B, typename T, class Before, class Done>
+__device__ __forceinline__ void stream(const Mat& m, const double* __restrict__ x, unsigned* claim, Ring& R, int lane, uint64_t policy,
+                                       Before&& before, Done&& done) {
+  typedef Cfg<B, T> C;
+  int f_slice = -1, f_j = 0, f_np = 0;  // fetch cursor: slice, next panel, panels of the slice
+  int64_t f_base = 0;
+  bool exhausted = false;
+  int d_slice[NST], d_cnt[NST];
+  bool d_first[NST], d_last[NST];
+
+  auto issue = [&](int st) {
+    while (f_j >= f_np && !exhausted) {
+      unsigned s = 0;
+      if (lane == 0) s = atomicAdd(claim, 1u);
+      s = __shfl_sync(0xffffffffu, s, 0);
+      if (s >= (unsigned)m.n_slices) {
+        exhausted = true;
+      } else {
+        f_slice = (int)s;
+        const int p0 = m.slice_ptr[s], p1 = m.slice_ptr[s + 1];
+        f_base = p0;
+        f_np = p1 - p0;
+        f_j = 0;
+      }
+    }
+    if (f_j >= f_np) {
+      d_cnt[st] = 0;
+      return;
+    }
+    const int cnt = min(C::SJ, f_np - f_j);
+    d_slice[st] = f_slice;
+    d_cnt[st] = cnt;
+    d_first[st] = f_j == 0;
+    d_last[st] = f_j + cnt == f_np;
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)cnt * C::PANEL;
+      mbar_expect_tx(R.bar + 8 * st, bytes);
+      bulk_g2s(R.base + (uint32_t)st * STAGE_BYTES, m.panels + (size_t)(f_base + f_j) * C::PANEL, bytes, R.bar + 8 * st, policy);
+    }
+    f_j += cnt;
+  };
+
+#pragma unroll
+  for (int st = 0; st < NST; ++st) issue(st);
+
+  double acc[B];
+  bool more = true;
+  while (more) {
+#pragma unroll
+    for (int st = 0; st < NST; ++st) {
+      if (!more) break;
+      if (d_cnt[st] == 0) {
+        more = false;
+        break;
+      }
+      const int cnt = d_cnt[st];
+      if (d_first[st]) {
+        before(d_slice[st]);
+#pragma unroll
+        for (int r = 0; r < B; ++r) acc[r] = 0.0;
+      }
+      while (!mbar_try_wait(R.bar + 8 * st, (R.parity >> st) & 1u)) {}
+      R.parity ^= 1u << st;
+      const uint32_t sb = R.base + (uint32_t)st * STAGE_BYTES;
+      // columns, then all gathers of the stage (independent loads in flight), then values + FMAs
+      int col[C::SJ];
+#pragma unroll
+      for (int jj = 0; jj < C::SJ; ++jj) col[jj] = jj < cnt ? lds_i32(sb + jj * C::PANEL + lane * 4) : 0;
+      double xv[C::SJ][B];
+#pragma unroll
+      for (int jj = 0; jj < C::SJ; ++jj)
+#pragma unroll
+        for (int cc = 0; cc < B; ++cc) xv[jj][cc] = jj < cnt ? ld_gather(x + (size_t)col[jj] * B + cc) : 0.0;
+#pragma unroll
+      for (int jj = 0; jj < C::SJ; ++jj) {
+        if (jj < cnt) {
+#pragma unroll
+          for (int r = 0; r < B; ++r)
+#pragma unroll
+            for (int cc = 0; cc < B; ++cc)
+              acc[r] += lds_val(sb + jj * C::PANEL + 128 + ((r * B + cc) * 32 + lane) * (int)sizeof(T), T()) * xv[jj][cc];
+        }
+      }
+      __syncwarp();  // every lane has read the stage: lane 0 may re-arm it
+      const bool last = d_last[st];
+      const int slice = d_slice[st];
+      issue(st);
+      if (last) done(slice, acc);
+    }
+  }
+}
+
+// Deterministic sums with dynamic work distribution: called by all lanes after a slice is complete; v holds the
+// lane's contributions.  Slot layout: spart[k*cap + slice], gpart[k*gcap + group].
+template <int NV>
+__device__ __forceinline__ void slice_sums(const Work& w, int n_slices, int slice, double (&v)[NV], int lane) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double t = v[k];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    v[k] = t;
+  }
+  const int g = slice >> 5, g0 = g << 5;
+  unsigned old = 0;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) __stcg(w.spart + (size_t)k * w.cap + slice, v[k]);
+    // release only: a gpu-scope __threadfence() also invalidates the SM's L1 (CCTL.IVALL), which would throw away the
+    // cached x lines once per slice; the acquire side below runs once per 32 slices
+    asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(w.gcnt + g) : "memory");
+  }
+  old = __shfl_sync(0xffffffffu, old, 0);
+  const int gsize = min(32, n_slices - g0);
+  if ((int)old == gsize - 1) {  // this warp completed the group: add its partials in slice order
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double t = lane < gsize ? __ldcg(w.spart + (size_t)k * w.cap + g0 + lane) : 0.0;
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) __stcg(w.gpart + (size_t)k * w.gcap + g, t);
+    }
+    if (lane == 0) w.gcnt[g] = 0u;  // ready for the next pass
+  }
+}
+
+// Fixed-order sum of the group totals by one CTA (all threads call; result valid in thread 0).
+template <int NV>
+__device__ __forceinline__ void sum_groups(const Work& w, int n_groups, double (&tot)[NV], double* s_buf /* NV*32 */) {
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n_groups; i += blockDim.x) t += __ldcg(w.gpart + (size_t)k * w.gcap + i);
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) s_buf[k * 32 + wp] = t;
+  }
+  __syncthreads();
+  if (wp == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double t = lane < nw ? s_buf[k * 32 + lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      tot[k] = t;
+    }
+  }
+}
+
+}  // namespace sell

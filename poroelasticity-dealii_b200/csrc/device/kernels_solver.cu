@@ -51,6 +51,7 @@ __device__ __forceinline__ double red_fetch(const RedIn& r, int slot, bool* ok) 
   if (r.ctl == nullptr) return r.local[slot];
   __shared__ double s_val[PE_RED_SLOTS];
   __shared__ int s_ok;
+  __syncthreads();  // a second fetch in the same kernel must not overwrite s_ok / s_val before every warp has read them
   if (threadIdx.x < 32) {
     bool good = true;
     if ((int)threadIdx.x < r.nranks) good = pe_wait_flag(&r.ctl->red_flag[threadIdx.x], r.epoch);
@@ -258,6 +259,7 @@ struct SpmvArgs {
   const P2PControl* ctl;
   const int32_t* neigh_rank;
   int n_neigh, field, halo_epoch;
+  int* comm_err;          // pinned error word (set on a halo timeout, also outside a solve)
 };
 
 // CSR SpMV with warp-blocked rows.  A warp owns 32 CONSECUTIVE rows: their row pointers arrive with one
@@ -271,7 +273,10 @@ __global__ void __launch_bounds__(SPMV_T) k_spmv(SpmvArgs a) {
   if (a.ctl) {
     bool ok = true;
     if ((int)threadIdx.x < a.n_neigh) ok = pe_wait_flag(&a.ctl->halo_flag[a.field][a.neigh_rank[threadIdx.x]], a.halo_epoch);
-    if (!ok && a.state) { CgState* st = const_cast<CgState*>(a.state); st->pad = 1; st->done = -1; }
+    if (!ok) {
+      *a.comm_err = 1;
+      if (a.state) { CgState* st = const_cast<CgState*>(a.state); st->pad = 1; st->done = -1; }
+    }
     __threadfence_system();
     __syncthreads();
   }
@@ -400,7 +405,10 @@ __global__ void __launch_bounds__(SPMV_T) k_spmv_bsr(SpmvArgs a, BsrArgs m) {
   if (a.ctl) {
     bool ok = true;
     if ((int)threadIdx.x < a.n_neigh) ok = pe_wait_flag(&a.ctl->halo_flag[a.field][a.neigh_rank[threadIdx.x]], a.halo_epoch);
-    if (!ok && a.state) { CgState* st = const_cast<CgState*>(a.state); st->pad = 1; st->done = -1; }
+    if (!ok) {
+      *a.comm_err = 1;
+      if (a.state) { CgState* st = const_cast<CgState*>(a.state); st->pad = 1; st->done = -1; }
+    }
     __threadfence_system();
     __syncthreads();
   }
@@ -429,6 +437,90 @@ __global__ void __launch_bounds__(SPMV_T) k_spmv_bsr(SpmvArgs a, BsrArgs m) {
     }
   }
   if (EPI == EPI_DOT || EPI == EPI_RESID) grid_reduce<1>(acc, a.red, a.slot);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-fed SpMV on the sliced block-ELL copy (kernels_sell.cuh): the default matrix pass of every CG solve.
+#include "kernels_sell.cuh"
+
+template <int B, typename T, int EPI>
+__global__ void __launch_bounds__(sell::THREADS, 1) k_spmv_sell(SpmvArgs a, sell::Mat m, sell::Work w) {
+  extern __shared__ __align__(128) char sell_smem[];
+  __shared__ double s_buf[32];
+  __shared__ bool s_last;
+  if (a.state && a.state->done) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  sell::Ring R = sell::ring_setup(sell_smem, warp, lane);
+  const uint64_t policy = sell::evict_first_policy();
+  bool waited = false;
+  auto before = [&](int slice) {
+    // boundary slices gather ghost values: wait (once per warp) until every neighbour's halo of this epoch has landed
+    if (a.ctl && !waited && slice >= m.first_boundary_slice) {
+      bool ok = true;
+      if (lane < a.n_neigh) ok = pe_wait_flag(&a.ctl->halo_flag[a.field][a.neigh_rank[lane]], a.halo_epoch);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok && lane == 0) {
+        *a.comm_err = 1;
+        if (a.state) { CgState* st = const_cast<CgState*>(a.state); st->pad = 1; st->done = -1; }
+      }
+      __threadfence_system();
+      waited = true;
+    }
+  };
+  auto done = [&](int slice, double (&acc)[B]) {
+    const int64_t brow = (int64_t)slice * 32 + lane;
+    double v[1] = {0.0};
+    if (brow < m.n_brows) {
+#pragma unroll
+      for (int r = 0; r < B; ++r) {
+        const int64_t row = brow * B + r;
+        if (EPI == EPI_PLAIN) a.y[row] = acc[r];
+        if (EPI == EPI_DOT) { a.y[row] = acc[r]; v[0] += acc[r] * a.x[row]; }
+        if (EPI == EPI_RESID) { const double g = acc[r] - a.b[row]; a.y[row] = g; v[0] += g * g; }
+        if (EPI == EPI_CHEB) {
+          const double rn = a.r[row] - acc[r];
+          a.r[row] = rn;
+          const double dn = a.c1 * a.x[row] + a.c2 * a.invdiag[row] * rn;
+          a.d_out[row] = dn;
+          a.z[row] += dn;
+        }
+      }
+    }
+    if (EPI == EPI_DOT || EPI == EPI_RESID) sell::slice_sums<1>(w, m.n_slices, slice, v, lane);
+  };
+  sell::stream<B, T>(m, a.x, w.claim, R, lane, policy, before, done);
+  // the last CTA adds the group totals in a fixed order, publishes, and re-arms the claim counter
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(a.red.counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (EPI == EPI_DOT || EPI == EPI_RESID) {
+    double tot[1];
+    sell::sum_groups<1>(w, (m.n_slices + 31) >> 5, tot, s_buf);
+    if (threadIdx.x == 0) {
+      double y = tot[0];
+      if (a.red.add_from) y += a.red.add_from[0];
+      a.red.out[a.slot] = y;
+      s_buf[0] = y;
+    }
+    if (a.red.peer) {  // fused allreduce: total -> every rank's mailbox, fence, epoch flag (as grid_reduce)
+      __syncthreads();
+      if ((int)threadIdx.x < a.red.nranks) {
+        P2PControl* ctl = reinterpret_cast<P2PControl*>(a.red.peer[threadIdx.x]);
+        ctl->red_val[a.red.epoch & 1][a.red.me][a.slot] = s_buf[0];
+        __threadfence_system();
+        pe_st_flag(&ctl->red_flag[a.red.me], a.red.epoch);
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    *a.red.counter = 0u;
+    *w.claim = 0u;
+  }
 }
 
 // ---- Chebyshev inner pass with the FP32 copy of the block values (opt-in, PE_CHEB_FP32=1) -------------------------------
@@ -525,7 +617,10 @@ __global__ void __launch_bounds__(SPMV_T) k_spmv_bsr_cheb_f32(SpmvArgs a, BsrArg
   if (a.ctl) {
     bool ok = true;
     if ((int)threadIdx.x < a.n_neigh) ok = pe_wait_flag(&a.ctl->halo_flag[a.field][a.neigh_rank[threadIdx.x]], a.halo_epoch);
-    if (!ok && a.state) { CgState* st = const_cast<CgState*>(a.state); st->pad = 1; st->done = -1; }
+    if (!ok) {
+      *a.comm_err = 1;
+      if (a.state) { CgState* st = const_cast<CgState*>(a.state); st->pad = 1; st->done = -1; }
+    }
     __threadfence_system();
     __syncthreads();
   }
@@ -810,6 +905,40 @@ inline int spmv_grid(pe_ctx* c, int64_t n, int lpr) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min<int64_t>(PE_MAX_RED_BLOCKS, (int64_t)c->sm_count * mult)));
 }
 
+template <int B, typename T, int EPI>
+void launch_sell_t(pe_ctx* c, const SpmvArgs& a, const sell::Mat& m, const sell::Work& w) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PE_CUDA(cudaFuncSetAttribute(k_spmv_sell<B, T, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, sell::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = std::max(1, std::min(c->sm_count, (m.n_slices + sell::WARPS - 1) / sell::WARPS));
+  k_spmv_sell<B, T, EPI><<<grid, sell::THREADS, sell::SMEM_BYTES, c->stream>>>(a, m, w);
+}
+
+inline sell::Mat sell_mat(const SellMat& S) { return sell::Mat{S.panels.p, S.slice_ptr.p, S.n_slices, S.first_boundary_slice, S.n_brows}; }
+inline sell::Work sell_work(pe_ctx* c, int parity = 0) {
+  return sell::Work{c->red.claim.p + parity, c->red.spart.p, c->red.gcnt.p, c->red.gpart.p, c->red.cap, c->red.gcap};
+}
+
+template <int EPI>
+void launch_sell(pe_ctx* c, const SellMat& S, const SpmvArgs& a) {
+  const sell::Mat m = sell_mat(S);
+  const sell::Work w = sell_work(c);
+  if (S.f32) {  // only the Chebyshev inner passes read the FP32 copy
+    if constexpr (EPI == EPI_CHEB) {
+      if (S.B == 3) launch_sell_t<3, float, EPI_CHEB>(c, a, m, w);
+      else if (S.B == 2) launch_sell_t<2, float, EPI_CHEB>(c, a, m, w);
+      else launch_sell_t<1, float, EPI_CHEB>(c, a, m, w);
+      return;
+    }
+    throw PeError(PE_ERR_STATE, "FP32 matrix copy outside the preconditioner");
+  }
+  if (S.B == 3) launch_sell_t<3, double, EPI>(c, a, m, w);
+  else if (S.B == 2) launch_sell_t<2, double, EPI>(c, a, m, w);
+  else launch_sell_t<1, double, EPI>(c, a, m, w);
+}
+
 template <int EPI>
 void launch_spmv(pe_ctx* c, Field& F, SpmvArgs& a) {
   a.rowptr = F.rowptr.p;
@@ -819,6 +948,18 @@ void launch_spmv(pe_ctx* c, Field& F, SpmvArgs& a) {
   const int lpr = lanes_per_row(F);
   const int grid = spmv_grid(c, a.n - a.row0, lpr);
   if (c->profiling && !c->prof_hold) pe_prof_begin(c, &F == &c->fu ? 1 : 0);
+  if (a.row0 == 0 && a.n == F.n_owned) {  // TMA-fed sliced block-ELL copy (default for every matrix it could be built for)
+    static const bool cheb32 = std::getenv("PE_CHEB_FP32") == nullptr || std::string(std::getenv("PE_CHEB_FP32")) != "0";
+    const SellMat* S = nullptr;
+    if (EPI == EPI_CHEB && cheb32) S = F.find_sell(a.val, true);
+    if (!S) S = F.find_sell(a.val, false);
+    if (S) {
+      launch_sell<EPI>(c, *S, a);
+      if (c->profiling && !c->prof_hold) pe_prof_end(c);
+      c->st.kernel_launches++;
+      return;
+    }
+  }
   if (F.bsr.B && a.val == c->A.p && a.row0 == 0 && a.n == F.n_owned) {  // the displacement matrix has a block-CSR copy
     BsrArgs m{F.bsr.bptr.p, F.bsr.bcol.p, F.bsr.bval.p, F.bsr.n_brows};
     const int bgrid = spmv_grid(c, F.bsr.n_brows, 32);
@@ -849,9 +990,9 @@ void launch_spmv(pe_ctx* c, Field& F, SpmvArgs& a) {
 
 template <int LPR, int B>
 void launch_pcg_t(pe_ctx* c, PcgArgs& a, int& grid_cache) {
-  if (grid_cache == 0) {
-    int per_sm = 0;
-    PE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<LPR, B>, SPMV_T, 0));
+  {  // the cooperative grid belongs to THIS instantiation (the format / lanes per row of a field can change with the mesh)
+    static int per_sm = 0;
+    if (per_sm == 0) PE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<LPR, B>, SPMV_T, 0));
     grid_cache = std::max(1, std::min(per_sm * c->sm_count, PE_MAX_RED_BLOCKS));
   }
   void* params[] = {&a};
@@ -949,7 +1090,7 @@ double pe_vec_dot(pe_ctx* c, Field& F, const double* a, const double* b) {
   c->st.kernel_launches++;
   pe_allreduce_sum(c, c->red.out.p, 1);
   PE_CUDA(cudaMemcpyAsync(c->h_scalars, c->red.out.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  PE_CUDA(cudaStreamSynchronize(c->stream));
+  pe_sync_checked(c);
   PE_CUDA(cudaGetLastError());
   return c->h_scalars[0];
 }
@@ -993,7 +1134,7 @@ double pe_pressure_residual(pe_ctx* c, double dt) {
   c->st.spmv_launches_p += 2;
   pe_allreduce_sum(c, c->red.out.p, 1);
   PE_CUDA(cudaMemcpyAsync(c->h_scalars, c->red.out.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  PE_CUDA(cudaStreamSynchronize(c->stream));
+  pe_sync_checked(c);
   PE_CUDA(cudaGetLastError());
   return std::sqrt(c->h_scalars[0]);
 }
@@ -1020,7 +1161,7 @@ double pe_estimate_eig_max(pe_ctx* c, Field& F, const double* val, const double*
     c->st.kernel_launches += 3;
     pe_allreduce_sum(c, c->red.out.p, 2);
     PE_CUDA(cudaMemcpyAsync(c->h_scalars, c->red.out.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    PE_CUDA(cudaStreamSynchronize(c->stream));
+    pe_sync_checked(c);
     const double ny = std::sqrt(c->h_scalars[0]), nv = std::sqrt(c->h_scalars[1]);
     lambda = ny / nv;
     k_axpby<<<vec_grid(c, n), VEC_T, 0, c->stream>>>(n, 1.0 / ny, y, 0.0, y, v);  // v = y / ||y||
@@ -1105,6 +1246,7 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
       a.n_neigh = F.halo.n_neigh;
       a.field = fi;
       a.halo_epoch = halo_epoch;
+      a.comm_err = c->h_comm_err;
     }
     launch_spmv<EPI>(c, F, a);
     if (split && c->profiling) {
@@ -1172,6 +1314,7 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
   }
   pe_allreduce_sum(c, red, PE_RED_SLOTS);
   k_cg_init_state<<<1, 1, 0, c->stream>>>(st, red, tol, tol_relative_to_b ? 1 : 0, c->prm.cg_max_iterations);
+  const unsigned red_epoch_start = c->p2p.red_epoch;  // mailbox posts of this solve count from here
   {
     const int e = apply_precond_and_dot(false, consumer(0), 0);
     k_cg_start<<<vg, VEC_T, 0, c->stream>>>(n, st, consumer(e), ghbuf, d, z);
@@ -1247,7 +1390,7 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
     unsigned long long h_timing[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     PE_CUDA(cudaMemcpyAsync(&c->h_state[0], st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
     PE_CUDA(cudaMemcpyAsync(h_timing, c->pcg_timing.p, sizeof h_timing, cudaMemcpyDeviceToHost, c->stream));
-    PE_CUDA(cudaStreamSynchronize(c->stream));
+    pe_sync_checked(c);
     PE_CUDA(cudaGetLastError());
     const CgState last = c->h_state[0];
     const int its = last.it;
@@ -1330,7 +1473,16 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
     PE_CUDA(cudaEventSynchronize(c->ev_poll[inflight.front()]));
     inflight.pop_front();
   }
+  pe_sync_checked(c);
   PE_CUDA(cudaGetLastError());
+  if (fused) {
+    // Kernels enqueued behind the converging iteration returned at `state->done` without posting, but the host counted
+    // an epoch for each of them.  Rewind to the posts that really happened (identical on every rank: all ranks take the
+    // same stopping decision), so the next post has the opposite mailbox parity of the last one and can never
+    // overwrite a value a slower rank has not read yet.
+    const unsigned posts = last.it <= 0 ? 0u : (cheb ? 3u * (unsigned)last.it : 1u + 2u * (unsigned)last.it);
+    c->p2p.red_epoch = red_epoch_start + posts;
+  }
   CgResult out;
   out.its = last.it;
   out.res = last.res;

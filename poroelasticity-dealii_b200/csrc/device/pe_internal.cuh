@@ -88,6 +88,17 @@ struct Halo {
   }
 };
 
+// Sliced block-ELL copy of a matrix for the TMA-fed CG kernels (layout and rationale: kernels_sell.cuh).
+struct SellMat {
+  const double* src = nullptr;  // value array this copy was built from (look-up key together with f32)
+  bool f32 = false;             // values stored as float (read only inside the Chebyshev preconditioner)
+  int B = 0, panel_bytes = 0;
+  int n_slices = 0, first_boundary_slice = 0;
+  int64_t n_brows = 0, n_panels = 0, nnzb = 0;
+  DBuf<int32_t> slice_ptr;      // n_slices + 1 (in panels)
+  DBuf<char> panels;
+};
+
 struct Field {
   int degree = 1, ncomp = 1, ns = 0, nloc = 0;
   int64_t n_owned = 0, n_local = 0;
@@ -136,6 +147,12 @@ struct Field {
     DBuf<float> bval32;    // FP32 copy of bval, read ONLY inside the Chebyshev preconditioner (PE_CHEB_FP32=1): a fixed SPD
                            // polynomial in D^-1 A~, so CG still converges to the FP64 solution at 40 instead of 76 B per block
   } bsr;
+  SellMat sell[4];  // slots: 0 = displacement matrix, 1 = its FP32 copy, 2 = pressure Jacobian, 3 = projection (mass) matrix
+  const SellMat* find_sell(const double* val, bool f32) const {
+    for (const SellMat& m : sell)
+      if (m.B && m.src == val && m.f32 == f32) return &m;
+    return nullptr;
+  }
 };
 
 // device-resident scalar state of one CG solve
@@ -151,7 +168,13 @@ struct Reducer {
   DBuf<double> partials;   // PE_RED_SLOTS * PE_MAX_RED_BLOCKS
   DBuf<unsigned> counter;  // 1
   DBuf<double> out;        // PE_RED_SLOTS (+ scratch)
+  // deterministic sums of the dynamically distributed sliced kernels (kernels_sell.cuh): per-slice and per-group slots
+  DBuf<unsigned> claim;    // 2 (one per parity of the persistent kernel's passes)
+  DBuf<double> spart, gpart;
+  DBuf<unsigned> gcnt;
+  int cap = 0, gcap = 0;   // slices / groups the slot arrays hold
 };
+static constexpr int PE_SELL_NV = 4;  // values a pass can reduce at once
 
 // Peer-memory communication over NVLink (kernels_comm.cu): every rank exports one region
 // [control block | six CG work vectors] with cudaIpc; halo values are stored by the SENDER straight into the
@@ -244,6 +267,11 @@ struct pe_ctx {
   DBuf<CgState> cg_state;
   CgState* h_state = nullptr;  // pinned
   double* h_scalars = nullptr; // pinned, PE_RED_SLOTS
+  // Communication error word in pinned, device-mapped host memory: every bounded wait of the peer-memory protocol
+  // that times out stores a code here (kernels_comm.cu, the fused waits of the SpMV kernels, k_pcg).  The host reads
+  // it after its next stream synchronisation (pe_sync_checked) and fails the call with PE_ERR_NCCL, so a late peer can
+  // never leave rank-local partial sums or stale ghost values behind silently.
+  int* h_comm_err = nullptr;
   cudaEvent_t ev_poll[2] = {nullptr, nullptr};
 
   pe_stats st{};
@@ -263,6 +291,11 @@ void pe_prof_flush(pe_ctx* c);
 void pe_build_pattern(pe_ctx* c, Field& F);
 bool pe_build_bsr(pe_ctx* c, Field& F, const double* csr_val);  // false when the matrix has no block structure
 int64_t pe_exclusive_scan_i32(pe_ctx* c, int32_t* data, int64_t n);  // in place, n+1 entries written (last = total)
+
+// ---- kernels_sell.cu
+// (Re)builds sell slot `slot` of F from the matrix `val` (CSR for scalar fields, the block-CSR copy otherwise); returns false
+// and clears the slot when padding would cost more than PE_SELL_MAX_PAD (default 1.5) times the real blocks.
+bool pe_build_sell(pe_ctx* c, Field& F, int slot, const double* val, bool f32);
 
 // ---- kernels_constraints.cu (hanging-node lines; active only when a field has lines with entries)
 void pe_hanging_upload(pe_ctx* c, Field& F);
@@ -300,6 +333,7 @@ void pe_distribute(pe_ctx* c, Field& F, double* v);  // constrained dofs <- inho
 double pe_linfty(pe_ctx* c, Field& F, const double* v);
 void pe_stress_kernel(pe_ctx* c);
 void pe_allreduce_sum(pe_ctx* c, double* dev, int count, bool in_solve = false);
+void pe_sync_checked(pe_ctx* c);  // cudaStreamSynchronize + the communication error word (throws PE_ERR_NCCL)
 double pe_vec_dot(pe_ctx* c, Field& F, const double* a, const double* b);
 void pe_build_bsr_fp32(pe_ctx* c, Field& F);  // no-op unless PE_CHEB_FP32=1 and the preconditioner is Chebyshev  // global dot product over owned entries
 // ---- kernels_comm.cu

@@ -1,11 +1,8 @@
 """GPU parity of the hanging-node / adaptive path against the CPU oracle.
 
-STATUS: the device kernels of csrc/device/kernels_constraints.cu (and the opt-in FP32 Chebyshev pass of kernels_solver.cu,
-last test below) were written after this round's GPU budget was spent;
-they compile for sm_100a and the algorithm they implement (E^T A E on assembled objects) is verified on the CPU against
-the oracle by tests/test_oracle_amr.py, but they have NOT run on a GPU yet.  The cases are therefore expected to pass
-but marked xfail(strict=False), run last (file name) and each in its own process with a timeout, so that an unverified
-path can neither hide behind nor take down the verified suite.  Remove the marker once a GPU run is green.
+The device kernels of csrc/device/kernels_constraints.cu implement E^T A E on the assembled objects; the same algorithm is
+verified on the CPU by tests/test_oracle_amr.py.  First green on a B200 in the round-1 driver run (GPUTEST_r01: all seven
+cases passed), so the cases are plain (strict) tests now.  Each runs in its own process with a timeout.
 """
 import json
 import subprocess
@@ -15,7 +12,7 @@ import pytest
 
 import helpers as H
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="hanging-node kernels not yet executed on a GPU (round-1 budget spent)")]
+pytestmark = pytest.mark.gpu
 
 
 def run_case(*args, env=None):
