@@ -110,6 +110,12 @@ typedef struct pe_stats {
   int64_t pcg_iterations_p, pcg_iterations_u;/* CG iterations executed inside those launches */
   int64_t bsr_block_size;                    /* block size of the block-CSR copy of the displacement matrix (0 = plain CSR);
                                                 spmv_bytes_u then counts 8 B per value + 4 B per BLOCK column index */
+  /* persistent single-reduction CG kernel on the TMA-fed sliced copies (profiling on; displacement solves only):     */
+  double  inner_ms_u;                        /* time in the passes inside the polynomial preconditioner (incl. their barrier) */
+  int64_t inner_passes_u;                    /* number of those passes                                                  */
+  double  inner_bytes_u;                     /* algorithmic bytes of one such pass (FP32 copy of the values when built)  */
+  double  update_ms_u, reduce_ms_u;          /* vector-update phases; the one allreduce per iteration (incl. its barrier) */
+  int64_t sell_format_u;                     /* 1: the displacement matrix is streamed from its sliced block-ELL copy     */
 } pe_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------- */

@@ -113,6 +113,10 @@ int  peh_constraints_view_get(const peh_constraints*, peh_constraints_view* out)
 /* ---- cell partition of a mesh for one rank (owned + ghost cell layer, local numbering) ---- */
 typedef struct peh_part peh_part;
 peh_part* peh_partition(const peh_mesh*, const peh_dofs* dofs_p, const peh_dofs* dofs_u, int rank, int nranks);
+/* the same part for a structured box with FE_Q(1) for both fields (Morton 2^L grid of FSS:418-435 or a lexicographic
+ * n_x x n_y x n_z box), built from the lattice alone: no global mesh, no global dof maps on the rank.  Identical to
+ * peh_partition() on the global mesh, array by array.                                                              */
+peh_part* peh_partition_structured(int dim, const double* size, const int32_t* cells_per_axis, int morton_order, int rank, int nranks);
 void peh_part_destroy(peh_part*);
 typedef struct peh_part_field_view {
   int64_t n_owned, n_local; int32_t n_neighbors, reserved;

@@ -54,6 +54,8 @@ class PeStats(C.Structure):
         ("spmv_ms_p", C.c_double), ("spmv_ms_u", C.c_double), ("spmv_timed_p", C.c_int64), ("spmv_timed_u", C.c_int64),
         ("pcg_ms_p", C.c_double), ("pcg_ms_u", C.c_double), ("pcg_iterations_p", C.c_int64), ("pcg_iterations_u", C.c_int64),
         ("bsr_block_size", C.c_int64),
+        ("inner_ms_u", C.c_double), ("inner_passes_u", C.c_int64), ("inner_bytes_u", C.c_double), ("update_ms_u", C.c_double),
+        ("reduce_ms_u", C.c_double), ("sell_format_u", C.c_int64),
     ]
 
     def as_dict(self):
@@ -133,7 +135,7 @@ HOST_SYMBOLS = [
     "peh_forest_create", "peh_forest_destroy", "peh_forest_active_mesh", "peh_forest_active_levels", "peh_forest_set_flags",
     "peh_forest_get_flags", "peh_forest_prepare", "peh_forest_execute", "peh_forest_kelly", "peh_forest_mark_fixed_fraction",
     "peh_forest_store", "peh_forest_fetch", "peh_constraints_make", "peh_constraints_destroy", "peh_constraints_view_get",
-    "peh_partition", "peh_part_destroy", "peh_part_view_get", "peh_problem_create", "peh_problem_destroy", "peh_problem_initialize",
+    "peh_partition", "peh_partition_structured", "peh_part_destroy", "peh_part_view_get", "peh_problem_create", "peh_problem_destroy", "peh_problem_initialize",
     "peh_problem_step", "peh_problem_run", "peh_problem_ctx", "peh_problem_mesh", "peh_problem_global_ids",
 ]
 
@@ -264,6 +266,8 @@ def _declare_host_api(lib):
     lib.peh_constraints_view_get.argtypes = [P, C.POINTER(ConstraintsView)]
     lib.peh_partition.argtypes = [P, P, P, C.c_int, C.c_int]
     lib.peh_partition.restype = P
+    lib.peh_partition_structured.argtypes = [C.c_int, f64p, i32p, C.c_int, C.c_int, C.c_int]
+    lib.peh_partition_structured.restype = P
     lib.peh_part_destroy.argtypes = [P]
     lib.peh_part_view_get.argtypes = [P, C.POINTER(PartView)]
     lib.peh_problem_create.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]

@@ -107,7 +107,10 @@ int pe_create(pe_ctx** out, int device, int rank, int nranks, const void* nccl_i
       require(nccl_id && id_bytes == sizeof(ncclUniqueId), PE_ERR_BAD_INPUT, "nranks > 1 needs the 128-byte NCCL unique id of rank 0");
       ncclUniqueId id;
       std::memcpy(&id, nccl_id, sizeof id);
+      const auto tn = std::chrono::steady_clock::now();
       PE_NCCL(ncclCommInitRank(&c->comm, nranks, id, rank));
+      if (std::getenv("PE_SETUP_TIMING"))
+        std::fprintf(stderr, "[pe rank %d] ncclCommInitRank %.1f ms\n", rank, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tn).count());
     }
     c->red.partials.alloc_zero((size_t)PE_RED_SLOTS * PE_MAX_RED_BLOCKS, c->stream);
     c->red.counter.alloc_zero(1, c->stream);
@@ -115,7 +118,7 @@ int pe_create(pe_ctx** out, int device, int rank, int nranks, const void* nccl_i
     c->cg_state.alloc_zero(1, c->stream);
     c->pcg_tickets.alloc_zero(4, c->stream);
     c->pcg_flags.alloc_zero(2, c->stream);
-    c->pcg_timing.alloc_zero(10, c->stream);
+    c->pcg_timing.alloc_zero(PE_PCG_TIMING_WORDS, c->stream);
     PE_CUDA(cudaMallocHost((void**)&c->h_state, 2 * sizeof(CgState)));
     PE_CUDA(cudaMallocHost((void**)&c->h_scalars, (PE_RED_SLOTS + 8) * sizeof(double)));
     PE_CUDA(cudaHostAlloc((void**)&c->h_comm_err, sizeof(int), cudaHostAllocMapped));
@@ -344,6 +347,17 @@ int pe_setup(pe_ctx* c) {
           "hanging-node (adaptive) meshes run on one rank; partitioned runs need uniform meshes");
   auto t0 = std::chrono::steady_clock::now();
   cudaStream_t s = c->stream;
+  // PE_SETUP_TIMING=1: wall time of every phase of pe_setup on stderr (init_s of partitioned runs is mostly this call)
+  static const bool timing = std::getenv("PE_SETUP_TIMING") != nullptr;
+  auto t_last = t0;
+  std::string t_report;
+  auto tick = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(s);
+    const auto now = std::chrono::steady_clock::now();
+    t_report += std::string(" ") + what + " " + std::to_string(std::chrono::duration<double, std::milli>(now - t_last).count()).substr(0, 7) + " ms;";
+    t_last = now;
+  };
   for (Field* F : {&c->fp, &c->fu}) {
     for (SellMat& S : F->sell) {  // sliced copies belong to the previous mesh
       S.B = 0;
@@ -367,8 +381,10 @@ int pe_setup(pe_ctx* c) {
     } else
       pe_build_pattern(c, *F);
   }
+  tick("patterns");
   pe_build_tables(c);
   pe_color_cells(c);
+  tick("tables+colouring");
   const int64_t npl = c->fp.n_local, nul = c->fu.n_local;
   for (DBuf<double>* v : {&c->p, &c->p_old, &c->dp, &c->resid, &c->ev, &c->ev0, &c->frhs, &c->t1}) v->alloc_zero((size_t)npl, s);
   for (DBuf<double>* v : {&c->u, &c->b, &c->b_const}) v->alloc_zero((size_t)nul, s);
@@ -381,7 +397,9 @@ int pe_setup(pe_ctx* c) {
     c->proj_rhs[e].alloc_zero((size_t)npl, s);
     c->stresses[e].alloc_zero((size_t)npl, s);
   }
+  tick("vectors");
   pe_comm_setup(c, (size_t)std::max(npl, nul));
+  tick("comm setup (IPC region, NCCL handshakes)");
   c->M.alloc((size_t)c->fp.nnz);
   c->K.alloc((size_t)c->fp.nnz);
   c->J.alloc_zero((size_t)c->fp.nnz, s);
@@ -390,6 +408,7 @@ int pe_setup(pe_ctx* c) {
   c->invdiag_J.alloc((size_t)c->fp.n_owned);
   c->invdiag_A.alloc((size_t)c->fu.n_owned);
   pe_assemble_pressure_matrices(c);  // PS:96-101 (+ cached well source, PS:142-147)
+  tick("M, K, well rhs");
   if (c->fp.hang.n) {
     // constraints.condense() of PS:168 and SP:105 is linear in the matrix, so it is applied once to M and K;
     // constrained diagonals get the average |diagonal| of the uncondensed matrix (ConstraintMatrix::condense)
@@ -406,6 +425,8 @@ int pe_setup(pe_ctx* c) {
   pe_extract_invdiag(c, c->fp, m_proj, c->invdiag_M.p);
   pe_build_sell(c, c->fp, 3, m_proj, false);  // the projection solves (SP:201-232) stream this copy
   c->eig_M = 1.1 * pe_estimate_eig_max(c, c->fp, m_proj, c->invdiag_M.p);
+  tick("sliced copy + eigenvalue estimate of M");
+  if (timing) std::fprintf(stderr, "[pe rank %d] pe_setup:%s\n", c->rank, t_report.c_str());
   c->jac_dt = -1;
   c->matrix_u_built = false;
   c->proj_matrix_ready = false;
@@ -472,7 +493,14 @@ int pe_pressure_assemble_jacobian(pe_ctx* c, double dt) {
     const double* Ks = c->fp.hang.n ? c->Kc.p : c->K.p;
     pe_vec_axpby_vals(c, c->fp.nnz, 1. / c->prm.m_modulus / dt, Ms, c->prm.perm_over_visc, Ks, c->J.p);
     pe_extract_invdiag(c, c->fp, c->J.p, c->invdiag_J.p);
-    pe_build_sell(c, c->fp, 2, c->J.p, false);
+    const bool have_j = pe_build_sell(c, c->fp, 2, c->J.p, false);
+    {  // FP32 twin for the passes inside the Chebyshev polynomial (as for the displacement matrix)
+      const char* f32 = std::getenv("PE_CHEB_FP32");
+      if (have_j && c->prm.preconditioner == PE_PRECOND_CHEBYSHEV && c->prm.chebyshev_degree > 1 && !(f32 && std::string(f32) == "0"))
+        pe_build_sell(c, c->fp, 4, c->J.p, true);
+      else
+        c->fp.sell[4].B = 0;
+    }
     c->eig_J = 1.1 * pe_estimate_eig_max(c, c->fp, c->J.p, c->invdiag_J.p);
     c->st.eig_max_p = c->eig_J;
     c->jac_dt = dt;
@@ -538,6 +566,7 @@ int pe_displacement_assemble(pe_ctx* c) {
         pe_build_bsr_fp32(c, c->fu);
         // TMA-fed sliced copy (+ its FP32 twin for the passes inside the Chebyshev polynomial unless PE_CHEB_FP32=0)
         const bool have_sell = pe_build_sell(c, c->fu, 0, c->A.p, false);
+        c->st.sell_format_u = have_sell ? 1 : 0;
         const char* f32 = std::getenv("PE_CHEB_FP32");
         if (have_sell && c->prm.preconditioner == PE_PRECOND_CHEBYSHEV && c->prm.chebyshev_degree > 1 && !(f32 && std::string(f32) == "0"))
           pe_build_sell(c, c->fu, 1, c->A.p, true);
@@ -727,6 +756,8 @@ int pe_reset_stats(pe_ctx* c) {
   c->st.spmv_timed_p = c->st.spmv_timed_u = 0;
   c->st.pcg_ms_p = c->st.pcg_ms_u = 0;
   c->st.pcg_iterations_p = c->st.pcg_iterations_u = 0;
+  c->st.inner_ms_u = c->st.update_ms_u = c->st.reduce_ms_u = 0;
+  c->st.inner_passes_u = 0;
   PE_LEAVE(c)
 }
 int pe_synchronize(pe_ctx* c) {

@@ -191,12 +191,12 @@ void pe_comm_setup(pe_ctx* c, size_t n_work) {
     PE_CUDA(cudaMemcpyAsync(&stride, d.p, sizeof stride, cudaMemcpyDeviceToHost, s));
     PE_CUDA(cudaStreamSynchronize(s));
   }
-  M.region_bytes = M.ctrl_bytes + (size_t)6 * stride * sizeof(double);
+  M.region_bytes = M.ctrl_bytes + (size_t)PE_WORK_VECTORS * stride * sizeof(double);
   PE_CUDA(cudaMalloc((void**)&M.region, M.region_bytes));
   PE_CUDA(cudaMemsetAsync(M.region, 0, M.region_bytes, s));
   double* w0 = reinterpret_cast<double*>(M.region + M.ctrl_bytes);
-  pe_ctx::WPtr* ws[6] = {&c->w_g, &c->w_h, &c->w_d, &c->w_z, &c->w_d2, &c->w_r};
-  for (int k = 0; k < 6; ++k) ws[k]->p = w0 + (size_t)k * stride;
+  pe_ctx::WPtr* ws[PE_WORK_VECTORS] = {&c->w_g, &c->w_h, &c->w_d, &c->w_z, &c->w_d2, &c->w_r, &c->w_s, &c->w_c1};
+  for (int k = 0; k < PE_WORK_VECTORS; ++k) ws[k]->p = w0 + (size_t)k * stride;
   M.peer.assign(c->nranks, nullptr);
   M.peer[c->rank] = M.region;
   M.on = false;
@@ -276,6 +276,32 @@ void pe_comm_setup(pe_ctx* c, size_t n_work) {
         P.send_dest.upload(dest, s);
         P.send_nb.upload(nb, s);
         P.neigh_rank.upload(nr, s);
+        // the same entries grouped by source row (counting sort; order inside a row = neighbour order)
+        {
+          const int64_t n_b = F.n_owned - F.n_interior, ns = H.n_send();
+          std::vector<int32_t> h_idx((size_t)ns);
+          PE_CUDA(cudaMemcpyAsync(h_idx.data(), H.send_idx.p, (size_t)ns * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+          PE_CUDA(cudaStreamSynchronize(s));
+          std::vector<int32_t> ptr((size_t)n_b + 1, 0), pdest((size_t)ns), pnb((size_t)ns);
+          bool all_boundary = true;
+          for (int64_t i = 0; i < ns; ++i) {
+            if (h_idx[i] < F.n_interior) { all_boundary = false; break; }
+            ptr[h_idx[i] - F.n_interior + 1]++;
+          }
+          P.push_ok = all_boundary;
+          if (all_boundary) {
+            for (int64_t r = 0; r < n_b; ++r) ptr[r + 1] += ptr[r];
+            std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+            for (int64_t i = 0; i < ns; ++i) {
+              const int32_t at = fill[h_idx[i] - F.n_interior]++;
+              pdest[at] = dest[i];
+              pnb[at] = nb[i];
+            }
+            P.push_ptr.upload(ptr, s);
+            P.push_dest.upload(pdest, s);
+            P.push_nb.upload(pnb, s);
+          }
+        }
       }
       M.red_epoch = 0;
       // nobody may start storing into a region before every rank has zeroed its own

@@ -1,0 +1,351 @@
+// kernels_pcg2.cuh — persistent, single-reduction preconditioned CG on the TMA-fed matrix stream (included inside the
+// anonymous namespace of kernels_solver.cu, after kernels_sell.cuh and kernels_pcg.cuh).
+//
+// The whole loop of dealii::SolverCG (call sites PS:176-179, DS:300-305, SP:210-214) runs in ONE cooperative launch, with
+// the recurrence rearranged after Chronopoulos & Gear so that an iteration needs a single global reduction:
+//     z = P^-1 g;  w = A z;  gamma = g.z, delta = w.z, rho = g.g          (one pass over A, three fused dot products)
+//     beta = gamma/gamma_old;  alpha = gamma / (delta - beta gamma / alpha_old)
+//     d = beta d - z;  s = beta s - w;  x += alpha d;  g += alpha s        (s tracks A d; g = A x - b as in deal.II)
+// In exact arithmetic the iterates are those of the classic recurrence (profiles/single_reduction_cg_prototype.txt: same
+// iteration counts to +-3 % and the same solution to 1e-15 on the assembled matrices).  SolverControl::check sees
+// rho = ||g||^2 of the iterate BEFORE the current pass, so convergence is noticed one pass late: x is already final and the
+// reported iteration count is the number of updates of x, as in deal.II.
+// P^-1 is Jacobi (degree 1) or the Chebyshev polynomial in D^-1 A of kernels_solver.cu, whose inner passes may stream the
+// FP32 copy of the matrix (TI = float) — a fixed SPD operator, so CG converges to the FP64 solution.
+//
+// Phases of an iteration and what separates them (m = polynomial degree):
+//   m-1 inner passes  r -= A~ c;  c' = c1 c + c2 D^-1 r;  z += c'     each ends with a grid barrier
+//   CG pass           w = A z + the three dot products                ends with the ONE allreduce (grid barrier + mailboxes)
+//   update            the four vector recurrences + the first polynomial term of the next iteration, ends with a grid barrier
+// Multi-GPU: whoever produces an entry of the next pass's input vector also stores it into the neighbours' ghost segments
+// (peer memory over NVLink) — the update phase for z / c0, the epilogue of an inner pass for c' — and the CTA that releases
+// the grid barrier publishes the halo epoch.  Receivers wait per WARP, and only the warps that claimed a boundary slice;
+// interior slices never wait.  Slices are claimed dynamically, so ranks and SMs that are late (halo, clocks) do not set the pace,
+// and all sums are formed in a fixed order (kernels_sell.cuh), so every rank takes bitwise the same decisions.
+
+struct Pcg2Args {
+  sell::Mat m64, m32;  // m32.panels == nullptr: the inner passes stream m64
+  sell::Work work;     // work.claim points at TWO counters (pass parity)
+  const double* invdiag;
+  double *x, *g, *d, *s, *w, *z, *r, *c0, *c1;
+  int64_t n, n_interior;
+  CgState* state;
+  int degree;                 // 1 = Jacobi
+  double inv_theta;           // first polynomial term c0 = (1/theta) D^-1 g
+  double k1[8], k2[8];        // coefficients of inner pass j (1-based): c' = k1[j] c + k2[j] D^-1 r
+  unsigned* tickets;          // [1] grid barrier
+  int* bar_flag;
+  int* abort;
+  unsigned long long* timing; // [0] ns in CG passes (CTA 0), [1] CG passes, [2] ns in inner passes, [3] inner passes, [4] ns in updates,
+                              // [5] ns in allreduces, [10] halo exchanges posted, [11] reductions posted
+  char* const* peer;
+  int nranks, me, red_epoch0;
+  int n_neigh, field, halo_epoch0;
+  const int32_t* neigh_rank;
+  const int32_t* push_ptr;    // per boundary row (row - n_interior): its entries in push_dest / push_nb
+  const int32_t* push_dest;   // index in the receiver's vector
+  const int32_t* push_nb;     // neighbour slot
+  size_t ctrl_bytes, off_z, off_c0, off_c1;  // offsets (in doubles) of the exchanged vectors inside every rank's work area
+  int max_iterations;
+};
+
+template <int B, typename TI>
+__global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
+  extern __shared__ __align__(128) char sell_smem[];
+  __shared__ double s_buf[4 * 32];
+  __shared__ double s_tot[4];
+  __shared__ int s_ok;
+  CgState* st = a.state;
+  if (st->done) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsize = (int64_t)gridDim.x * blockDim.x;
+  const int gwarp = (int)blockIdx.x * sell::WARPS + warp, n_warps = (int)gridDim.x * sell::WARPS;
+  sell::Ring R = sell::ring_setup(sell_smem, warp, lane);
+  const uint64_t policy = sell::evict_first_policy();
+  const double tol = st->tol;
+  const int max_it = st->max_it;
+  const P2PControl* my_ctl = reinterpret_cast<const P2PControl*>(a.peer[a.me]);
+  int bar_epoch = pe_ld_flag(a.bar_flag);  // the same value in every CTA: the flag only moves inside barriers
+  int halo_seq = 0;                        // halo exchanges published so far (identical on every rank)
+  int pass = 0;                            // matrix passes so far (parity selects the claim counter)
+  const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long t_acc[4] = {0, 0, 0, 0}, n_cg = 0, n_in = 0, t_last = 0;
+  auto now = [&]() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+  };
+  auto lap = [&](int slot) {
+    if (timer) {
+      const unsigned long long t = now();
+      t_acc[slot] += t - t_last;
+      t_last = t;
+    }
+  };
+
+  // store v into the ghost copies of (boundary) row `row` on the neighbour ranks
+  auto push = [&](int64_t row, double v, size_t off) {
+    const int64_t k = row - a.n_interior;
+    for (int e = a.push_ptr[k]; e < a.push_ptr[k + 1]; ++e) {
+      double* dst = reinterpret_cast<double*>(a.peer[a.neigh_rank[a.push_nb[e]]] + a.ctrl_bytes) + off;
+      dst[a.push_dest[e]] = v;
+    }
+  };
+  // grid barrier; with `publish` the releasing CTA also posts the epoch of the halo exchange that the phase just stored
+  auto barrier = [&](bool publish) {
+    const bool remote = publish && a.n_neigh > 0;
+    if (publish) ++halo_seq;
+    ++bar_epoch;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (remote) __threadfence_system(); else __threadfence();  // release, cumulative over the CTA
+      if (atomicAdd(&a.tickets[1], 1u) == gridDim.x - 1) {
+        a.tickets[1] = 0u;
+        if (remote) {
+          __threadfence_system();
+          for (int q = 0; q < a.n_neigh; ++q)
+            pe_st_flag(&reinterpret_cast<P2PControl*>(a.peer[a.neigh_rank[q]])->halo_flag[a.field][a.me], a.halo_epoch0 + halo_seq);
+        }
+        __threadfence();
+        pe_st_flag(a.bar_flag, bar_epoch);
+      } else {
+        pcg_wait(a.bar_flag, bar_epoch, a.abort);
+      }
+      __threadfence();  // acquire (also drops this SM's stale L1 lines)
+    }
+    __syncthreads();
+  };
+  // first polynomial term from a fresh g_i (Jacobi: the whole preconditioner)
+  auto precond_first = [&](int64_t i, double gi) {
+    if (a.degree <= 1) {
+      const double zi = a.invdiag[i] * gi;
+      a.z[i] = zi;
+      if (a.n_neigh && i >= a.n_interior) push(i, zi, a.off_z);
+    } else {
+      const double ci = a.inv_theta * a.invdiag[i] * gi;
+      a.r[i] = gi;
+      a.c0[i] = ci;
+      a.z[i] = ci;
+      if (a.n_neigh && i >= a.n_interior) push(i, ci, a.off_c0);
+    }
+  };
+  bool waited = false;
+  auto halo_wait = [&](int slice, const sell::Mat& m) {
+    if (a.n_neigh && !waited && slice >= m.first_boundary_slice) {
+      if (lane < a.n_neigh) pcg_wait(&my_ctl->halo_flag[a.field][a.neigh_rank[lane]], a.halo_epoch0 + halo_seq, a.abort);
+      __syncwarp();
+      __threadfence_system();  // acquire; drops stale L1 lines of the ghost segment
+      waited = true;
+    }
+  };
+  auto begin_pass = [&]() {
+    waited = false;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.work.claim[(pass + 1) & 1] = 0u;  // idle since the barrier before last
+  };
+
+  // ---- prologue: z (or c0, r) from the start residual; publish its halo
+  for (int64_t i = gtid; i < a.n; i += gsize) precond_first(i, a.g[i]);
+  barrier(true);
+  if (timer) t_last = now();
+
+  const sell::Mat& m_in = a.m32.panels ? a.m32 : a.m64;
+  const int n_chunks = (a.m64.n_slices + a.m64.chunk - 1) / a.m64.chunk;  // units of the deterministic sums of the CG pass
+  double gamma_old = 1.0, alpha_old = 1.0;
+  bool first = true;
+  const int it0 = st->it;  // read before anyone can write it (writes happen only on exit, behind a grid barrier)
+  for (int k = 1; k <= a.max_iterations + 1; ++k) {
+    // ---- m-1 inner passes of the polynomial preconditioner
+    for (int j = 1; j < a.degree; ++j) {
+      const double* cin = (j & 1) ? a.c0 : a.c1;
+      double* cout = (j & 1) ? a.c1 : a.c0;
+      const size_t off_out = (j & 1) ? a.off_c1 : a.off_c0;
+      const bool last_inner = j == a.degree - 1;
+      const double k1 = a.k1[j], k2 = a.k2[j];
+      double pr[B], pc[B], pi[B], pz[B];
+      begin_pass();
+      auto before = [&](int slice) {
+        halo_wait(slice, m_in);
+        const int64_t brow = (int64_t)slice * 32 + lane;
+        if (brow < m_in.n_brows) {
+#pragma unroll
+          for (int r = 0; r < B; ++r) {  // epilogue operands: in flight while the slice streams
+            const int64_t row = brow * B + r;
+            pr[r] = a.r[row]; pc[r] = cin[row]; pi[r] = a.invdiag[row]; pz[r] = a.z[row];
+          }
+        }
+      };
+      auto done = [&](int slice, double (&acc)[B], int) {
+        const int64_t brow = (int64_t)slice * 32 + lane;
+        if (brow < m_in.n_brows) {
+#pragma unroll
+          for (int r = 0; r < B; ++r) {
+            const int64_t row = brow * B + r;
+            const double rn = pr[r] - acc[r];
+            const double cn = k1 * pc[r] + k2 * pi[r] * rn;
+            const double zn = pz[r] + cn;
+            a.r[row] = rn;
+            cout[row] = cn;
+            a.z[row] = zn;
+            if (a.n_neigh && row >= a.n_interior) {
+              if (last_inner) push(row, zn, a.off_z); else push(row, cn, off_out);
+            }
+          }
+        }
+      };
+      if (a.m32.panels) sell::stream<B, TI>(m_in, cin, a.work.claim + (pass & 1), gwarp, n_warps, R, lane, policy, before, done);
+      else sell::stream<B, double>(m_in, cin, a.work.claim + (pass & 1), gwarp, n_warps, R, lane, policy, before, done);
+      ++pass;
+      barrier(true);
+      if (timer) ++n_in;
+      lap(1);
+    }
+    // ---- CG pass: w = A z, gamma = g.z, delta = w.z, rho = g.g
+    {
+      double pg[B], pz[B];
+      sell::Pending pend{0u, -1};
+      begin_pass();
+      auto before = [&](int slice) {
+        halo_wait(slice, a.m64);
+        const int64_t brow = (int64_t)slice * 32 + lane;
+        if (brow < a.m64.n_brows) {
+#pragma unroll
+          for (int r = 0; r < B; ++r) { pg[r] = a.g[brow * B + r]; pz[r] = a.z[brow * B + r]; }
+        }
+      };
+      double v[3] = {0.0, 0.0, 0.0};  // this lane's contributions to the current chunk's partial sums
+      auto done = [&](int slice, double (&acc)[B], int chunk) {
+        const int64_t brow = (int64_t)slice * 32 + lane;
+        if (brow < a.m64.n_brows) {
+#pragma unroll
+          for (int r = 0; r < B; ++r) {
+            a.w[brow * B + r] = acc[r];
+            v[0] += pg[r] * pz[r];
+            v[1] += acc[r] * pz[r];
+            v[2] += pg[r] * pg[r];
+          }
+        }
+        if (chunk >= 0) {
+          sell::sums_finish<3>(a.work, n_chunks, pend, lane);  // the previous chunk's ticket has long arrived
+          pend = sell::sums_post<3>(a.work, chunk, v, lane);
+          v[0] = v[1] = v[2] = 0.0;
+        }
+      };
+      sell::stream<B, double>(a.m64, a.z, a.work.claim + (pass & 1), gwarp, n_warps, R, lane, policy, before, done);
+      sell::sums_finish<3>(a.work, n_chunks, pend, lane);
+      ++pass;
+    }
+    lap(0);
+    if (timer) ++n_cg;
+    // ---- the one reduction of the iteration: group totals -> (grid barrier) -> every CTA adds them in the same order
+    barrier(false);
+    double tot[3];
+    sell::sum_groups<3>(a.work, (n_chunks + 31) >> 5, tot, s_buf);
+    if (threadIdx.x < 32) {
+      bool good = true;
+      if (a.nranks > 1) {
+        const int e = a.red_epoch0 + k;
+        if (blockIdx.x == 0 && lane < a.nranks) {
+          P2PControl* ctl = reinterpret_cast<P2PControl*>(a.peer[lane]);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) ctl->red_val[e & 1][a.me][q] = tot[q];
+          __threadfence_system();
+          pe_st_flag(&ctl->red_flag[a.me], e);
+        }
+        if (lane < a.nranks) good = pcg_wait(&my_ctl->red_flag[lane], e, a.abort);
+        good = __all_sync(0xffffffffu, good);
+        __threadfence();  // orders the mailbox loads behind the flag loads (both bypass L1)
+        double mail[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) mail[q] = (good && lane < a.nranks) ? pe_ld_mail(&my_ctl->red_val[e & 1][lane][q]) : 0.0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          double sum = 0.0;
+          for (int rk = 0; rk < a.nranks; ++rk) sum += __shfl_sync(0xffffffffu, mail[q], rk);
+          tot[q] = sum;
+        }
+      }
+      if (lane == 0) {
+        s_tot[0] = tot[0]; s_tot[1] = tot[1]; s_tot[2] = tot[2];
+        s_ok = (good && !pe_ld_flag(a.abort)) ? 1 : 0;
+      }
+    }
+    __syncthreads();
+    const double gamma = s_tot[0], delta = s_tot[1], rho = s_tot[2];
+    const bool ok = s_ok != 0;
+    lap(3);
+    // ---- SolverControl::check on the iterate the pass started from (it has seen k-1 updates)
+    const int done_its = it0 + k - 1;
+    const double res = sqrt(rho);
+    const bool converged = ok && res <= tol;
+    const bool failed = !ok || isnan(res) || (!converged && done_its >= max_it);
+    if (converged || failed) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->it = done_its;
+        st->res = res;
+        if (!ok) st->pad = 1;
+        st->done = converged ? 1 : -1;
+        a.timing[11] = (unsigned long long)k;
+      }
+      break;
+    }
+    // ---- update: d, s, x, g and the first polynomial term of the next iteration (stores the next halo)
+    const double beta = first ? 0.0 : gamma / gamma_old;
+    const double alpha = first ? gamma / delta : gamma / (delta - beta * gamma / alpha_old);
+    // four rows per thread and trip: all 28 loads are issued before the first use (one CTA per SM has only 8 warps to
+    // hide DRAM latency with)
+    for (int64_t i0 = gtid; i0 < a.n; i0 += 4 * gsize) {
+      double zi[4], wi[4], di[4], si[4], xi[4], gi[4], vi[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + u * gsize;
+        const bool in = i < a.n;
+        zi[u] = in ? a.z[i] : 0.0;
+        wi[u] = in ? a.w[i] : 0.0;
+        di[u] = (in && !first) ? a.d[i] : 0.0;
+        si[u] = (in && !first) ? a.s[i] : 0.0;
+        xi[u] = in ? a.x[i] : 0.0;
+        gi[u] = in ? a.g[i] : 0.0;
+        vi[u] = in ? a.invdiag[i] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + u * gsize;
+        if (i < a.n) {
+          const double dn = beta * di[u] - zi[u], sn = beta * si[u] - wi[u];
+          const double gn = gi[u] + alpha * sn;
+          a.d[i] = dn;
+          a.s[i] = sn;
+          a.x[i] = xi[u] + alpha * dn;
+          a.g[i] = gn;
+          if (a.degree <= 1) {
+            const double zn = vi[u] * gn;
+            a.z[i] = zn;
+            if (a.n_neigh && i >= a.n_interior) push(i, zn, a.off_z);
+          } else {
+            const double cn = a.inv_theta * vi[u] * gn;
+            a.r[i] = gn;
+            a.c0[i] = cn;
+            a.z[i] = cn;
+            if (a.n_neigh && i >= a.n_interior) push(i, cn, a.off_c0);
+          }
+        }
+      }
+    }
+    gamma_old = gamma;
+    alpha_old = alpha;
+    first = false;
+    barrier(true);
+    lap(2);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.work.claim[0] = 0u;
+    a.work.claim[1] = 0u;
+    a.timing[0] += t_acc[0];
+    a.timing[1] += n_cg;
+    a.timing[2] += t_acc[1];
+    a.timing[3] += n_in;
+    a.timing[4] += t_acc[2];
+    a.timing[5] += t_acc[3];
+    a.timing[10] = (unsigned long long)halo_seq;
+  }
+}

@@ -48,6 +48,7 @@ struct Mat {
   const int32_t* slice_ptr;  // n_slices + 1, in panels
   int n_slices;
   int first_boundary_slice;  // slices before this one reference no ghost column
+  int chunk;                 // slices per claim (~64 KB of panels), 1..16
   int64_t n_brows;
 };
 
@@ -126,32 +127,62 @@ __device__ __forceinline__ Ring ring_setup(char* smem, int warp, int lane) {
 }
 
 // Streams the slices this warp claims.  `before(slice)` runs once per slice ahead of its first gather (halo wait of
-// boundary slices); `done(slice, acc)` receives the B row sums of block row 32*slice + lane.  x is gathered with plain
-// cached loads.  All control flow is warp-uniform.
+// boundary slices, epilogue operand prefetch); `done(slice, acc, chunk)` receives the B row sums of block row 32*slice + lane
+// and, when the slice is the last one of its chunk, the chunk's number (else -1): partial sums are formed per CHUNK.
+// x is gathered with plain cached loads.  All control flow is warp-uniform.
+//
+// Claims: work is handed out in CHUNKS of m.chunk consecutive slices (~64 KB of matrix, so the atomic and the slice-pointer
+// load are paid once per 64 KB whatever the block size).  A warp's first two chunks are static (its global warp index, then
+// + n_warps: no atomic before the first TMA copy), every later one is `2 n_warps + atomicAdd(claim, 1)`.  Both latencies are off the
+// critical path: the atomic for the chunk after next and the slice pointers of the next chunk are always in flight
+// while the current chunk streams.
 template <int B, typename T, class Before, class Done>
-__device__ __forceinline__ void stream(const Mat& m, const double* __restrict__ x, unsigned* claim, Ring& R, int lane, uint64_t policy,
-                                       Before&& before, Done&& done) {
+__device__ __forceinline__ void stream(const Mat& m, const double* __restrict__ x, unsigned* claim, int gwarp, int n_warps, Ring& R, int lane,
+                                       uint64_t policy, Before&& before, Done&& done) {
   typedef Cfg<B, T> C;
+  const int CH = m.chunk, n_chunks = (m.n_slices + CH - 1) / CH;
+  auto load_ptrs = [&](int chunk) {  // lane q holds slice_ptr[first slice of the chunk + q], q <= CH
+    const int s = chunk * CH + lane;
+    return (chunk < n_chunks && lane <= CH) ? m.slice_ptr[min(s, m.n_slices)] : 0;
+  };
+  auto claim_one = [&]() {
+    unsigned v = 0;
+    if (lane == 0) v = atomicAdd(claim, 1u);
+    return v;  // consumed (shuffled) one chunk later
+  };
+  int c_cur = gwarp;            // the first two chunks of a warp are static: nothing to wait for at the start of a pass
+  int sp_cur = load_ptrs(c_cur);
+  int c_next = gwarp + n_warps;
+  int sp_next = load_ptrs(c_next);
+  unsigned a_nn = claim_one();  // chunk ids from here on: 2 n_warps + ticket
+  int q = -1, nq = c_cur < n_chunks ? min(CH, m.n_slices - c_cur * CH) : 0;
+  bool exhausted = c_cur >= n_chunks;
+
   int f_slice = -1, f_j = 0, f_np = 0;  // fetch cursor: slice, next panel, panels of the slice
   int64_t f_base = 0;
-  bool exhausted = false;
-  int d_slice[NST], d_cnt[NST];
-  bool d_first[NST], d_last[NST];
+  int d_slice[NST], d_cnt[NST], d_chunk[NST];
+  bool d_first[NST], d_last[NST], d_cend[NST];
 
   auto issue = [&](int st) {
     while (f_j >= f_np && !exhausted) {
-      unsigned s = 0;
-      if (lane == 0) s = atomicAdd(claim, 1u);
-      s = __shfl_sync(0xffffffffu, s, 0);
-      if (s >= (unsigned)m.n_slices) {
-        exhausted = true;
-      } else {
-        f_slice = (int)s;
-        const int p0 = m.slice_ptr[s], p1 = m.slice_ptr[s + 1];
-        f_base = p0;
-        f_np = p1 - p0;
-        f_j = 0;
+      if (++q >= nq) {  // next chunk
+        c_cur = c_next;
+        sp_cur = sp_next;
+        c_next = 2 * n_warps + (int)__shfl_sync(0xffffffffu, a_nn, 0);
+        sp_next = load_ptrs(c_next);
+        if (c_next < n_chunks) a_nn = claim_one();
+        if (c_cur >= n_chunks) {
+          exhausted = true;
+          break;
+        }
+        q = 0;
+        nq = min(CH, m.n_slices - c_cur * CH);
       }
+      f_slice = c_cur * CH + q;
+      const int p0 = __shfl_sync(0xffffffffu, sp_cur, q), p1 = __shfl_sync(0xffffffffu, sp_cur, q + 1);
+      f_base = p0;
+      f_np = p1 - p0;
+      f_j = 0;
     }
     if (f_j >= f_np) {
       d_cnt[st] = 0;
@@ -162,6 +193,8 @@ __device__ __forceinline__ void stream(const Mat& m, const double* __restrict__ 
     d_cnt[st] = cnt;
     d_first[st] = f_j == 0;
     d_last[st] = f_j + cnt == f_np;
+    d_chunk[st] = c_cur;
+    d_cend[st] = q == nq - 1;  // (with d_last) the chunk ends here: its partial sums are complete
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)cnt * C::PANEL;
       mbar_expect_tx(R.bar + 8 * st, bytes);
@@ -213,34 +246,47 @@ __device__ __forceinline__ void stream(const Mat& m, const double* __restrict__ 
       }
       __syncwarp();  // every lane has read the stage: lane 0 may re-arm it
       const bool last = d_last[st];
-      const int slice = d_slice[st];
+      const int slice = d_slice[st], chunk = d_cend[st] ? d_chunk[st] : -1;
       issue(st);
-      if (last) done(slice, acc);
+      if (last) done(slice, acc, chunk);
     }
   }
 }
 
-// Deterministic sums with dynamic work distribution: called by all lanes after a slice is complete; v holds the
-// lane's contributions.  Slot layout: spart[k*cap + slice], gpart[k*gcap + group].
+// Deterministic sums with dynamic work distribution, in two halves so that the atomic's round trip overlaps the next slice:
+// sums_post() is called by all lanes when a CHUNK is complete (v = the lane's contributions over the chunk's slices, a fixed
+// set processed in a fixed order by one warp) and returns the ticket of the chunk's group (meaningful in lane 0, not yet waited
+// for); sums_finish() is called with it one chunk later (and once after the stream) and, if this warp's chunk completed its
+// group of 32, adds the group's partials in chunk order.  Slot layout: spart[k*cap + chunk], gpart[k*gcap + group].
+struct Pending {
+  unsigned ticket;
+  int slice;  // -1: nothing pending
+};
 template <int NV>
-__device__ __forceinline__ void slice_sums(const Work& w, int n_slices, int slice, double (&v)[NV], int lane) {
+__device__ __forceinline__ Pending sums_post(const Work& w, int slice, double (&v)[NV], int lane) {
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     double t = v[k];
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     v[k] = t;
   }
-  const int g = slice >> 5, g0 = g << 5;
-  unsigned old = 0;
+  Pending p{0u, slice};
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) __stcg(w.spart + (size_t)k * w.cap + slice, v[k]);
     // release only: a gpu-scope __threadfence() also invalidates the SM's L1 (CCTL.IVALL), which would throw away the
-    // cached x lines once per slice; the acquire side below runs once per 32 slices
-    asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(w.gcnt + g) : "memory");
+    // cached x lines once per slice; the acquire side runs once per 32 slices
+    asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(p.ticket) : "l"(w.gcnt + (slice >> 5)) : "memory");
   }
-  old = __shfl_sync(0xffffffffu, old, 0);
+  return p;
+}
+template <int NV>
+__device__ __forceinline__ void sums_finish(const Work& w, int n_slices, Pending& p, int lane) {
+  if (p.slice < 0) return;
+  const int g = p.slice >> 5, g0 = g << 5;
+  const unsigned old = __shfl_sync(0xffffffffu, p.ticket, 0);
   const int gsize = min(32, n_slices - g0);
+  p.slice = -1;
   if ((int)old == gsize - 1) {  // this warp completed the group: add its partials in slice order
     __threadfence();
 #pragma unroll

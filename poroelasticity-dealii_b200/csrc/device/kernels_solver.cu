@@ -453,6 +453,8 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_spmv_sell(SpmvArgs a, sell
   sell::Ring R = sell::ring_setup(sell_smem, warp, lane);
   const uint64_t policy = sell::evict_first_policy();
   bool waited = false;
+  double p0[B], p1[B], p2[B], p3[B];
+  sell::Pending pend{0u, -1};
   auto before = [&](int slice) {
     // boundary slices gather ghost values: wait (once per warp) until every neighbour's halo of this epoch has landed
     if (a.ctl && !waited && slice >= m.first_boundary_slice) {
@@ -466,29 +468,46 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_spmv_sell(SpmvArgs a, sell
       __threadfence_system();
       waited = true;
     }
-  };
-  auto done = [&](int slice, double (&acc)[B]) {
+    // operands of the fused epilogue: requested now, in flight while the slice streams
     const int64_t brow = (int64_t)slice * 32 + lane;
-    double v[1] = {0.0};
+    if (brow < m.n_brows) {
+#pragma unroll
+      for (int r = 0; r < B; ++r) {
+        const int64_t row = brow * B + r;
+        if (EPI == EPI_DOT || EPI == EPI_CHEB) p0[r] = a.x[row];
+        if (EPI == EPI_RESID) p0[r] = a.b[row];
+        if (EPI == EPI_CHEB) { p1[r] = a.r[row]; p2[r] = a.invdiag[row]; p3[r] = a.z[row]; }
+      }
+    }
+  };
+  double v[1] = {0.0};  // this lane's contributions to the current chunk's partial sum
+  const int n_chunks = (m.n_slices + m.chunk - 1) / m.chunk;
+  auto done = [&](int slice, double (&acc)[B], int chunk) {
+    const int64_t brow = (int64_t)slice * 32 + lane;
     if (brow < m.n_brows) {
 #pragma unroll
       for (int r = 0; r < B; ++r) {
         const int64_t row = brow * B + r;
         if (EPI == EPI_PLAIN) a.y[row] = acc[r];
-        if (EPI == EPI_DOT) { a.y[row] = acc[r]; v[0] += acc[r] * a.x[row]; }
-        if (EPI == EPI_RESID) { const double g = acc[r] - a.b[row]; a.y[row] = g; v[0] += g * g; }
+        if (EPI == EPI_DOT) { a.y[row] = acc[r]; v[0] += acc[r] * p0[r]; }
+        if (EPI == EPI_RESID) { const double g = acc[r] - p0[r]; a.y[row] = g; v[0] += g * g; }
         if (EPI == EPI_CHEB) {
-          const double rn = a.r[row] - acc[r];
+          const double rn = p1[r] - acc[r];
           a.r[row] = rn;
-          const double dn = a.c1 * a.x[row] + a.c2 * a.invdiag[row] * rn;
+          const double dn = a.c1 * p0[r] + a.c2 * p2[r] * rn;
           a.d_out[row] = dn;
-          a.z[row] += dn;
+          a.z[row] = p3[r] + dn;
         }
       }
     }
-    if (EPI == EPI_DOT || EPI == EPI_RESID) sell::slice_sums<1>(w, m.n_slices, slice, v, lane);
+    if ((EPI == EPI_DOT || EPI == EPI_RESID) && chunk >= 0) {
+      sell::sums_finish<1>(w, n_chunks, pend, lane);  // the previous chunk's ticket has long arrived
+      pend = sell::sums_post<1>(w, chunk, v, lane);
+      v[0] = 0.0;
+    }
   };
-  sell::stream<B, T>(m, a.x, w.claim, R, lane, policy, before, done);
+  sell::stream<B, T>(m, a.x, w.claim, (int)blockIdx.x * sell::WARPS + warp, (int)gridDim.x * sell::WARPS, R, lane, policy, before, done);
+  if (EPI == EPI_DOT || EPI == EPI_RESID) sell::sums_finish<1>(w, n_chunks, pend, lane);
   // the last CTA adds the group totals in a fixed order, publishes, and re-arms the claim counter
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -500,7 +519,7 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_spmv_sell(SpmvArgs a, sell
   __threadfence();
   if (EPI == EPI_DOT || EPI == EPI_RESID) {
     double tot[1];
-    sell::sum_groups<1>(w, (m.n_slices + 31) >> 5, tot, s_buf);
+    sell::sum_groups<1>(w, (n_chunks + 31) >> 5, tot, s_buf);
     if (threadIdx.x == 0) {
       double y = tot[0];
       if (a.red.add_from) y += a.red.add_from[0];
@@ -916,7 +935,11 @@ void launch_sell_t(pe_ctx* c, const SpmvArgs& a, const sell::Mat& m, const sell:
   k_spmv_sell<B, T, EPI><<<grid, sell::THREADS, sell::SMEM_BYTES, c->stream>>>(a, m, w);
 }
 
-inline sell::Mat sell_mat(const SellMat& S) { return sell::Mat{S.panels.p, S.slice_ptr.p, S.n_slices, S.first_boundary_slice, S.n_brows}; }
+inline sell::Mat sell_mat(const SellMat& S) {
+  const double slice_bytes = (double)S.n_panels * S.panel_bytes / std::max(1, S.n_slices);
+  const int chunk = (int)std::min(16.0, std::max(1.0, std::floor(65536.0 / slice_bytes + 0.5)));
+  return sell::Mat{S.panels.p, S.slice_ptr.p, S.n_slices, S.first_boundary_slice, chunk, S.n_brows};
+}
 inline sell::Work sell_work(pe_ctx* c, int parity = 0) {
   return sell::Work{c->red.claim.p + parity, c->red.spart.p, c->red.gcnt.p, c->red.gpart.p, c->red.cap, c->red.gcap};
 }
@@ -987,6 +1010,22 @@ void launch_spmv(pe_ctx* c, Field& F, SpmvArgs& a) {
 }
 
 #include "kernels_pcg.cuh"
+#include "kernels_pcg2.cuh"
+
+template <int B, typename TI>
+void launch_pcg2_t(pe_ctx* c, Pcg2Args& a) {
+  static int per_sm = -1;
+  if (per_sm < 0) {
+    PE_CUDA(cudaFuncSetAttribute(k_pcg2<B, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, sell::SMEM_BYTES));
+    PE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg2<B, TI>, sell::THREADS, sell::SMEM_BYTES));
+  }
+  if (per_sm < 1) throw PeError(PE_ERR_CUDA, "persistent CG kernel does not fit on an SM");
+  // one CTA per SM; small systems take fewer CTAs (cheaper barriers), every CTA at least eight slices
+  const int grid = std::max(1, std::min(c->sm_count, (a.m64.n_slices + sell::WARPS - 1) / sell::WARPS));
+  void* params[] = {&a};
+  PE_CUDA(cudaLaunchCooperativeKernel((const void*)k_pcg2<B, TI>, dim3(grid), dim3(sell::THREADS), params, sell::SMEM_BYTES, c->stream));
+  c->st.kernel_launches++;
+}
 
 template <int LPR, int B>
 void launch_pcg_t(pe_ctx* c, PcgArgs& a, int& grid_cache) {
@@ -1315,13 +1354,18 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
   pe_allreduce_sum(c, red, PE_RED_SLOTS);
   k_cg_init_state<<<1, 1, 0, c->stream>>>(st, red, tol, tol_relative_to_b ? 1 : 0, c->prm.cg_max_iterations);
   const unsigned red_epoch_start = c->p2p.red_epoch;  // mailbox posts of this solve count from here
-  {
+  const int max_it = c->prm.cg_max_iterations;
+  static const bool pcg_off = std::getenv("PE_PCG") && std::string(std::getenv("PE_PCG")) == "0";
+  static const bool pcg2_off = std::getenv("PE_PCG2") && std::string(std::getenv("PE_PCG2")) == "0";
+  const SellMat* S64 = F.find_sell(val, false);
+  const SellMat* S32 = cheb ? F.find_sell(val, true) : nullptr;
+  const bool use_pcg2 = S64 && !pcg_off && !pcg2_off && (!multi || (fused && c->p2p.f[fi].push_ok)) && (!cheb || kdeg <= 8);
+  if (!use_pcg2) {  // the multi-kernel loop and the first persistent kernel start from z = P^-1 g, d = -z (k_pcg2 has its own prologue)
     const int e = apply_precond_and_dot(false, consumer(0), 0);
     k_cg_start<<<vg, VEC_T, 0, c->stream>>>(n, st, consumer(e), ghbuf, d, z);
     c->st.kernel_launches += 2;
   }
 
-  const int max_it = c->prm.cg_max_iterations;
   // The persistent kernel removes every launch gap and host/NCCL round trip, but its static row assignment cannot
   // balance slow SMs the way CTA scheduling does: measured on B200, it wins when a matrix pass is short
   // (<= ~0.3 ms: 4- and 8-GPU blocks of the 128^3 problem, all pressure solves; 148 vs 161 ms per step at 4 GPUs)
@@ -1329,6 +1373,104 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
   static const bool pcg_disabled = std::getenv("PE_PCG") && std::string(std::getenv("PE_PCG")) == "0";
   static const long long pcg_max_nnz = std::getenv("PE_PCG_MAX_NNZ") ? std::atoll(std::getenv("PE_PCG_MAX_NNZ")) : 150000000LL;
   const bool has_bsr = F.bsr.B && val == c->A.p;
+  // ---- default: the persistent single-reduction CG kernel on the TMA-fed sliced copy (kernels_pcg2.cuh)
+  if (use_pcg2) {
+    P2PField& PF = c->p2p.f[fi];
+    Pcg2Args pa{};
+    pa.m64 = sell_mat(*S64);
+    if (S32) pa.m32 = sell_mat(*S32);
+    pa.work = sell_work(c);
+    pa.invdiag = invdiag;
+    pa.x = x; pa.g = g; pa.d = d; pa.s = c->w_s.p; pa.w = h; pa.z = z; pa.r = r; pa.c0 = d2; pa.c1 = c->w_c1.p;
+    pa.n = n;
+    pa.n_interior = multi ? F.n_interior : n;
+    pa.state = st;
+    pa.degree = cheb ? kdeg : 1;
+    pa.inv_theta = 1.0 / theta;
+    {
+      double rho = 1.0 / sigma;
+      for (int k = 1; k < pa.degree; ++k) {
+        const double rho_new = 1.0 / (2.0 * sigma - rho);
+        pa.k1[k] = rho_new * rho;
+        pa.k2[k] = 2.0 * rho_new / delta;
+        rho = rho_new;
+      }
+    }
+    pa.tickets = c->pcg_tickets.p;
+    pa.bar_flag = c->pcg_flags.p;
+    pa.abort = c->pcg_flags.p + 1;
+    pa.timing = c->pcg_timing.p;
+    pa.peer = c->p2p.d_peer.p;
+    pa.nranks = c->nranks;
+    pa.me = c->rank;
+    pa.red_epoch0 = (int)c->p2p.red_epoch;
+    pa.n_neigh = multi ? F.halo.n_neigh : 0;
+    pa.field = fi;
+    pa.halo_epoch0 = (int)PF.epoch;
+    pa.neigh_rank = PF.neigh_rank.p;
+    pa.push_ptr = PF.push_ptr.p;
+    pa.push_dest = PF.push_dest.p;
+    pa.push_nb = PF.push_nb.p;
+    pa.ctrl_bytes = c->p2p.ctrl_bytes;
+    const double* w0 = reinterpret_cast<const double*>(c->p2p.region + c->p2p.ctrl_bytes);
+    pa.off_z = (size_t)(z - w0);
+    pa.off_c0 = (size_t)(d2 - w0);
+    pa.off_c1 = (size_t)(c->w_c1.p - w0);
+    pa.max_iterations = max_it;
+    PE_CUDA(cudaMemsetAsync(c->pcg_timing.p, 0, PE_PCG_TIMING_WORDS * sizeof(unsigned long long), c->stream));
+    PE_CUDA(cudaMemsetAsync(c->pcg_flags.p + 1, 0, sizeof(int), c->stream));  // abort flag
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profiling) {
+      PE_CUDA(cudaEventCreate(&e0));
+      PE_CUDA(cudaEventCreate(&e1));
+      PE_CUDA(cudaEventRecord(e0, c->stream));
+    }
+    const bool f32 = S32 != nullptr;
+    if (S64->B == 3) { if (f32) launch_pcg2_t<3, float>(c, pa); else launch_pcg2_t<3, double>(c, pa); }
+    else if (S64->B == 2) { if (f32) launch_pcg2_t<2, float>(c, pa); else launch_pcg2_t<2, double>(c, pa); }
+    else { if (f32) launch_pcg2_t<1, float>(c, pa); else launch_pcg2_t<1, double>(c, pa); }
+    if (c->profiling) PE_CUDA(cudaEventRecord(e1, c->stream));
+    unsigned long long h_timing[PE_PCG_TIMING_WORDS] = {0};
+    PE_CUDA(cudaMemcpyAsync(&c->h_state[0], st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    PE_CUDA(cudaMemcpyAsync(h_timing, c->pcg_timing.p, sizeof h_timing, cudaMemcpyDeviceToHost, c->stream));
+    pe_sync_checked(c);
+    PE_CUDA(cudaGetLastError());
+    const CgState last = c->h_state[0];
+    if (last.pad) {  // a wait timed out: barriers, claim counters and group counters may be half-used; start clean next time
+      PE_CUDA(cudaMemsetAsync(c->pcg_tickets.p, 0, 4 * sizeof(unsigned), c->stream));
+      PE_CUDA(cudaMemsetAsync(c->red.claim.p, 0, 2 * sizeof(unsigned), c->stream));
+      PE_CUDA(cudaMemsetAsync(c->red.gcnt.p, 0, (size_t)c->red.gcap * sizeof(unsigned), c->stream));
+      PE_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    c->p2p.red_epoch += (unsigned)h_timing[11];  // identical on every rank
+    if (multi) PF.epoch += (unsigned)h_timing[10];
+    const long long passes_cg = (long long)last.it + (last.done ? 1 : 0), passes_in = passes_cg * (pa.degree - 1);
+    *spmv_counter += passes_cg + passes_in;
+    if (c->profiling) {
+      float ms = 0.f;
+      PE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      (fi ? c->st.pcg_ms_u : c->st.pcg_ms_p) += ms;
+      (fi ? c->st.pcg_iterations_u : c->st.pcg_iterations_p) += last.it;
+      // in-kernel %globaltimer of CTA 0: the FP64 CG passes including the reduction that ends them
+      (fi ? c->st.spmv_ms_u : c->st.spmv_ms_p) += (double)(h_timing[0] + h_timing[5]) * 1e-6;
+      (fi ? c->st.spmv_timed_u : c->st.spmv_timed_p) += (int64_t)h_timing[1];
+      if (fi) {
+        c->st.inner_ms_u += (double)h_timing[2] * 1e-6;
+        c->st.inner_passes_u += (int64_t)h_timing[3];
+        c->st.update_ms_u += (double)h_timing[4] * 1e-6;
+        c->st.reduce_ms_u += (double)h_timing[5] * 1e-6;
+        const SellMat* Sin = S32 ? S32 : S64;
+        c->st.inner_bytes_u = (double)Sin->nnzb * (Sin->B * Sin->B * (Sin->f32 ? 4.0 : 8.0) + 4.0) + (double)Sin->n_slices * 4.0 + (double)n * 56.0;
+      }
+    }
+    CgResult out;
+    out.its = last.it;
+    out.res = last.res;
+    out.status = last.done == 1 ? PE_OK : (last.pad ? PE_ERR_NCCL : (std::isnan(last.res) ? PE_ERR_NAN : PE_ERR_NO_CONVERGENCE));
+    return out;
+  }
   if (!cheb && !pcg_disabled && (!multi || fused) && F.nnz <= pcg_max_nnz) {
     // ---- the whole CG loop in one persistent cooperative launch (kernels_pcg.cuh)
     P2PField& PF = c->p2p.f[fi];

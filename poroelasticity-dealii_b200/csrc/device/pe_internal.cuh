@@ -147,7 +147,7 @@ struct Field {
     DBuf<float> bval32;    // FP32 copy of bval, read ONLY inside the Chebyshev preconditioner (PE_CHEB_FP32=1): a fixed SPD
                            // polynomial in D^-1 A~, so CG still converges to the FP64 solution at 40 instead of 76 B per block
   } bsr;
-  SellMat sell[4];  // slots: 0 = displacement matrix, 1 = its FP32 copy, 2 = pressure Jacobian, 3 = projection (mass) matrix
+  SellMat sell[5];  // slots: 0 = displacement matrix, 1 = its FP32 copy, 2 = pressure Jacobian, 3 = projection (mass) matrix, 4 = FP32 Jacobian
   const SellMat* find_sell(const double* val, bool f32) const {
     for (const SellMat& m : sell)
       if (m.B && m.src == val && m.f32 == f32) return &m;
@@ -182,6 +182,8 @@ static constexpr int PE_SELL_NV = 4;  // values a pass can reduce at once
 // published with a system-scope fence + an epoch flag the receiver polls.  NCCL stays for setup and for
 // the few exchanges outside the CG loop.
 static constexpr int PE_P2P_MAX_RANKS = 16;
+static constexpr int PE_WORK_VECTORS = 8;
+static constexpr int PE_PCG_TIMING_WORDS = 16;
 struct P2PControl {                                   // lives at the start of every rank's region
   int halo_flag[2][PE_P2P_MAX_RANKS];                 // [field][sender rank] = epoch of the last halo it stored here
   int red_flag[PE_P2P_MAX_RANKS];                     // [sender rank] = epoch of its last mailbox post
@@ -191,6 +193,10 @@ struct P2PField {
   DBuf<int32_t> send_dest;   // per send entry: index in the receiver's vector (ghost segment)
   DBuf<int32_t> send_nb;     // per send entry: neighbour slot
   DBuf<int32_t> neigh_rank;  // neighbour ranks (device copy)
+  // the same plan indexed by the SOURCE row (boundary rows only, row - n_interior): the persistent CG kernel lets the
+  // thread that produces an entry store it to the neighbours itself
+  DBuf<int32_t> push_ptr, push_dest, push_nb;
+  bool push_ok = false;      // every sent row is a boundary row (>= n_interior); true for symmetric patterns
   unsigned epoch = 0;        // halo exchanges posted so far
 };
 struct P2P {
@@ -253,7 +259,7 @@ struct pe_ctx {
   int n_stress = 0;
   // CG work vectors sized for the larger field; they live in `comm.region` (IPC-exported when nranks > 1)
   struct WPtr { double* p = nullptr; };
-  WPtr w_g, w_h, w_d, w_z, w_d2, w_r;
+  WPtr w_g, w_h, w_d, w_z, w_d2, w_r, w_s, w_c1;
   P2P p2p;
 
   Reducer red;

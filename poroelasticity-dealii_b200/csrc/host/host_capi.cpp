@@ -329,6 +329,14 @@ peh_part* peh_partition(const peh_mesh* m, const peh_dofs* dp, const peh_dofs* d
   return p;
   PEH_CATCH(nullptr)
 }
+peh_part* peh_partition_structured(int dim, const double* size, const int32_t* cells_per_axis, int morton_order, int rank, int nranks) {
+  PEH_TRY
+  auto* p = new peh_part();
+  int n[3] = {cells_per_axis[0], cells_per_axis[1], dim == 3 ? cells_per_axis[2] : 1};
+  p->p = partition::make_part_structured(dim, size, n, morton_order != 0, rank, nranks);
+  return p;
+  PEH_CATCH(nullptr)
+}
 void peh_part_destroy(peh_part* p) { delete p; }
 int peh_part_view_get(const peh_part* p, peh_part_view* v) {
   fill_mesh_view(p->p.mesh, &v->mesh);

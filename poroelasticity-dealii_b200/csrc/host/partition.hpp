@@ -225,4 +225,177 @@ inline Part make_part(const mesh::Mesh& m, const dofs::DofMap& dp, const dofs::D
   return P;
 }
 
+// ---- structured fast path ------------------------------------------------------------------------------------------------
+// make_part() above needs the GLOBAL mesh and both GLOBAL dof maps on every rank (at 286^2 x 1144 cells: ~6 GB of host
+// memory and tens of seconds per rank, all ranks at once).  For boxes with FE_Q(1) for both fields everything it computes
+// is a function of the lattice, so a rank can build its part from two streaming sweeps over the global CELL ORDER that keep
+// only two small arrays per lattice vertex (its first-touch number and its owner) and store nothing else global:
+//   sweep 1  first-touch vertex numbers in cell order (== dofs::distribute_dofs for FE_Q(1): the pressure dof of a vertex is
+//            that number, its displacement dofs are dim*number + component) and the owner = rank of the numbering cell;
+//   sweep 2  the cells that touch a vertex this rank owns (own cells + one ghost layer), with the set of ranks that also
+//            keep each of them.
+// The result is identical, array by array, to make_part() on the global mesh (tests/test_partition.py).
+inline Part make_part_structured(int dim, const double* size, const int* n_axis, bool morton_order, int rank, int nranks) {
+  if (nranks > 32) throw std::runtime_error("make_part_structured: at most 32 ranks");
+  Part P;
+  const int vpc = 1 << dim;
+  const int nn[3] = {n_axis[0], n_axis[1], dim == 3 ? n_axis[2] : 1};
+  const int nv[3] = {nn[0] + 1, nn[1] + 1, dim == 3 ? nn[2] + 1 : 1};
+  const int64_t n_cells = (int64_t)nn[0] * nn[1] * nn[2], n_lat = (int64_t)nv[0] * nv[1] * nv[2];
+  int level = 0;
+  if (morton_order) {
+    while ((1 << level) < nn[0]) ++level;
+    for (int a = 0; a < dim; ++a)
+      if (nn[a] != (1 << level)) throw std::runtime_error("mesh: Morton order needs 2^L cells on every axis");
+  }
+  auto cell_ijk = [&](int64_t c, int ijk[3]) {
+    if (morton_order) mesh::morton_decode((uint64_t)c, dim, level, ijk);
+    else {
+      ijk[0] = (int)(c % nn[0]);
+      ijk[1] = (int)((c / nn[0]) % nn[1]);
+      ijk[2] = (int)(c / ((int64_t)nn[0] * nn[1]));
+    }
+  };
+  auto lattice = [&](const int ijk[3], int v) {
+    const int i = ijk[0] + (v & 1), j = ijk[1] + ((v >> 1) & 1), k = dim == 3 ? ijk[2] + ((v >> 2) & 1) : 0;
+    return (int64_t)i + (int64_t)nv[0] * (j + (int64_t)nv[1] * k);
+  };
+  std::vector<int64_t> first_cell(nranks + 1);
+  for (int r = 0; r <= nranks; ++r) first_cell[r] = (int64_t)((__int128)n_cells * r / nranks);
+  // sweep 1
+  std::vector<int32_t> vnum((size_t)n_lat, -1);
+  std::vector<int8_t> vowner((size_t)n_lat, -1);
+  {
+    int32_t next = 0;
+    int r = 0;
+    for (int64_t c = 0; c < n_cells; ++c) {
+      while (c >= first_cell[r + 1]) ++r;
+      int ijk[3];
+      cell_ijk(c, ijk);
+      for (int v = 0; v < vpc; ++v) {
+        const int64_t lv = lattice(ijk, v);
+        if (vnum[lv] < 0) {
+          vnum[lv] = next++;
+          vowner[lv] = (int8_t)r;
+        }
+      }
+    }
+  }
+  // sweep 2
+  std::vector<uint32_t> cell_mask;  // ranks that keep each local cell
+  {
+    int r = 0;
+    for (int64_t c = 0; c < n_cells; ++c) {
+      while (c >= first_cell[r + 1]) ++r;
+      int ijk[3];
+      cell_ijk(c, ijk);
+      uint32_t mask = 0;
+      for (int v = 0; v < vpc; ++v) mask |= 1u << vowner[lattice(ijk, v)];
+      if (mask & (1u << rank)) {
+        P.cell_global.push_back(c);
+        cell_mask.push_back(mask);
+        if (r == rank) P.n_owned_cells++;
+      }
+    }
+  }
+  const int64_t nlc = (int64_t)P.cell_global.size();
+  // local sub-mesh: vertices in order of first appearance
+  mesh::Mesh& M = P.mesh;
+  M.dim = dim;
+  M.morton = false;
+  M.cell_vertices.resize((size_t)nlc * vpc);
+  std::vector<int32_t> lat2l((size_t)n_lat, -1);
+  std::vector<int64_t> lverts;  // lattice id of every local mesh vertex
+  for (int64_t lc = 0; lc < nlc; ++lc) {
+    int ijk[3];
+    cell_ijk(P.cell_global[lc], ijk);
+    for (int v = 0; v < vpc; ++v) {
+      const int64_t lv = lattice(ijk, v);
+      if (lat2l[lv] < 0) {
+        lat2l[lv] = (int32_t)lverts.size();
+        lverts.push_back(lv);
+        int idx[3] = {(int)(lv % nv[0]), (int)((lv / nv[0]) % nv[1]), (int)(lv / ((int64_t)nv[0] * nv[1]))};
+        for (int a = 0; a < dim; ++a) M.xyz.push_back(-0.5 * size[a] + size[a] * ((double)idx[a] / (double)nn[a]));
+      }
+      M.cell_vertices[lc * vpc + v] = lat2l[lv];
+    }
+    for (int a = 0; a < dim; ++a) {
+      if (ijk[a] == 0) { M.bface_cell.push_back((int32_t)lc); M.bface_local.push_back((int8_t)(2 * a)); M.bface_id.push_back(2 * a); }
+      if (ijk[a] == nn[a] - 1) { M.bface_cell.push_back((int32_t)lc); M.bface_local.push_back((int8_t)(2 * a + 1)); M.bface_id.push_back(2 * a + 1); }
+    }
+  }
+  // vertex-level plan: [owned interior | owned boundary | ghosts by owner], each ascending in the global number
+  const int64_t nlv = (int64_t)lverts.size();
+  std::vector<uint8_t> boundary((size_t)nlv, 0);
+  for (int64_t lc = 0; lc < nlc; ++lc) {
+    bool has_ghost = false;
+    for (int v = 0; v < vpc; ++v) has_ghost |= vowner[lverts[M.cell_vertices[lc * vpc + v]]] != rank;
+    if (has_ghost)
+      for (int v = 0; v < vpc; ++v) boundary[M.cell_vertices[lc * vpc + v]] = 1;
+  }
+  std::vector<int32_t> owned, ghost;  // local mesh vertex ids
+  for (int64_t l = 0; l < nlv; ++l) (vowner[lverts[l]] == rank ? owned : ghost).push_back((int32_t)l);
+  auto gnum = [&](int32_t l) { return vnum[lverts[l]]; };
+  std::sort(owned.begin(), owned.end(), [&](int32_t a, int32_t b) { return boundary[a] != boundary[b] ? boundary[a] < boundary[b] : gnum(a) < gnum(b); });
+  std::sort(ghost.begin(), ghost.end(), [&](int32_t a, int32_t b) {
+    const int oa = vowner[lverts[a]], ob = vowner[lverts[b]];
+    return oa != ob ? oa < ob : gnum(a) < gnum(b);
+  });
+  std::vector<int32_t> pos((size_t)nlv);  // local mesh vertex -> position in the plan
+  for (size_t i = 0; i < owned.size(); ++i) pos[owned[i]] = (int32_t)i;
+  for (size_t i = 0; i < ghost.size(); ++i) pos[ghost[i]] = (int32_t)(owned.size() + i);
+  // send sets per neighbour (owned vertices of local cells another rank keeps too), receive counts per owner
+  std::vector<std::vector<int32_t>> send_sets(nranks);
+  for (int64_t lc = 0; lc < nlc; ++lc) {
+    const uint32_t others = cell_mask[lc] & ~(1u << rank);
+    if (!others) continue;
+    for (int v = 0; v < vpc; ++v) {
+      const int32_t l = M.cell_vertices[lc * vpc + v];
+      if (vowner[lverts[l]] != rank) continue;
+      for (int r = 0; r < nranks; ++r)
+        if (others & (1u << r)) send_sets[r].push_back(l);
+    }
+  }
+  std::vector<int64_t> recv_count(nranks, 0);
+  for (int32_t l : ghost) recv_count[vowner[lverts[l]]]++;
+  for (int f = 0; f < 2; ++f) {
+    FieldPart& F = P.field[f];
+    const int nc = f == 0 ? 1 : dim;
+    F.n_owned = (int64_t)owned.size() * nc;
+    F.n_local = (int64_t)nlv * nc;
+    F.local_to_global.resize((size_t)F.n_local);
+    for (size_t i = 0; i < owned.size(); ++i)
+      for (int c = 0; c < nc; ++c) F.local_to_global[i * nc + c] = (int64_t)gnum(owned[i]) * nc + c;
+    for (size_t i = 0; i < ghost.size(); ++i)
+      for (int c = 0; c < nc; ++c) F.local_to_global[(owned.size() + i) * nc + c] = (int64_t)gnum(ghost[i]) * nc + c;
+    F.cell_dofs.resize((size_t)nlc * vpc * nc);
+    for (int64_t lc = 0; lc < nlc; ++lc)
+      for (int v = 0; v < vpc; ++v)
+        for (int c = 0; c < nc; ++c) F.cell_dofs[(lc * vpc + v) * nc + c] = pos[M.cell_vertices[lc * vpc + v]] * nc + c;
+    F.neighbor_rank.clear();
+    F.send_ptr.assign(1, 0);
+    F.recv_ptr.assign(1, 0);
+    F.send_idx.clear();
+    for (int r = 0; r < nranks; ++r) {
+      if (r == rank || (send_sets[r].empty() && recv_count[r] == 0)) continue;
+      F.neighbor_rank.push_back(r);
+      std::vector<int32_t> s = send_sets[r];
+      std::sort(s.begin(), s.end(), [&](int32_t a, int32_t b) { return gnum(a) < gnum(b); });
+      s.erase(std::unique(s.begin(), s.end()), s.end());
+      for (int32_t l : s)
+        for (int c = 0; c < nc; ++c) F.send_idx.push_back(pos[l] * nc + c);
+      F.send_ptr.push_back((int64_t)F.send_idx.size());
+      F.recv_ptr.push_back(F.recv_ptr.back() + recv_count[r] * nc);
+    }
+  }
+  return P;
+}
+
+// global dof counts of the FE_Q(1) box (the structured path never builds the global maps)
+inline int64_t structured_vertex_count(int dim, const int* n_axis) {
+  int64_t n = 1;
+  for (int a = 0; a < dim; ++a) n *= n_axis[a] + 1;
+  return n;
+}
+
 }  // namespace partition

@@ -85,8 +85,63 @@ class PoroElasticProblem {
     if (rc != 0) throw std::runtime_error(std::string(what) + ": " + pe_last_error(ctx) + " (status " + std::to_string(rc) + ")");
   }
 
+  // Partitioned runs on structured FE_Q(1) boxes build only this rank's part (partition.hpp::make_part_structured): no
+  // global mesh, no global dof maps.  PE_STRUCTURED_PART=0 forces the general path.
+  bool structured_fast_path() const {
+    const char* e = std::getenv("PE_STRUCTURED_PART");
+    return nranks > 1 && nranks <= 32 && data.refine_every == 0 && !data.mesh_from_file && data.displacement_degree == 1 &&
+           !partition::balanced_ownership_requested() && !(e && e[0] == '0');
+  }
+  void setup_dofs_structured() {
+    int n[3] = {1, 1, 1};
+    const bool morton = data.cells_per_axis[0] <= 0;
+    for (int a = 0; a < dim; ++a) n[a] = morton ? (1 << data.initial_refinement_level) : data.cells_per_axis[a];
+    part = partition::make_part_structured(dim, data.domain_size.data(), n, morton, rank, nranks);
+    n_global_p = partition::structured_vertex_count(dim, n);
+    n_global_u = n_global_p * dim;
+    pe_params prm = params_from_input(data);
+    check(pe_set_params(ctx, &prm), "pe_set_params");
+    const mesh::Mesh* lm = &part.mesh;
+    // Dirichlet lines (DS:117-135) straight on the local sub-mesh: a local dof on the domain boundary always lies on a
+    // boundary face of a LOCAL cell of a box mesh, so this equals the global table restricted to the local dofs
+    dofs::DofMap du_local;
+    du_local.degree = 1;
+    du_local.n_comp = dim;
+    du_local.n_loc = (1 << dim) * dim;
+    du_local.n_dofs = part.field[1].n_local;
+    du_local.cell_dofs = part.field[1].cell_dofs;
+    dofs::Constraints cons = dofs::make_dirichlet(*lm, du_local, data.displacement_boundary_labels, data.displacement_boundary_components,
+                                                  data.displacement_boundary_values);
+    std::vector<std::pair<int32_t, double>> ll;
+    for (size_t i = 0; i < cons.line_dof.size(); ++i) ll.push_back({cons.line_dof[i], cons.inhomogeneity[i]});
+    std::sort(ll.begin(), ll.end());
+    std::vector<int32_t> line_dof;
+    std::vector<double> line_g;
+    for (auto& e : ll) { line_dof.push_back(e.first); line_g.push_back(e.second); }
+    std::vector<int64_t> entry_ptr(line_dof.size() + 1, 0);
+    for (int f = 0; f < 2; ++f)
+      global_ids[f] = std::vector<int64_t>(part.field[f].local_to_global.begin(), part.field[f].local_to_global.begin() + part.field[f].n_owned);
+    check(pe_upload_mesh(ctx, dim, lm->n_vertices(), lm->xyz.data(), lm->n_cells(), lm->cell_vertices.data(), lm->n_bfaces(),
+                         lm->bface_cell.data(), lm->bface_local.data(), lm->bface_id.data()), "pe_upload_mesh");
+    check(pe_upload_dofs(ctx, PE_FIELD_PRESSURE, part.field[0].n_local, part.field[0].cell_dofs.data()), "pe_upload_dofs(p)");
+    check(pe_upload_dofs(ctx, PE_FIELD_DISPLACEMENT, part.field[1].n_local, part.field[1].cell_dofs.data()), "pe_upload_dofs(u)");
+    check(pe_upload_constraints(ctx, PE_FIELD_DISPLACEMENT, (int64_t)line_dof.size(), line_dof.data(), entry_ptr.data(), nullptr, nullptr,
+                                line_g.data()), "pe_upload_constraints(u)");
+    std::vector<int32_t> nl(data.stress_boundary_labels.begin(), data.stress_boundary_labels.end()),
+        ncmp(data.stress_boundary_components.begin(), data.stress_boundary_components.end());
+    check(pe_upload_neumann(ctx, (int)nl.size(), nl.data(), ncmp.data(), data.stress_boundary_values.data()), "pe_upload_neumann");
+    for (int f = 0; f < 2; ++f) {
+      auto& F = part.field[f];
+      check(pe_upload_partition(ctx, f, F.n_owned, (int)F.neighbor_rank.size(), F.neighbor_rank.data(), F.send_ptr.data(), F.send_idx.data(),
+                                F.recv_ptr.data()), "pe_upload_partition");
+    }
+    local_mesh = lm;
+    check(pe_setup(ctx), "pe_setup");
+  }
+
   // setup_dofs() (FSS:131-151) on the current mesh + upload + pe_setup
   void setup_dofs() {
+    if (structured_fast_path()) { setup_dofs_structured(); return; }
     const bool adaptive = data.refine_every != 0;
     // distribute_dofs for both handlers (PS:73, DS:110)
     dofs::NodeMaps maps_p, maps_u;
@@ -179,7 +234,9 @@ class PoroElasticProblem {
     if (data.refine_every != 0 && nranks != 1)
       throw std::runtime_error("adaptive refinement (FSS:333-340) runs on one rank: set 'Refine every = 0' for partitioned runs");
     // create_mesh() / read_mesh()
-    if (data.mesh_from_file) {
+    if (structured_fast_path()) {
+      // nothing global is built: setup_dofs_structured() derives this rank's part from the lattice
+    } else if (data.mesh_from_file) {
       global_mesh = mesh::read_msh(data.mesh_file, dim);
       // partitioned runs on unstructured meshes: contiguous cell ranges of a space-filling-curve order are compact
       // subdomains (every rank computes the same order); single-rank runs keep the file order of GridIn::read_msh

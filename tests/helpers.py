@@ -22,8 +22,8 @@ def load_oracle():
     global _oracle
     if _oracle is None:
         path = ROOT / "oracle" / "liboracle.so"
-        if not path.exists():
-            subprocess.check_call(["make", "-C", str(ROOT / "oracle")])
+        # no-op when up to date; rebuilds (-march=native) when the library was compiled on another host CPU (oracle/Makefile)
+        subprocess.check_call(["make", "-s", "-C", str(ROOT / "oracle")], stdout=subprocess.DEVNULL)
         lib = C.CDLL(str(path))
         capi._declare_operator_api(lib, "po_")
         lib.po_create.argtypes = [C.POINTER(C.c_void_p)]

@@ -249,7 +249,8 @@ def test_large_mesh_properties():
         assert rep["fss_iterations"] == 1
         hist = np.array(rep["residual_history"])
         ratio = hist[2:] / hist[1:-1]
-        assert np.all(ratio < 0.39) and np.all(ratio > 0.05)          # T7: contraction alpha^2 M_b/K_b = 0.38756
+        assert np.all(ratio < 0.39)                                   # T7: contraction alpha^2 M_b/K_b = 0.38756 ...
+        assert np.all(np.abs(ratio[-2:] - 0.38756) <= 0.02 * 0.38756), ratio  # ... reached asymptotically (the first ratio is a transient)
         # the converged displacement satisfies the assembled system to the CG tolerance
         u, b = dev.get_vector(capi.VEC_U), dev.get_vector(capi.VEC_U_RHS)
         free = np.ones(u.size, bool)

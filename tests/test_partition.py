@@ -217,3 +217,56 @@ def test_halo_plan_with_two_gloo_ranks(balanced, monkeypatch):
         assert p.exitcode == 0
     for r in res:
         assert all(r[1:]), r
+
+
+class StructuredPart(Part):
+    """peh_partition_structured: the same view, built from the lattice alone"""
+
+    def __init__(self, dim, size, cells, morton, rank, nranks):
+        lib = capi.load_host()
+        s = np.asarray(size, dtype=np.float64)
+        n = np.asarray(list(cells) + [1] * (3 - len(cells)), dtype=np.int32)
+        self.h = lib.peh_partition_structured(dim, capi._p(s, C.c_double), capi._p(n, C.c_int32), int(morton), rank, nranks)
+        assert self.h, lib.peh_last_error()
+        v = capi.PartView()
+        lib.peh_part_view_get(self.h, C.byref(v))
+        self.mesh = capi.Mesh(v.mesh)
+        self.cell_global = capi._np(v.cell_global, self.mesh.n_cells, np.int64)
+        self.n_owned_cells = v.n_owned_cells
+        self.field = []
+        for f, n_loc in ((0, 1 << dim), (1, (1 << dim) * dim)):
+            F = v.field[f]
+            nn = F.n_neighbors
+            send_ptr = capi._np(F.send_ptr, nn + 1, np.int64)
+            self.field.append(dict(
+                n_owned=F.n_owned, n_local=F.n_local,
+                cell_dofs=capi._np(F.cell_dofs, self.mesh.n_cells * n_loc, np.int32).reshape(-1, n_loc),
+                l2g=capi._np(F.local_to_global, F.n_local, np.int64),
+                neigh=capi._np(F.neighbor_rank, nn, np.int32), send_ptr=send_ptr,
+                send_idx=capi._np(F.send_idx, int(send_ptr[-1]) if nn else 0, np.int32),
+                recv_ptr=capi._np(F.recv_ptr, nn + 1, np.int64)))
+
+
+@pytest.mark.parametrize("dim,cells,morton", [(3, [4, 4, 4], True), (3, [8, 8, 8], True), (3, [5, 3, 4], False), (3, [7, 5, 6], False),
+                                              (2, [8, 8], True), (2, [6, 4], False), (3, [3, 3, 12], False)])
+@pytest.mark.parametrize("nranks", [2, 3, 4, 8])
+def test_structured_part_equals_the_general_partition(dim, cells, morton, nranks):
+    """The per-rank structured builder (no global mesh / dof maps on the rank) reproduces make_part() array by array: local
+    sub-mesh, cell lists, local numbering [owned interior | owned boundary | ghosts by owner], global ids, send / receive plans."""
+    size = [10.0, 7.0, 13.0][:dim]
+    if morton:
+        level = int(np.log2(cells[0]))
+        m = capi.mesh_rectangle(dim, size, level)
+    else:
+        m = capi.mesh_subdivided(dim, size, cells)
+    dp, du = capi.HostDofs(m, 1, 1), capi.HostDofs(m, 1, dim)
+    for rank in range(nranks):
+        A = Part(m, dp, du, rank, nranks)
+        B = StructuredPart(dim, size, cells, morton, rank, nranks)
+        assert A.n_owned_cells == B.n_owned_cells
+        assert np.array_equal(A.cell_global, B.cell_global)
+        for name in ("xyz", "cell_vertices", "bface_cell", "bface_local", "bface_id"):
+            assert np.array_equal(getattr(A.mesh, name), getattr(B.mesh, name)), name
+        for f in range(2):
+            for k in A.field[f]:
+                assert np.array_equal(np.asarray(A.field[f][k]), np.asarray(B.field[f][k])), (f, k, rank)
