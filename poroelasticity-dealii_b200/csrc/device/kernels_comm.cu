@@ -157,6 +157,16 @@ void pe_halo_exchange(pe_ctx* c, Field& F, double* v, bool in_solve, int* fused_
     c->st.kernel_launches++;
     return;
   }
+  if (c->p2p.on && !in_solve) {
+    // Vectors outside the exported work area (p, t1, u, an initial guess): staged through one of TWO exported buffers.  A fast
+    // neighbour's next exchange lands in the other buffer, and the one after that needs this rank's next send, which sits
+    // behind this copy-back on the stream — so nothing is overwritten before it has been read.  No NCCL in the time loop.
+    double* w = (c->p2p.stage_epoch++ & 1u) ? c->w_x1.p : c->w_x0.p;
+    PE_CUDA(cudaMemcpyAsync(w, v, (size_t)F.n_owned * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    pe_halo_exchange(c, F, w, false, nullptr);
+    PE_CUDA(cudaMemcpyAsync(v + F.n_owned, w + F.n_owned, (size_t)(F.n_local - F.n_owned) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return;
+  }
   pe_pack_launch(c, ns, H.send_idx.p, v, H.send_buf.p);
   PE_NCCL(ncclGroupStart());
   for (int k = 0; k < H.n_neigh; ++k) {
@@ -177,140 +187,140 @@ void pe_comm_release(pe_ctx* c) {
   M.on = false;
 }
 
+// What every rank tells every other rank at setup, exchanged with ONE kind of NCCL collective (ncclAllGather of a
+// fixed-size record).  NCCL connects lazily per collective algorithm and per peer-to-peer channel, seconds each at 8 ranks;
+// the earlier sequence (allreduce, allgather, grouped send/recv per field, allreduce) paid that three times inside pe_setup.
+struct SetupRecord {
+  long long stride;                        // work-vector length this rank needs
+  cudaIpcMemHandle_t handle;               // its region
+  int ok;                                  // could export / open so far
+  long long land[2][PE_P2P_MAX_RANKS];     // [field][sender rank]: where that rank's halo values start in MY vectors (-1: not a neighbour)
+};
+
+static std::vector<SetupRecord> gather_records(pe_ctx* c, const SetupRecord& mine) {
+  cudaStream_t s = c->stream;
+  DBuf<char> all;
+  all.alloc((size_t)c->nranks * sizeof(SetupRecord));
+  PE_CUDA(cudaMemcpyAsync(all.p + (size_t)c->rank * sizeof(SetupRecord), &mine, sizeof(SetupRecord), cudaMemcpyHostToDevice, s));
+  PE_NCCL(ncclAllGather(all.p + (size_t)c->rank * sizeof(SetupRecord), all.p, sizeof(SetupRecord), ncclChar, c->comm_nccl(), s));
+  std::vector<SetupRecord> out((size_t)c->nranks);
+  PE_CUDA(cudaMemcpyAsync(out.data(), all.p, all.n, cudaMemcpyDeviceToHost, s));
+  PE_CUDA(cudaStreamSynchronize(s));
+  return out;
+}
+
 void pe_comm_setup(pe_ctx* c, size_t n_work) {
   pe_comm_release(c);
   P2P& M = c->p2p;
   cudaStream_t s = c->stream;
   M.ctrl_bytes = (sizeof(P2PControl) + 255) / 256 * 256;
+  const char* env = std::getenv("PE_COMM");
+  const bool want = c->nranks > 1 && !(env && std::strcmp(env, "nccl") == 0) && c->nranks <= PE_P2P_MAX_RANKS;
   // every rank must use the same vector stride so that offsets mean the same thing in every region
   long long stride = (long long)((n_work + 31) / 32 * 32);
+  SetupRecord mine;
+  std::memset(&mine, 0, sizeof mine);
+  std::vector<SetupRecord> all;
   if (c->nranks > 1) {
-    DBuf<long long> d;
-    d.upload(&stride, 1, s);
-    PE_NCCL(ncclAllReduce(d.p, d.p, 1, ncclInt64, ncclMax, c->comm_nccl(), s));
-    PE_CUDA(cudaMemcpyAsync(&stride, d.p, sizeof stride, cudaMemcpyDeviceToHost, s));
-    PE_CUDA(cudaStreamSynchronize(s));
+    mine.stride = stride;
+    mine.ok = 1;
+    for (int fi = 0; fi < 2; ++fi) {
+      Field& F = fi ? c->fu : c->fp;
+      for (int r = 0; r < PE_P2P_MAX_RANKS; ++r) mine.land[fi][r] = -1;
+      if (c->nranks <= PE_P2P_MAX_RANKS)
+        for (int k = 0; k < F.halo.n_neigh; ++k) mine.land[fi][F.halo.rank[k]] = (long long)F.n_owned + F.halo.recv_ptr[k];
+    }
+    all = gather_records(c, mine);  // round 1: strides (the region cannot be allocated before the common stride is known)
+    for (const SetupRecord& r : all) stride = std::max(stride, r.stride);
   }
   M.region_bytes = M.ctrl_bytes + (size_t)PE_WORK_VECTORS * stride * sizeof(double);
   PE_CUDA(cudaMalloc((void**)&M.region, M.region_bytes));
   PE_CUDA(cudaMemsetAsync(M.region, 0, M.region_bytes, s));
   double* w0 = reinterpret_cast<double*>(M.region + M.ctrl_bytes);
-  pe_ctx::WPtr* ws[PE_WORK_VECTORS] = {&c->w_g, &c->w_h, &c->w_d, &c->w_z, &c->w_d2, &c->w_r, &c->w_s, &c->w_c1};
+  pe_ctx::WPtr* ws[PE_WORK_VECTORS] = {&c->w_g, &c->w_h, &c->w_d, &c->w_z, &c->w_d2, &c->w_r, &c->w_s, &c->w_c1, &c->w_x0, &c->w_x1};
   for (int k = 0; k < PE_WORK_VECTORS; ++k) ws[k]->p = w0 + (size_t)k * stride;
   M.peer.assign(c->nranks, nullptr);
   M.peer[c->rank] = M.region;
   M.on = false;
-  M.d_peer.upload(M.peer, s);  // one rank: the persistent CG kernel posts to its own mailbox
-  if (c->nranks > 1) {
-    const char* env = std::getenv("PE_COMM");
-    const bool want = !(env && std::strcmp(env, "nccl") == 0) && c->nranks <= PE_P2P_MAX_RANKS;
-    if (want) {
-      // exchange the IPC handles of all regions through NCCL.  Every step that can fail for environmental reasons
-      // (IPC disabled in the container, no peer access between two devices) is followed by a collective vote, so
-      // either every rank uses the peer-memory transport or every rank stays on NCCL.
-      auto all_agree = [&](bool mine_ok) {
-        int v = mine_ok ? 1 : 0;
-        DBuf<int> d;
-        d.upload(&v, 1, s);
-        PE_NCCL(ncclAllReduce(d.p, d.p, 1, ncclInt, ncclMin, c->comm_nccl(), s));
-        PE_CUDA(cudaMemcpyAsync(&v, d.p, sizeof v, cudaMemcpyDeviceToHost, s));
-        PE_CUDA(cudaStreamSynchronize(s));
-        return v == 1;
-      };
-      cudaIpcMemHandle_t mine;
-      std::memset(&mine, 0, sizeof mine);
-      bool ok = cudaIpcGetMemHandle(&mine, M.region) == cudaSuccess;
+  M.stage_epoch = 0;
+  M.d_peer.upload(M.peer, s);  // one rank: the persistent CG kernels post to their own mailbox
+  if (want) {
+    // Every step that can fail for environmental reasons (IPC disabled in the container, no peer access between two devices)
+    // is followed by a collective look at everybody's flag, so either every rank uses the peer-memory transport or every
+    // rank stays on NCCL.
+    PE_CUDA(cudaStreamSynchronize(s));
+    mine.ok = cudaIpcGetMemHandle(&mine.handle, M.region) == cudaSuccess ? 1 : 0;
+    (void)cudaGetLastError();
+    if (env && std::strcmp(env, "ipcfail") == 0 && c->rank == c->nranks - 1) mine.ok = 0;  // test hook: one rank cannot export
+    all = gather_records(c, mine);  // round 2: handles + landing offsets + export votes
+    bool ok = true;
+    for (const SetupRecord& r : all) ok = ok && r.ok;
+    if (ok) {
+      for (int r = 0; r < c->nranks && ok; ++r)
+        if (r != c->rank) ok = cudaIpcOpenMemHandle((void**)&M.peer[r], all[r].handle, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
       (void)cudaGetLastError();
-      if (env && std::strcmp(env, "ipcfail") == 0 && c->rank == c->nranks - 1) ok = false;  // test hook: one rank cannot export
-      DBuf<char> all;
-      all.alloc((size_t)c->nranks * sizeof mine);
-      PE_CUDA(cudaMemcpyAsync(all.p + (size_t)c->rank * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice, s));
-      PE_NCCL(ncclAllGather(all.p + (size_t)c->rank * sizeof mine, all.p, sizeof mine, ncclChar, c->comm_nccl(), s));
-      std::vector<cudaIpcMemHandle_t> h(c->nranks);
-      PE_CUDA(cudaMemcpyAsync(h.data(), all.p, all.n, cudaMemcpyDeviceToHost, s));
-      PE_CUDA(cudaStreamSynchronize(s));
-      ok = all_agree(ok);
-      if (ok) {
-        for (int r = 0; r < c->nranks && ok; ++r)
-          if (r != c->rank) ok = cudaIpcOpenMemHandle((void**)&M.peer[r], h[r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-        (void)cudaGetLastError();
-        ok = all_agree(ok);
-      }
-      if (!ok) {  // fall back to NCCL inside the CG loop as well
-        for (int r = 0; r < c->nranks; ++r)
-          if (r != c->rank && M.peer[r]) { cudaIpcCloseMemHandle(M.peer[r]); M.peer[r] = nullptr; }
-        (void)cudaGetLastError();
-        std::fprintf(stderr, "[poroel rank %d] peer-memory transport unavailable (cudaIpc), using NCCL inside the CG loop\n", c->rank);
-        PE_CUDA(cudaStreamSynchronize(s));
-        return;
-      }
-      M.d_peer.upload(M.peer, s);
-      M.ticket.alloc_zero(1, s);
-      // landing offsets: neighbour k must be told where its values go inside MY vector (n_owned + recv_ptr[k]);
-      // I need the same number from it.
-      for (int fi = 0; fi < 2; ++fi) {
-        Field& F = fi ? c->fu : c->fp;
-        Halo& H = F.halo;
-        P2PField& P = M.f[fi];
-        P.epoch = 0;
-        const int nn = H.n_neigh;
-        std::vector<long long> mine_off(std::max(nn, 1)), theirs(std::max(nn, 1));
-        for (int k = 0; k < nn; ++k) mine_off[k] = (long long)F.n_owned + H.recv_ptr[k];
-        DBuf<long long> d_out, d_in;
-        d_out.upload(mine_off, s);
-        d_in.alloc(mine_off.size());
-        PE_NCCL(ncclGroupStart());
-        for (int k = 0; k < nn; ++k) {
-          PE_NCCL(ncclSend(d_out.p + k, 1, ncclInt64, H.rank[k], c->comm_nccl(), s));
-          PE_NCCL(ncclRecv(d_in.p + k, 1, ncclInt64, H.rank[k], c->comm_nccl(), s));
-        }
-        PE_NCCL(ncclGroupEnd());
-        PE_CUDA(cudaMemcpyAsync(theirs.data(), d_in.p, theirs.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
-        PE_CUDA(cudaStreamSynchronize(s));
-        std::vector<int32_t> dest((size_t)H.n_send()), nb((size_t)H.n_send()), nr(H.rank.begin(), H.rank.end());
-        for (int k = 0; k < nn; ++k)
-          for (int64_t i = H.send_ptr[k]; i < H.send_ptr[k + 1]; ++i) {
-            dest[i] = (int32_t)(theirs[k] + (i - H.send_ptr[k]));
-            nb[i] = k;
-          }
-        P.send_dest.upload(dest, s);
-        P.send_nb.upload(nb, s);
-        P.neigh_rank.upload(nr, s);
-        // the same entries grouped by source row (counting sort; order inside a row = neighbour order)
-        {
-          const int64_t n_b = F.n_owned - F.n_interior, ns = H.n_send();
-          std::vector<int32_t> h_idx((size_t)ns);
-          PE_CUDA(cudaMemcpyAsync(h_idx.data(), H.send_idx.p, (size_t)ns * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-          PE_CUDA(cudaStreamSynchronize(s));
-          std::vector<int32_t> ptr((size_t)n_b + 1, 0), pdest((size_t)ns), pnb((size_t)ns);
-          bool all_boundary = true;
-          for (int64_t i = 0; i < ns; ++i) {
-            if (h_idx[i] < F.n_interior) { all_boundary = false; break; }
-            ptr[h_idx[i] - F.n_interior + 1]++;
-          }
-          P.push_ok = all_boundary;
-          if (all_boundary) {
-            for (int64_t r = 0; r < n_b; ++r) ptr[r + 1] += ptr[r];
-            std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
-            for (int64_t i = 0; i < ns; ++i) {
-              const int32_t at = fill[h_idx[i] - F.n_interior]++;
-              pdest[at] = dest[i];
-              pnb[at] = nb[i];
-            }
-            P.push_ptr.upload(ptr, s);
-            P.push_dest.upload(pdest, s);
-            P.push_nb.upload(pnb, s);
-          }
-        }
-      }
-      M.red_epoch = 0;
-      // nobody may start storing into a region before every rank has zeroed its own
-      DBuf<int> bar;
-      bar.alloc_zero(1, s);
-      PE_NCCL(ncclAllReduce(bar.p, bar.p, 1, ncclInt, ncclSum, c->comm_nccl(), s));
-      PE_CUDA(cudaStreamSynchronize(s));
-      M.on = true;
     }
+    mine.ok = ok ? 1 : 0;
+    std::vector<SetupRecord> votes = gather_records(c, mine);  // round 3: open votes; also the barrier behind the zeroed regions
+    for (const SetupRecord& r : votes) ok = ok && r.ok;
+    if (!ok) {  // fall back to NCCL inside the CG loop as well
+      for (int r = 0; r < c->nranks; ++r)
+        if (r != c->rank && M.peer[r]) { cudaIpcCloseMemHandle(M.peer[r]); M.peer[r] = nullptr; }
+      (void)cudaGetLastError();
+      std::fprintf(stderr, "[poroel rank %d] peer-memory transport unavailable (cudaIpc), using NCCL inside the CG loop\n", c->rank);
+      PE_CUDA(cudaStreamSynchronize(s));
+      return;
+    }
+    M.d_peer.upload(M.peer, s);
+    M.ticket.alloc_zero(1, s);
+    for (int fi = 0; fi < 2; ++fi) {
+      Field& F = fi ? c->fu : c->fp;
+      Halo& H = F.halo;
+      P2PField& P = M.f[fi];
+      P.epoch = 0;
+      const int nn = H.n_neigh;
+      // neighbour k told everybody where MY values land inside ITS vectors: all[rank k].land[fi][me]
+      std::vector<int32_t> dest((size_t)H.n_send()), nb((size_t)H.n_send()), nr(H.rank.begin(), H.rank.end());
+      for (int k = 0; k < nn; ++k) {
+        const long long theirs = all[H.rank[k]].land[fi][c->rank];
+        if (theirs < 0 && H.send_ptr[k + 1] > H.send_ptr[k]) throw PeError(PE_ERR_BAD_INPUT, "halo plans of two ranks do not match");
+        for (int64_t i = H.send_ptr[k]; i < H.send_ptr[k + 1]; ++i) {
+          dest[i] = (int32_t)(theirs + (i - H.send_ptr[k]));
+          nb[i] = k;
+        }
+      }
+      P.send_dest.upload(dest, s);
+      P.send_nb.upload(nb, s);
+      P.neigh_rank.upload(nr, s);
+      // the same entries grouped by source row (counting sort; order inside a row = neighbour order)
+      {
+        const int64_t n_b = F.n_owned - F.n_interior, ns = H.n_send();
+        std::vector<int32_t> h_idx((size_t)ns);
+        PE_CUDA(cudaMemcpyAsync(h_idx.data(), H.send_idx.p, (size_t)ns * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        PE_CUDA(cudaStreamSynchronize(s));
+        std::vector<int32_t> ptr((size_t)n_b + 1, 0), pdest((size_t)ns), pnb((size_t)ns);
+        bool all_boundary = true;
+        for (int64_t i = 0; i < ns; ++i) {
+          if (h_idx[i] < F.n_interior) { all_boundary = false; break; }
+          ptr[h_idx[i] - F.n_interior + 1]++;
+        }
+        P.push_ok = all_boundary;
+        if (all_boundary) {
+          for (int64_t r = 0; r < n_b; ++r) ptr[r + 1] += ptr[r];
+          std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+          for (int64_t i = 0; i < ns; ++i) {
+            const int32_t at = fill[h_idx[i] - F.n_interior]++;
+            pdest[at] = dest[i];
+            pnb[at] = nb[i];
+          }
+          P.push_ptr.upload(ptr, s);
+          P.push_dest.upload(pdest, s);
+          P.push_nb.upload(pnb, s);
+        }
+      }
+    }
+    M.red_epoch = 0;
+    M.on = true;
   }
   PE_CUDA(cudaStreamSynchronize(s));
 }

@@ -25,7 +25,7 @@
 
 struct Pcg2Args {
   sell::Mat m64, m32;  // m32.panels == nullptr: the inner passes stream m64
-  sell::Work work;     // work.claim points at TWO counters (pass parity)
+  sell::Work work;     // work.claim points at THREE counters (pass number mod 3)
   const double* invdiag;
   double *x, *g, *d, *s, *w, *z, *r, *c0, *c1;
   int64_t n, n_interior;
@@ -138,17 +138,27 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
       waited = true;
     }
   };
+  // Three claim counters in rotation: pass k claims from counter k % 3.  The stream of pass k+1 is begun (first claim included)
+  // at the END of pass k, before the barrier, so its counter must be clean by then: it is zeroed at the start of pass k-1,
+  // when it has been idle since pass k-2 ended, and that store is published by the barrier between passes k-1 and k.
   auto begin_pass = [&]() {
     waited = false;
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.work.claim[(pass + 1) & 1] = 0u;  // idle since the barrier before last
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.work.claim[(pass + 2) % 3] = 0u;
+  };
+  const sell::Mat& m_in = a.m32.panels ? a.m32 : a.m64;
+  sell::Stream S;  // the upcoming pass, begun ahead of the barrier in front of it
+  auto begin_stream = [&](bool inner) {
+    unsigned* ctr = a.work.claim + (pass % 3);
+    if (inner && a.m32.panels) sell::stream_begin<B, TI>(S, a.m32, ctr, gwarp, n_warps, R, lane, policy);
+    else sell::stream_begin<B, double>(S, a.m64, ctr, gwarp, n_warps, R, lane, policy);
   };
 
   // ---- prologue: z (or c0, r) from the start residual; publish its halo
   for (int64_t i = gtid; i < a.n; i += gsize) precond_first(i, a.g[i]);
+  begin_stream(a.degree > 1);
   barrier(true);
   if (timer) t_last = now();
 
-  const sell::Mat& m_in = a.m32.panels ? a.m32 : a.m64;
   const int n_chunks = (a.m64.n_slices + a.m64.chunk - 1) / a.m64.chunk;  // units of the deterministic sums of the CG pass
   double gamma_old = 1.0, alpha_old = 1.0;
   bool first = true;
@@ -192,9 +202,10 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
           }
         }
       };
-      if (a.m32.panels) sell::stream<B, TI>(m_in, cin, a.work.claim + (pass & 1), gwarp, n_warps, R, lane, policy, before, done);
-      else sell::stream<B, double>(m_in, cin, a.work.claim + (pass & 1), gwarp, n_warps, R, lane, policy, before, done);
+      if (a.m32.panels) sell::stream_run<B, TI>(S, cin, R, lane, policy, before, done);
+      else sell::stream_run<B, double>(S, cin, R, lane, policy, before, done);
       ++pass;
+      begin_stream(!last_inner);  // the next pass's first copies fly while this warp waits for the slowest one
       barrier(true);
       if (timer) ++n_in;
       lap(1);
@@ -230,9 +241,10 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
           v[0] = v[1] = v[2] = 0.0;
         }
       };
-      sell::stream<B, double>(a.m64, a.z, a.work.claim + (pass & 1), gwarp, n_warps, R, lane, policy, before, done);
+      sell::stream_run<B, double>(S, a.z, R, lane, policy, before, done);
       sell::sums_finish<3>(a.work, n_chunks, pend, lane);
       ++pass;
+      begin_stream(a.degree > 1);  // first pass of the next iteration (drained below if the solve ends here)
     }
     lap(0);
     if (timer) ++n_cg;
@@ -286,6 +298,7 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
         st->done = converged ? 1 : -1;
         a.timing[11] = (unsigned long long)k;
       }
+      sell::stream_drain(S, R);
       break;
     }
     // ---- update: d, s, x, g and the first polynomial term of the next iteration (stores the next halo)
@@ -340,6 +353,7 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.work.claim[0] = 0u;
     a.work.claim[1] = 0u;
+    a.work.claim[2] = 0u;
     a.timing[0] += t_acc[0];
     a.timing[1] += n_cg;
     a.timing[2] += t_acc[1];

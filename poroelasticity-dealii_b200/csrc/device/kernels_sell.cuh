@@ -49,6 +49,7 @@ struct Mat {
   int n_slices;
   int first_boundary_slice;  // slices before this one reference no ghost column
   int chunk;                 // slices per claim (~64 KB of panels), 1..16
+  int l2_resident;           // the panels are small enough to live in L2 between passes: no evict-first hint
   int64_t n_brows;
 };
 
@@ -84,11 +85,18 @@ __device__ __forceinline__ uint64_t evict_first_policy() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-// 1-D bulk copy global -> shared, completion counted in bytes on `bar` (TMA engine; SASS: UBLKCP)
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar` (TMA engine; SASS: UBLKCP).  policy != 0: L2 cache
+// hint (evict-first for matrices that cannot stay in L2 anyway, so they do not push the gathered vector out); policy == 0:
+// default policy — small matrices (a pressure Jacobian of an 8-GPU block is ~60 MB) then stay resident in the 126 MB L2
+// from one pass to the next.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar), "l"(policy)
-               : "memory");
+  if (policy)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar), "l"(policy)
+                 : "memory");
+  else
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 __device__ __forceinline__ int lds_i32(uint32_t addr) {
   int v;
@@ -126,99 +134,131 @@ __device__ __forceinline__ Ring ring_setup(char* smem, int warp, int lane) {
   return r;
 }
 
-// Streams the slices this warp claims.  `before(slice)` runs once per slice ahead of its first gather (halo wait of
-// boundary slices, epilogue operand prefetch); `done(slice, acc, chunk)` receives the B row sums of block row 32*slice + lane
-// and, when the slice is the last one of its chunk, the chunk's number (else -1): partial sums are formed per CHUNK.
-// x is gathered with plain cached loads.  All control flow is warp-uniform.
-//
+// ---- per-warp stream of claimed slices ------------------------------------------------------------------------------
 // Claims: work is handed out in CHUNKS of m.chunk consecutive slices (~64 KB of matrix, so the atomic and the slice-pointer
 // load are paid once per 64 KB whatever the block size).  A warp's first two chunks are static (its global warp index, then
 // + n_warps: no atomic before the first TMA copy), every later one is `2 n_warps + atomicAdd(claim, 1)`.  Both latencies are off the
 // critical path: the atomic for the chunk after next and the slice pointers of the next chunk are always in flight
 // while the current chunk streams.
-template <int B, typename T, class Before, class Done>
-__device__ __forceinline__ void stream(const Mat& m, const double* __restrict__ x, unsigned* claim, int gwarp, int n_warps, Ring& R, int lane,
-                                       uint64_t policy, Before&& before, Done&& done) {
-  typedef Cfg<B, T> C;
-  const int CH = m.chunk, n_chunks = (m.n_slices + CH - 1) / CH;
-  auto load_ptrs = [&](int chunk) {  // lane q holds slice_ptr[first slice of the chunk + q], q <= CH
-    const int s = chunk * CH + lane;
-    return (chunk < n_chunks && lane <= CH) ? m.slice_ptr[min(s, m.n_slices)] : 0;
-  };
-  auto claim_one = [&]() {
-    unsigned v = 0;
-    if (lane == 0) v = atomicAdd(claim, 1u);
-    return v;  // consumed (shuffled) one chunk later
-  };
-  int c_cur = gwarp;            // the first two chunks of a warp are static: nothing to wait for at the start of a pass
-  int sp_cur = load_ptrs(c_cur);
-  int c_next = gwarp + n_warps;
-  int sp_next = load_ptrs(c_next);
-  unsigned a_nn = claim_one();  // chunk ids from here on: 2 n_warps + ticket
-  int q = -1, nq = c_cur < n_chunks ? min(CH, m.n_slices - c_cur * CH) : 0;
-  bool exhausted = c_cur >= n_chunks;
-
-  int f_slice = -1, f_j = 0, f_np = 0;  // fetch cursor: slice, next panel, panels of the slice
-  int64_t f_base = 0;
+//
+// The stream is split in two so that a persistent kernel can hide the start-up latency of a pass as well: stream_begin()
+// only needs the MATRIX (which never changes), so it is called for the next pass BEFORE the grid barrier that ends the
+// current one — slice pointers, first claim and the first NST bulk copies are in flight while the warp waits for the
+// slowest warp of the grid; stream_run() consumes (and keeps issuing) behind the barrier.  stream_drain() waits for copies
+// that were issued but will never be consumed (a kernel must not exit with bulk copies in flight into its shared memory).
+struct Stream {
+  const char* panels;
+  const int32_t* slice_ptr;
+  unsigned* claim;
+  int n_slices, CH, n_chunks, n_warps, panel, sj;
+  int c_cur, c_next, sp_cur, sp_next, q, nq;
+  unsigned a_nn;
+  bool exhausted;
+  int f_slice, f_j, f_np;  // fetch cursor: slice, next panel, panels of the slice
+  int64_t f_base;
   int d_slice[NST], d_cnt[NST], d_chunk[NST];
   bool d_first[NST], d_last[NST], d_cend[NST];
+  bool resident;
+};
 
-  auto issue = [&](int st) {
-    while (f_j >= f_np && !exhausted) {
-      if (++q >= nq) {  // next chunk
-        c_cur = c_next;
-        sp_cur = sp_next;
-        c_next = 2 * n_warps + (int)__shfl_sync(0xffffffffu, a_nn, 0);
-        sp_next = load_ptrs(c_next);
-        if (c_next < n_chunks) a_nn = claim_one();
-        if (c_cur >= n_chunks) {
-          exhausted = true;
-          break;
-        }
-        q = 0;
-        nq = min(CH, m.n_slices - c_cur * CH);
+__device__ __forceinline__ int stream_load_ptrs(const Stream& S, int chunk, int lane) {  // lane q: slice_ptr[first slice of the chunk + q], q <= CH
+  const int s = chunk * S.CH + lane;
+  return (chunk < S.n_chunks && lane <= S.CH) ? S.slice_ptr[min(s, S.n_slices)] : 0;
+}
+__device__ __forceinline__ unsigned stream_claim(const Stream& S, int lane) {
+  unsigned v = 0;
+  if (lane == 0) v = atomicAdd(S.claim, 1u);
+  return v;  // consumed (shuffled) one chunk later
+}
+__device__ __forceinline__ void stream_issue(Stream& S, int st, Ring& R, int lane, uint64_t policy) {
+  while (S.f_j >= S.f_np && !S.exhausted) {
+    if (++S.q >= S.nq) {  // next chunk
+      S.c_cur = S.c_next;
+      S.sp_cur = S.sp_next;
+      S.c_next = 2 * S.n_warps + (int)__shfl_sync(0xffffffffu, S.a_nn, 0);
+      S.sp_next = stream_load_ptrs(S, S.c_next, lane);
+      if (S.c_next < S.n_chunks) S.a_nn = stream_claim(S, lane);
+      if (S.c_cur >= S.n_chunks) {
+        S.exhausted = true;
+        break;
       }
-      f_slice = c_cur * CH + q;
-      const int p0 = __shfl_sync(0xffffffffu, sp_cur, q), p1 = __shfl_sync(0xffffffffu, sp_cur, q + 1);
-      f_base = p0;
-      f_np = p1 - p0;
-      f_j = 0;
+      S.q = 0;
+      S.nq = min(S.CH, S.n_slices - S.c_cur * S.CH);
     }
-    if (f_j >= f_np) {
-      d_cnt[st] = 0;
-      return;
-    }
-    const int cnt = min(C::SJ, f_np - f_j);
-    d_slice[st] = f_slice;
-    d_cnt[st] = cnt;
-    d_first[st] = f_j == 0;
-    d_last[st] = f_j + cnt == f_np;
-    d_chunk[st] = c_cur;
-    d_cend[st] = q == nq - 1;  // (with d_last) the chunk ends here: its partial sums are complete
-    if (lane == 0) {
-      const uint32_t bytes = (uint32_t)cnt * C::PANEL;
-      mbar_expect_tx(R.bar + 8 * st, bytes);
-      bulk_g2s(R.base + (uint32_t)st * STAGE_BYTES, m.panels + (size_t)(f_base + f_j) * C::PANEL, bytes, R.bar + 8 * st, policy);
-    }
-    f_j += cnt;
-  };
+    S.f_slice = S.c_cur * S.CH + S.q;
+    const int p0 = __shfl_sync(0xffffffffu, S.sp_cur, S.q), p1 = __shfl_sync(0xffffffffu, S.sp_cur, S.q + 1);
+    S.f_base = p0;
+    S.f_np = p1 - p0;
+    S.f_j = 0;
+  }
+  if (S.f_j >= S.f_np) {
+    S.d_cnt[st] = 0;
+    return;
+  }
+  const int cnt = min(S.sj, S.f_np - S.f_j);
+  S.d_slice[st] = S.f_slice;
+  S.d_cnt[st] = cnt;
+  S.d_first[st] = S.f_j == 0;
+  S.d_last[st] = S.f_j + cnt == S.f_np;
+  S.d_chunk[st] = S.c_cur;
+  S.d_cend[st] = S.q == S.nq - 1;  // (with d_last) the chunk ends here: its partial sums are complete
+  if (lane == 0) {
+    const uint32_t bytes = (uint32_t)cnt * S.panel;
+    mbar_expect_tx(R.bar + 8 * st, bytes);
+    bulk_g2s(R.base + (uint32_t)st * STAGE_BYTES, S.panels + (size_t)(S.f_base + S.f_j) * S.panel, bytes, R.bar + 8 * st, S.resident ? 0ull : policy);
+  }
+  S.f_j += cnt;
+}
 
+template <int B, typename T>
+__device__ __forceinline__ void stream_begin(Stream& S, const Mat& m, unsigned* claim, int gwarp, int n_warps, Ring& R, int lane, uint64_t policy) {
+  typedef Cfg<B, T> C;
+  S.panels = m.panels;
+  S.slice_ptr = m.slice_ptr;
+  S.claim = claim;
+  S.n_slices = m.n_slices;
+  S.CH = m.chunk;
+  S.n_chunks = (m.n_slices + m.chunk - 1) / m.chunk;
+  S.n_warps = n_warps;
+  S.panel = C::PANEL;
+  S.sj = C::SJ;
+  S.resident = m.l2_resident != 0;
+  S.c_cur = gwarp;            // the first two chunks of a warp are static: nothing to wait for at the start of a pass
+  S.sp_cur = stream_load_ptrs(S, S.c_cur, lane);
+  S.c_next = gwarp + n_warps;
+  S.sp_next = stream_load_ptrs(S, S.c_next, lane);
+  S.a_nn = stream_claim(S, lane);  // chunk ids from here on: 2 n_warps + ticket
+  S.q = -1;
+  S.nq = S.c_cur < S.n_chunks ? min(S.CH, S.n_slices - S.c_cur * S.CH) : 0;
+  S.exhausted = S.c_cur >= S.n_chunks;
+  S.f_slice = -1;
+  S.f_j = 0;
+  S.f_np = 0;
+  S.f_base = 0;
 #pragma unroll
-  for (int st = 0; st < NST; ++st) issue(st);
+  for (int st = 0; st < NST; ++st) stream_issue(S, st, R, lane, policy);
+}
 
+// Consumes the stream.  `before(slice)` runs once per slice ahead of its first gather (halo wait of boundary slices, epilogue
+// operand prefetch); `done(slice, acc, chunk)` receives the B row sums of block row 32*slice + lane and, when the slice is the
+// last one of its chunk, the chunk's number (else -1): partial sums are formed per CHUNK.  x is gathered with plain cached
+// loads.  All control flow is warp-uniform.
+template <int B, typename T, class Before, class Done>
+__device__ __forceinline__ void stream_run(Stream& S, const double* __restrict__ x, Ring& R, int lane, uint64_t policy, Before&& before, Done&& done) {
+  typedef Cfg<B, T> C;
   double acc[B];
   bool more = true;
   while (more) {
 #pragma unroll
     for (int st = 0; st < NST; ++st) {
       if (!more) break;
-      if (d_cnt[st] == 0) {
+      if (S.d_cnt[st] == 0) {
         more = false;
         break;
       }
-      const int cnt = d_cnt[st];
-      if (d_first[st]) {
-        before(d_slice[st]);
+      const int cnt = S.d_cnt[st];
+      if (S.d_first[st]) {
+        before(S.d_slice[st]);
 #pragma unroll
         for (int r = 0; r < B; ++r) acc[r] = 0.0;
       }
@@ -245,12 +285,31 @@ __device__ __forceinline__ void stream(const Mat& m, const double* __restrict__ 
         }
       }
       __syncwarp();  // every lane has read the stage: lane 0 may re-arm it
-      const bool last = d_last[st];
-      const int slice = d_slice[st], chunk = d_cend[st] ? d_chunk[st] : -1;
-      issue(st);
+      const bool last = S.d_last[st];
+      const int slice = S.d_slice[st], chunk = S.d_cend[st] ? S.d_chunk[st] : -1;
+      stream_issue(S, st, R, lane, policy);
       if (last) done(slice, acc, chunk);
     }
   }
+}
+
+// Waits for the copies of a stream that was begun but is not going to be consumed.
+__device__ __forceinline__ void stream_drain(Stream& S, Ring& R) {
+#pragma unroll
+  for (int st = 0; st < NST; ++st) {
+    if (S.d_cnt[st] == 0) break;
+    while (!mbar_try_wait(R.bar + 8 * st, (R.parity >> st) & 1u)) {}
+    R.parity ^= 1u << st;
+  }
+}
+
+// one pass, start to end (the stand-alone SpMV kernels)
+template <int B, typename T, class Before, class Done>
+__device__ __forceinline__ void stream(const Mat& m, const double* __restrict__ x, unsigned* claim, int gwarp, int n_warps, Ring& R, int lane,
+                                       uint64_t policy, Before&& before, Done&& done) {
+  Stream S;
+  stream_begin<B, T>(S, m, claim, gwarp, n_warps, R, lane, policy);
+  stream_run<B, T>(S, x, R, lane, policy, before, done);
 }
 
 // Deterministic sums with dynamic work distribution, in two halves so that the atomic's round trip overlaps the next slice:

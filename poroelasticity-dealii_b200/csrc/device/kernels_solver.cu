@@ -937,8 +937,13 @@ void launch_sell_t(pe_ctx* c, const SpmvArgs& a, const sell::Mat& m, const sell:
 
 inline sell::Mat sell_mat(const SellMat& S) {
   const double slice_bytes = (double)S.n_panels * S.panel_bytes / std::max(1, S.n_slices);
-  const int chunk = (int)std::min(16.0, std::max(1.0, std::floor(65536.0 / slice_bytes + 0.5)));
-  return sell::Mat{S.panels.p, S.slice_ptr.p, S.n_slices, S.first_boundary_slice, chunk, S.n_brows};
+  // ~32 KB per claim: the claim's round trip is prefetched (kernels_sell.cuh), so small units cost nothing and keep the
+  // end-of-pass tail (at most one unit per warp) short
+  static const double chunk_bytes = std::getenv("PE_CHUNK_KB") ? 1024.0 * std::atof(std::getenv("PE_CHUNK_KB")) : 32768.0;
+  const int chunk = (int)std::min(16.0, std::max(1.0, std::floor(chunk_bytes / slice_bytes + 0.5)));
+  static const double l2_mb = std::getenv("PE_L2_RESIDENT_MB") ? std::atof(std::getenv("PE_L2_RESIDENT_MB")) : 64.0;
+  const int resident = (double)S.n_panels * S.panel_bytes <= l2_mb * 1048576.0 ? 1 : 0;
+  return sell::Mat{S.panels.p, S.slice_ptr.p, S.n_slices, S.first_boundary_slice, chunk, resident, S.n_brows};
 }
 inline sell::Work sell_work(pe_ctx* c, int parity = 0) {
   return sell::Work{c->red.claim.p + parity, c->red.spart.p, c->red.gcnt.p, c->red.gpart.p, c->red.cap, c->red.gcap};
@@ -1438,7 +1443,7 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
     const CgState last = c->h_state[0];
     if (last.pad) {  // a wait timed out: barriers, claim counters and group counters may be half-used; start clean next time
       PE_CUDA(cudaMemsetAsync(c->pcg_tickets.p, 0, 4 * sizeof(unsigned), c->stream));
-      PE_CUDA(cudaMemsetAsync(c->red.claim.p, 0, 2 * sizeof(unsigned), c->stream));
+      PE_CUDA(cudaMemsetAsync(c->red.claim.p, 0, 3 * sizeof(unsigned), c->stream));
       PE_CUDA(cudaMemsetAsync(c->red.gcnt.p, 0, (size_t)c->red.gcap * sizeof(unsigned), c->stream));
       PE_CUDA(cudaStreamSynchronize(c->stream));
     }

@@ -169,7 +169,7 @@ struct Reducer {
   DBuf<unsigned> counter;  // 1
   DBuf<double> out;        // PE_RED_SLOTS (+ scratch)
   // deterministic sums of the dynamically distributed sliced kernels (kernels_sell.cuh): per-slice and per-group slots
-  DBuf<unsigned> claim;    // 2 (one per parity of the persistent kernel's passes)
+  DBuf<unsigned> claim;    // 3 (the persistent kernel rotates them by pass number)
   DBuf<double> spart, gpart;
   DBuf<unsigned> gcnt;
   int cap = 0, gcap = 0;   // slices / groups the slot arrays hold
@@ -182,7 +182,7 @@ static constexpr int PE_SELL_NV = 4;  // values a pass can reduce at once
 // published with a system-scope fence + an epoch flag the receiver polls.  NCCL stays for setup and for
 // the few exchanges outside the CG loop.
 static constexpr int PE_P2P_MAX_RANKS = 16;
-static constexpr int PE_WORK_VECTORS = 8;
+static constexpr int PE_WORK_VECTORS = 10;
 static constexpr int PE_PCG_TIMING_WORDS = 16;
 struct P2PControl {                                   // lives at the start of every rank's region
   int halo_flag[2][PE_P2P_MAX_RANKS];                 // [field][sender rank] = epoch of the last halo it stored here
@@ -208,6 +208,7 @@ struct P2P {
   DBuf<unsigned> ticket;             // last-block counter of k_halo_send
   P2PField f[2];
   unsigned red_epoch = 0;
+  unsigned stage_epoch = 0;          // staged halo exchanges so far (parity picks the staging buffer)
 };
 
 struct pe_ctx {
@@ -259,7 +260,7 @@ struct pe_ctx {
   int n_stress = 0;
   // CG work vectors sized for the larger field; they live in `comm.region` (IPC-exported when nranks > 1)
   struct WPtr { double* p = nullptr; };
-  WPtr w_g, w_h, w_d, w_z, w_d2, w_r, w_s, w_c1;
+  WPtr w_g, w_h, w_d, w_z, w_d2, w_r, w_s, w_c1, w_x0, w_x1;
   P2P p2p;
 
   Reducer red;

@@ -89,7 +89,7 @@ class InputDataPoroel {
   int chebyshev_degree = 4;
   double chebyshev_eig_ratio = 30.0;
   int cg_max_iterations = 1000;     // PS:175, DS:299, SP:209
-  int refine_every = 0;             // reference: 5 (FSS:333); 0 = never (uniform-mesh benchmarks, partitioned runs)
+  int refine_every = 5;             // the reference's as-is schedule (FSS:333: time_step_number % 5); 0 = never (uniform-mesh benchmarks, partitioned runs)
   int couple_volumetric_strain = 0; // 1 re-enables FSS:399
   int write_vtk = 0;                // FSS:411
   int max_time_steps = 0;           // 0 = until t_max
@@ -182,7 +182,7 @@ class InputDataPoroel {
     declare("GPU", "Chebyshev degree", "4", 'i', 1, 64);
     declare("GPU", "Chebyshev eigenvalue ratio", "30", 'd', 1.0001);
     declare("GPU", "CG max iterations", "1000", 'i', 1);
-    declare("GPU", "Refine every", "0", 'i', 0);
+    declare("GPU", "Refine every", "5", 'i', 0);
     declare("GPU", "Couple volumetric strain", "0", 'i', 0, 1);
     declare("GPU", "Write VTK", "0", 'i', 0, 1);
     declare("GPU", "Max time steps", "0", 'i', 0);

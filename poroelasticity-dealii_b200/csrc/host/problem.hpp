@@ -7,7 +7,7 @@
 //   * mechanics -> flow feedback off unless `Couple volumetric strain = 1` (FSS:399 is commented out);
 //   * the initial volumetric strain is the reference state for all steps (FSS:317, PS:122-124);
 //   * create_mesh() is the default, read_mesh() optional (FSS:297-298).
-// Adaptive refinement (FSS:333-340, refine_mesh FSS:447-498) runs every `Refine every` steps (reference: 5; default 0 =
+// Adaptive refinement (FSS:333-340, refine_mesh FSS:447-498) runs every `Refine every` steps (default 5 = the reference's schedule; 0 =
 // never, the configuration of the BASELINE benchmarks) on one rank: amr.hpp provides the refinement forest, the Kelly
 // estimator, the marking and the solution transfer; hanging-node constraints go to the device as general lines.
 #pragma once

@@ -38,8 +38,10 @@ end
 """
 
 
-def make_input(dim=2, refine=4, degree_u=2, extra_gpu="", cells=None, neumann=None, dirichlet=None):
-    """input.data text with the shipped properties (input.data:24-35), extended to 3D as SURVEY §8d says."""
+def make_input(dim=2, refine=4, degree_u=2, extra_gpu="", cells=None, neumann=None, dirichlet=None, refine_every=0):
+    """input.data text with the shipped properties (input.data:24-35), extended to 3D as SURVEY §8d says.  Uniform mesh unless
+    `refine_every` (or a `Refine every` line in extra_gpu) says otherwise: the parser's default is the reference's every-5th-step
+    refinement (FSS:333), which the uniform-mesh parity cases and the benchmarks switch off."""
     size = ", ".join(["10"] * dim)
     if dirichlet is None:
         labels = ", ".join(str(i) for i in range(2 * dim))
@@ -49,6 +51,8 @@ def make_input(dim=2, refine=4, degree_u=2, extra_gpu="", cells=None, neumann=No
         labels, comps, vals = (", ".join(str(x) for x in col) for col in dirichlet)
     nl, nc, nv = (", ".join(str(x) for x in col) for col in neumann) if neumann else ("", "", "")
     cells_line = f"  set Cells per axis = {', '.join(str(c) for c in cells)}\n" if cells else ""
+    if "Refine every" not in extra_gpu:
+        cells_line += f"  set Refine every = {refine_every}\n"
     return f"""
 subsection Mesh
   set Dimensions               = {dim}

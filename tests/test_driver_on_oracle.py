@@ -150,13 +150,13 @@ def test_vtk_writer(on_oracle, tmp_path, monkeypatch, degree_u, refine_every):
 
 def test_fss_poroel_executable_runs_the_shipped_input_with_refinement(tmp_path):
     """csrc/host/main.cpp (`fss-poroel <input.data>`, PCL:5-27) built against the oracle shim: the reference's input.data
-    plus `Refine every = 5` runs all 17 steps, refines at steps 5, 10 and 15 (FSS:333-340) and prints the reference's log."""
+    as shipped (no GPU subsection; `Refine every` defaults to the reference's 5) runs all 17 steps, refines at steps 5, 10 and 15 (FSS:333-340) and prints the reference's log."""
     H.load_oracle()
     exe = tmp_path / "fss-poroel-on-oracle"
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", str(exe), str(H.ROOT / "poroelasticity-dealii_b200" / "csrc" / "host" / "main.cpp"),
                            str(H.ROOT / "tests" / "driver_on_oracle.cpp"), "-L", str(H.ROOT / "oracle"), "-loracle", f"-Wl,-rpath,{H.ROOT / 'oracle'}"])
     f = tmp_path / "input.data"
-    f.write_text(H.SHIPPED_INPUT + "\nsubsection GPU\n  set Refine every = 5\nend\n")
+    f.write_text(H.SHIPPED_INPUT)  # exactly the reference's file: the every-5th-step refinement is the default
     out = subprocess.run([str(exe), str(f)], capture_output=True, text=True, timeout=600, cwd=tmp_path)
     assert out.returncode == 0, out.stderr[-2000:]
     log = out.stdout

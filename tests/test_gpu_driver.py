@@ -62,3 +62,21 @@ def test_fss_poroel_default_iteration_cap(tmp_path):
     out = subprocess.run([str(BIN), str(f)], capture_output=True, text=True, timeout=300, cwd=tmp_path)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count("Coupling iteration: 1") == 3
+
+
+def test_fss_poroel_runs_the_shipped_input_as_is_with_refinement(tmp_path):
+    """`fss-poroel input.data` on the reference's file exactly as shipped (no GPU subsection): the as-is schedule of FSS:333-340
+    is the default, so the run refines at steps 5, 10 and 15 and completes all 17 steps on the hanging-node path."""
+    f = tmp_path / "input.data"
+    f.write_text(H.SHIPPED_INPUT)
+    out = subprocess.run([str(BIN), str(f)], capture_output=True, text=True, timeout=600, cwd=tmp_path)
+    assert out.returncode == 0, out.stderr[-2000:]
+    log = out.stdout
+    assert log.count("Time: ") == 17 and log.count("Refining mesh") == 3
+    assert log.count("Coupling iteration: 1") == 17 and "Coupling iteration: 2" not in log
+    lines = log.splitlines()
+    for step in (5, 10, 15):
+        i = lines.index(f"Time: {60 * step}")
+        assert lines[i + 1] == "Refining mesh" and "active cells" in lines[i + 2]
+    cells = [int(x) for x in re.findall(r"active cells: (\d+)", log)] or [int(x) for x in re.findall(r"(\d+) active cells", log)]
+    assert cells and max(cells) > 256

@@ -17,9 +17,11 @@ def _n_gpus():
     return torch.cuda.device_count()
 
 
-def _worker(rank, world, nccl_id, text, q):
+def _worker(rank, world, nccl_id, text, q, cwd=None):
     sys.path.insert(0, str(H.ROOT / "tests"))
     try:
+        if cwd:
+            os.chdir(cwd)  # read_mesh() opens "domain.msh" in the working directory (FSS:438-445)
         inp = capi.InputData(text=text)
         prob = capi.Problem(inp, device=rank, rank=rank, nranks=world, nccl_id=nccl_id)
         prob.initialize()
@@ -84,3 +86,56 @@ def test_partitioned_run_matches_single_gpu_and_oracle(world, case):
         assert [s["cg_its_displacement"] for s in r["reps"]] == [s["cg_its_displacement"] for s in res[0]["reps"]]
     assert [s["pressure_iterations"] for s in res[0]["reps"]] == [s["pressure_iterations"] for s in outs["oracle"][2]]
     assert sum(r["stats"]["n_dofs_u"] for r in res) == n_u
+
+
+def test_partitioned_gmsh_mesh_matches_single_gpu_and_oracle(tmp_path):
+    """SURVEY §8f row 4 at a non-toy size: a distorted 22^3 = 10,648-hex Gmsh mesh whose cells come in random order (as a mesh
+    generator writes them), read by read_mesh(), ordered along the space-filling curve and cell-partitioned over 2 ranks:
+    fields equal the single-GPU run and the CPU oracle to 1e-8, same iteration counts on both ranks."""
+    world = 2
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from golden import make_msh
+    make_msh.distorted_hex(n=22, amp=0.15, seed=5, path=str(tmp_path / "domain.msh"), shuffle=True)
+    text = H.make_input(dim=3, refine=2, degree_u=1, extra_gpu="  set Read mesh file = 1\n  set CG max iterations = 5000\n")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    nccl_id = capi.nccl_unique_id()
+    procs = [ctx.Process(target=_worker, args=(r, world, nccl_id, text, q, str(tmp_path))) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for r in res:
+        assert "error" not in r, r
+    res.sort(key=lambda r: r["rank"])
+    n_p, n_u = sum(len(r["gp"]) for r in res), sum(len(r["gu"]) for r in res)
+    assert n_p == 23 ** 3 and n_u == 3 * 23 ** 3
+    assert min(r["stats"]["n_cells"] for r in res) >= 22 ** 3 // 2  # each rank: half the cells + a ghost layer
+    p, u = np.zeros(n_p), np.zeros(n_u)
+    for r in res:
+        p[r["gp"]], u[r["gu"]] = r["p"], r["u"]
+    # single-GPU run and oracle on the same file; the partitioned run numbers dofs along the curve-ordered cells, the
+    # single-rank runs in file order (GridIn::read_msh), so fields are matched by support point
+    inp = capi.InputData(text=text)
+    mesh = capi.mesh_read_msh(tmp_path / "domain.msh", 3)
+    mesh_sfc = capi.mesh_read_msh(tmp_path / "domain.msh", 3)
+    mesh_sfc.reorder_sfc()
+    key = lambda pts: np.lexsort(np.round(pts, 9).T[::-1])
+    sp_file, sp_sfc = capi.HostDofs(mesh, 1, 1).support_points(), capi.HostDofs(mesh_sfc, 1, 1).support_points()
+    perm_p = np.empty(n_p, dtype=np.int64)
+    perm_p[key(sp_file)] = key(sp_sfc)          # file-order dof -> curve-order dof at the same point
+    assert np.allclose(sp_file, sp_sfc[perm_p], atol=1e-9)
+    perm_u = (3 * perm_p[:, None] + np.arange(3)[None, :]).ravel()
+    for name, b in (("gpu1", capi.create_device_backend(0)), ("oracle", H.create_oracle_backend())):
+        fss.upload_problem(b, inp, mesh)
+        fss.initialize(b, inp)
+        reps = [fss.time_step(b, inp) for _ in range(2)]
+        p1, u1 = b.get_vector(capi.VEC_P), b.get_vector(capi.VEC_U)
+        b.close()
+        assert fss.rel_l2(p[perm_p], p1) <= 1e-8, (name, fss.rel_l2(p[perm_p], p1))
+        assert fss.rel_l2(u[perm_u], u1) <= 1e-8, (name, fss.rel_l2(u[perm_u], u1))
+        assert [s["pressure_iterations"] for s in res[0]["reps"]] == [s["pressure_iterations"] for s in reps]
+    assert [s["cg_its_displacement"] for s in res[0]["reps"]] == [s["cg_its_displacement"] for s in res[1]["reps"]]
