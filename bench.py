@@ -525,7 +525,11 @@ def main():
                                            "launches_timed": int(stats["spmv_timed_p"])},
                          "phase_ms_per_step": {"fp64_passes": stats["spmv_ms_u"] / args.steps, "preconditioner_passes": stats["inner_ms_u"] / args.steps,
                                                "vector_updates": stats["update_ms_u"] / args.steps, "reductions": stats["reduce_ms_u"] / args.steps,
-                                               "displacement_solves": stats["pcg_ms_u"] / args.steps, "pressure_and_projection_solves": stats["pcg_ms_p"] / args.steps},
+                                               "displacement_solves": stats["pcg_ms_u"] / args.steps, "pressure_and_projection_solves": stats["pcg_ms_p"] / args.steps,
+                                               "waits_inside_the_phases": {"barrier_behind_inner_passes": stats["wait_inner_ms_u"] / args.steps,
+                                                                           "barrier_behind_cg_pass": stats["wait_cg_ms_u"] / args.steps,
+                                                                           "peer_mailboxes": stats["wait_peer_ms_u"] / args.steps,
+                                                                           "barrier_behind_updates": stats["wait_update_ms_u"] / args.steps}},
                          "spmv_share_of_step": (stats["spmv_ms_u"] + stats["inner_ms_u"] + stats["spmv_ms_p"]) / ms_total if ms_total > 0 else None},
             "iterations_per_step": {"pressure_inner": float(np.mean([r["pressure_iterations"] for r in reports])),
                                     "cg_pressure": float(np.mean([r["cg_its_pressure"] for r in reports])),

@@ -116,6 +116,9 @@ typedef struct pe_stats {
   double  inner_bytes_u;                     /* algorithmic bytes of one such pass (FP32 copy of the values when built)  */
   double  update_ms_u, reduce_ms_u;          /* vector-update phases; the one allreduce per iteration (incl. its barrier) */
   int64_t sell_format_u;                     /* 1: the displacement matrix is streamed from its sliced block-ELL copy     */
+  /* time CTA 0 of that kernel spent WAITING (a subset of the phase times above): at the grid barrier behind the inner
+     passes, at the one behind the CG pass, for the peers' reduction mailboxes, at the barrier behind the updates */
+  double  wait_inner_ms_u, wait_cg_ms_u, wait_peer_ms_u, wait_update_ms_u;
 } pe_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------- */

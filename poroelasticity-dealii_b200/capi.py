@@ -56,6 +56,7 @@ class PeStats(C.Structure):
         ("bsr_block_size", C.c_int64),
         ("inner_ms_u", C.c_double), ("inner_passes_u", C.c_int64), ("inner_bytes_u", C.c_double), ("update_ms_u", C.c_double),
         ("reduce_ms_u", C.c_double), ("sell_format_u", C.c_int64),
+        ("wait_inner_ms_u", C.c_double), ("wait_cg_ms_u", C.c_double), ("wait_peer_ms_u", C.c_double), ("wait_update_ms_u", C.c_double),
     ]
 
     def as_dict(self):

@@ -423,7 +423,8 @@ int pe_setup(pe_ctx* c) {
   }
   const double* m_proj = c->fp.hang.n ? c->Mc.p : c->M.p;
   pe_extract_invdiag(c, c->fp, m_proj, c->invdiag_M.p);
-  pe_build_sell(c, c->fp, 3, m_proj, false);  // the projection solves (SP:201-232) stream this copy
+  // the projection solves (SP:201-232) stream this copy; format decisions are collective (pe_all_ranks_agree)
+  if (!pe_all_ranks_agree(c, pe_build_sell(c, c->fp, 3, m_proj, false))) c->fp.sell[3].B = 0;
   c->eig_M = 1.1 * pe_estimate_eig_max(c, c->fp, m_proj, c->invdiag_M.p);
   tick("sliced copy + eigenvalue estimate of M");
   if (timing) std::fprintf(stderr, "[pe rank %d] pe_setup:%s\n", c->rank, t_report.c_str());
@@ -493,11 +494,12 @@ int pe_pressure_assemble_jacobian(pe_ctx* c, double dt) {
     const double* Ks = c->fp.hang.n ? c->Kc.p : c->K.p;
     pe_vec_axpby_vals(c, c->fp.nnz, 1. / c->prm.m_modulus / dt, Ms, c->prm.perm_over_visc, Ks, c->J.p);
     pe_extract_invdiag(c, c->fp, c->J.p, c->invdiag_J.p);
-    const bool have_j = pe_build_sell(c, c->fp, 2, c->J.p, false);
+    const bool have_j = pe_all_ranks_agree(c, pe_build_sell(c, c->fp, 2, c->J.p, false));
+    if (!have_j) c->fp.sell[2].B = 0;
     {  // FP32 twin for the passes inside the Chebyshev polynomial (as for the displacement matrix)
       const char* f32 = std::getenv("PE_CHEB_FP32");
       if (have_j && c->prm.preconditioner == PE_PRECOND_CHEBYSHEV && c->prm.chebyshev_degree > 1 && !(f32 && std::string(f32) == "0"))
-        pe_build_sell(c, c->fp, 4, c->J.p, true);
+        { if (!pe_all_ranks_agree(c, pe_build_sell(c, c->fp, 4, c->J.p, true))) c->fp.sell[4].B = 0; }
       else
         c->fp.sell[4].B = 0;
     }
@@ -559,17 +561,18 @@ int pe_displacement_assemble(pe_ctx* c) {
     {
       const char* fmt = std::getenv("PE_FORMAT");
       const bool want_bsr = !(fmt && std::string(fmt) == "csr");
-      if (want_bsr && pe_build_bsr(c, c->fu, c->A.p)) {
+      if (want_bsr && pe_all_ranks_agree(c, pe_build_bsr(c, c->fu, c->A.p))) {
         const Field::Bsr& S = c->fu.bsr;
         c->st.spmv_bytes_u = (double)S.nnzb * (S.B * S.B * 8.0 + 4.0) + (double)S.n_brows * 4.0 + (double)c->fu.n_owned * 16.0;
         c->st.bsr_block_size = S.B;
         pe_build_bsr_fp32(c, c->fu);
         // TMA-fed sliced copy (+ its FP32 twin for the passes inside the Chebyshev polynomial unless PE_CHEB_FP32=0)
-        const bool have_sell = pe_build_sell(c, c->fu, 0, c->A.p, false);
+        const bool have_sell = pe_all_ranks_agree(c, pe_build_sell(c, c->fu, 0, c->A.p, false));
+        if (!have_sell) c->fu.sell[0].B = 0;
         c->st.sell_format_u = have_sell ? 1 : 0;
         const char* f32 = std::getenv("PE_CHEB_FP32");
         if (have_sell && c->prm.preconditioner == PE_PRECOND_CHEBYSHEV && c->prm.chebyshev_degree > 1 && !(f32 && std::string(f32) == "0"))
-          pe_build_sell(c, c->fu, 1, c->A.p, true);
+          { if (!pe_all_ranks_agree(c, pe_build_sell(c, c->fu, 1, c->A.p, true))) c->fu.sell[1].B = 0; }
         else
           c->fu.sell[1].B = 0;
       } else {
@@ -757,6 +760,7 @@ int pe_reset_stats(pe_ctx* c) {
   c->st.pcg_ms_p = c->st.pcg_ms_u = 0;
   c->st.pcg_iterations_p = c->st.pcg_iterations_u = 0;
   c->st.inner_ms_u = c->st.update_ms_u = c->st.reduce_ms_u = 0;
+  c->st.wait_inner_ms_u = c->st.wait_cg_ms_u = c->st.wait_peer_ms_u = c->st.wait_update_ms_u = 0;
   c->st.inner_passes_u = 0;
   PE_LEAVE(c)
 }

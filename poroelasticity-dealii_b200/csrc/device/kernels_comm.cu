@@ -134,6 +134,20 @@ void pe_allreduce_sum(pe_ctx* c, double* dev, int count, bool in_solve) {
   PE_NCCL(ncclAllReduce(dev, dev, count, ncclDouble, ncclSum, c->comm_nccl(), c->stream));
 }
 
+// A rank-local yes/no (did my copy of the matrix build in format X?) turned into a decision every rank shares.  The solver
+// paths that follow from such a decision speak different peer-memory protocols, so ranks must never choose on their own:
+// a small rank whose sliced copy was rejected for padding next to ranks that kept theirs would wait for messages that
+// never come.  Collective; cold path (setup / first assembly / dt change).
+bool pe_all_ranks_agree(pe_ctx* c, bool mine) {
+  if (c->nranks <= 1) return mine;
+  c->h_scalars[0] = mine ? 0.0 : 1.0;
+  PE_CUDA(cudaMemcpyAsync(c->red.out.p, c->h_scalars, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  pe_allreduce_sum(c, c->red.out.p, 1);
+  PE_CUDA(cudaMemcpyAsync(c->h_scalars, c->red.out.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  pe_sync_checked(c);
+  return c->h_scalars[0] == 0.0;
+}
+
 // ghost values of v (entries [n_owned, n_local)) <- owners
 void pe_halo_exchange(pe_ctx* c, Field& F, double* v, bool in_solve, int* fused_epoch) {
   if (fused_epoch) *fused_epoch = 0;
@@ -304,8 +318,8 @@ void pe_comm_setup(pe_ctx* c, size_t n_work) {
           if (h_idx[i] < F.n_interior) { all_boundary = false; break; }
           ptr[h_idx[i] - F.n_interior + 1]++;
         }
-        P.push_ok = all_boundary;
-        if (all_boundary) {
+        P.push_ok = pe_all_ranks_agree(c, all_boundary);  // the persistent kernel is chosen by all ranks or by none
+        if (P.push_ok) {
           for (int64_t r = 0; r < n_b; ++r) ptr[r + 1] += ptr[r];
           std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
           for (int64_t i = 0; i < ns; ++i) {

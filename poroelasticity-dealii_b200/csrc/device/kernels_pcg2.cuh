@@ -37,7 +37,8 @@ struct Pcg2Args {
   int* bar_flag;
   int* abort;
   unsigned long long* timing; // [0] ns in CG passes (CTA 0), [1] CG passes, [2] ns in inner passes, [3] inner passes, [4] ns in updates,
-                              // [5] ns in allreduces, [10] halo exchanges posted, [11] reductions posted
+                              // [5] ns in allreduces, [6..9] ns CTA 0 waited at the barrier behind inner passes / behind the CG pass / for the
+                              // peer mailboxes / at the barrier behind updates, [10] halo exchanges posted, [11] reductions posted
   char* const* peer;
   int nranks, me, red_epoch0;
   int n_neigh, field, halo_epoch0;
@@ -59,7 +60,6 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
   if (st->done) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsize = (int64_t)gridDim.x * blockDim.x;
-  const int gwarp = (int)blockIdx.x * sell::WARPS + warp, n_warps = (int)gridDim.x * sell::WARPS;
   sell::Ring R = sell::ring_setup(sell_smem, warp, lane);
   const uint64_t policy = sell::evict_first_policy();
   const double tol = st->tol;
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
   int halo_seq = 0;                        // halo exchanges published so far (identical on every rank)
   int pass = 0;                            // matrix passes so far (parity selects the claim counter)
   const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
-  unsigned long long t_acc[4] = {0, 0, 0, 0}, n_cg = 0, n_in = 0, t_last = 0;
+  unsigned long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, n_cg = 0, n_in = 0, t_last = 0, t_mark = 0;
   auto now = [&]() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -82,6 +82,10 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
       t_last = t;
     }
   };
+  // second clock for the waits INSIDE a phase (slots 4..7: barrier behind an inner pass, barrier behind the CG pass, peer
+  // mailboxes, barrier behind the update) — what CTA 0 spends waiting for the slowest warp of the grid / the slowest rank
+  auto mark = [&]() { if (timer) t_mark = now(); };
+  auto since_mark = [&](int slot) { if (timer) t_acc[slot] += now() - t_mark; };
 
   // store v into the ghost copies of (boundary) row `row` on the neighbour ranks
   auto push = [&](int64_t row, double v, size_t off) {
@@ -122,10 +126,9 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
       a.z[i] = zi;
       if (a.n_neigh && i >= a.n_interior) push(i, zi, a.off_z);
     } else {
+      // r = g and z = c0 are not stored: the first inner pass reads g and c0 in their place
       const double ci = a.inv_theta * a.invdiag[i] * gi;
-      a.r[i] = gi;
       a.c0[i] = ci;
-      a.z[i] = ci;
       if (a.n_neigh && i >= a.n_interior) push(i, ci, a.off_c0);
     }
   };
@@ -149,8 +152,8 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
   sell::Stream S;  // the upcoming pass, begun ahead of the barrier in front of it
   auto begin_stream = [&](bool inner) {
     unsigned* ctr = a.work.claim + (pass % 3);
-    if (inner && a.m32.panels) sell::stream_begin<B, TI>(S, a.m32, ctr, gwarp, n_warps, R, lane, policy);
-    else sell::stream_begin<B, double>(S, a.m64, ctr, gwarp, n_warps, R, lane, policy);
+    if (inner && a.m32.panels) sell::stream_begin<B, TI>(S, a.m32, ctr, (int)blockIdx.x, (int)gridDim.x, warp, R, lane, policy);
+    else sell::stream_begin<B, double>(S, a.m64, ctr, (int)blockIdx.x, (int)gridDim.x, warp, R, lane, policy);
   };
 
   // ---- prologue: z (or c0, r) from the start residual; publish its halo
@@ -173,14 +176,16 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
       const double k1 = a.k1[j], k2 = a.k2[j];
       double pr[B], pc[B], pi[B], pz[B];
       begin_pass();
-      auto before = [&](int slice) {
-        halo_wait(slice, m_in);
+      auto ready = [&](int slice) { halo_wait(slice, m_in); };
+      auto pre = [&](int slice) {
         const int64_t brow = (int64_t)slice * 32 + lane;
         if (brow < m_in.n_brows) {
 #pragma unroll
           for (int r = 0; r < B; ++r) {  // epilogue operands: in flight while the slice streams
             const int64_t row = brow * B + r;
-            pr[r] = a.r[row]; pc[r] = cin[row]; pi[r] = a.invdiag[row]; pz[r] = a.z[row];
+            pc[r] = cin[row]; pi[r] = a.invdiag[row];
+            if (j == 1) { pr[r] = a.g[row]; pz[r] = pc[r]; }  // first pass: r = g, z = c0 (never stored as such)
+            else { pr[r] = a.r[row]; pz[r] = a.z[row]; }
           }
         }
       };
@@ -202,11 +207,13 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
           }
         }
       };
-      if (a.m32.panels) sell::stream_run<B, TI>(S, cin, R, lane, policy, before, done);
-      else sell::stream_run<B, double>(S, cin, R, lane, policy, before, done);
+      if (a.m32.panels) sell::stream_run<B, TI>(S, cin, R, lane, policy, ready, pre, done);
+      else sell::stream_run<B, double>(S, cin, R, lane, policy, ready, pre, done);
       ++pass;
       begin_stream(!last_inner);  // the next pass's first copies fly while this warp waits for the slowest one
+      mark();
       barrier(true);
+      since_mark(4);
       if (timer) ++n_in;
       lap(1);
     }
@@ -215,8 +222,8 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
       double pg[B], pz[B];
       sell::Pending pend{0u, -1};
       begin_pass();
-      auto before = [&](int slice) {
-        halo_wait(slice, a.m64);
+      auto ready = [&](int slice) { halo_wait(slice, a.m64); };
+      auto pre = [&](int slice) {
         const int64_t brow = (int64_t)slice * 32 + lane;
         if (brow < a.m64.n_brows) {
 #pragma unroll
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
           v[0] = v[1] = v[2] = 0.0;
         }
       };
-      sell::stream_run<B, double>(S, a.z, R, lane, policy, before, done);
+      sell::stream_run<B, double>(S, a.z, R, lane, policy, ready, pre, done);
       sell::sums_finish<3>(a.work, n_chunks, pend, lane);
       ++pass;
       begin_stream(a.degree > 1);  // first pass of the next iteration (drained below if the solve ends here)
@@ -249,7 +256,9 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
     lap(0);
     if (timer) ++n_cg;
     // ---- the one reduction of the iteration: group totals -> (grid barrier) -> every CTA adds them in the same order
+    mark();
     barrier(false);
+    since_mark(5);
     double tot[3];
     sell::sum_groups<3>(a.work, (n_chunks + 31) >> 5, tot, s_buf);
     if (threadIdx.x < 32) {
@@ -263,8 +272,10 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
           __threadfence_system();
           pe_st_flag(&ctl->red_flag[a.me], e);
         }
+        mark();
         if (lane < a.nranks) good = pcg_wait(&my_ctl->red_flag[lane], e, a.abort);
         good = __all_sync(0xffffffffu, good);
+        since_mark(6);
         __threadfence();  // orders the mailbox loads behind the flag loads (both bypass L1)
         double mail[3];
 #pragma unroll
@@ -336,9 +347,7 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
             if (a.n_neigh && i >= a.n_interior) push(i, zn, a.off_z);
           } else {
             const double cn = a.inv_theta * vi[u] * gn;
-            a.r[i] = gn;
             a.c0[i] = cn;
-            a.z[i] = cn;
             if (a.n_neigh && i >= a.n_interior) push(i, cn, a.off_c0);
           }
         }
@@ -347,7 +356,9 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
     gamma_old = gamma;
     alpha_old = alpha;
     first = false;
+    mark();
     barrier(true);
+    since_mark(7);
     lap(2);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -360,6 +371,10 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
     a.timing[3] += n_in;
     a.timing[4] += t_acc[2];
     a.timing[5] += t_acc[3];
+    a.timing[6] += t_acc[4];
+    a.timing[7] += t_acc[5];
+    a.timing[8] += t_acc[6];
+    a.timing[9] += t_acc[7];
     a.timing[10] = (unsigned long long)halo_seq;
   }
 }

@@ -41,6 +41,15 @@ struct Cfg {
   static constexpr int PANEL = 128 + B * B * 32 * (int)sizeof(T);
   static constexpr int SJ = (B == 1) ? 14 : (STAGE_BYTES / PANEL);  // panels per stage: (3,f64) 3, (3,f32) 6, (2,f64) 6, (2,f32) 12
   static_assert(SJ >= 1 && SJ * PANEL <= STAGE_BYTES, "stage does not fit");
+  // panels per GROUP, the unit of the gather pipeline (stream_run): two groups' gathers are in flight per lane
+  static constexpr int G = (B == 1) ? 7 : (B == 2 && sizeof(T) == 4) ? 6 : 3;
+  static constexpr int NG = SJ / G;
+  static_assert(SJ % G == 0, "a stage is a whole number of groups");
+  // Gather pipeline on/off.  Measured on B200 (C4, C3; profiles/README.md round 2): it lifts the scalar passes (pressure
+  // Jacobian 3.92 -> 4.24 TB/s), which wait on gather latency, and LOWERS the 3x3 block passes (FP64 0.716 -> 0.749 ms,
+  // FP32 0.476 -> 0.545 ms): those are bound by L1/TEX throughput, and looking one stage ahead costs them a stage of TMA depth
+  // (the next stage must have landed before the current one is consumed).
+  static constexpr bool PIPELINED = (B == 1);
 };
 
 struct Mat {
@@ -175,13 +184,13 @@ __device__ __forceinline__ void stream_issue(Stream& S, int st, Ring& R, int lan
     if (++S.q >= S.nq) {  // next chunk
       S.c_cur = S.c_next;
       S.sp_cur = S.sp_next;
-      S.c_next = 2 * S.n_warps + (int)__shfl_sync(0xffffffffu, S.a_nn, 0);
-      S.sp_next = stream_load_ptrs(S, S.c_next, lane);
-      if (S.c_next < S.n_chunks) S.a_nn = stream_claim(S, lane);
-      if (S.c_cur >= S.n_chunks) {
+      if (S.c_cur >= S.n_chunks) {  // checked BEFORE the next claim: a ticket taken by a warp that is done would be a lost chunk
         S.exhausted = true;
         break;
       }
+      S.c_next = 2 * S.n_warps + (int)__shfl_sync(0xffffffffu, S.a_nn, 0);  // a_nn is valid: it was claimed when c_cur proved valid
+      S.sp_next = stream_load_ptrs(S, S.c_next, lane);
+      if (S.c_next < S.n_chunks) S.a_nn = stream_claim(S, lane);
       S.q = 0;
       S.nq = min(S.CH, S.n_slices - S.c_cur * S.CH);
     }
@@ -210,8 +219,19 @@ __device__ __forceinline__ void stream_issue(Stream& S, int st, Ring& R, int lan
   S.f_j += cnt;
 }
 
+// Which chunk a warp starts on: ranks are CTA-major, so the warps of a CTA start on neighbouring slices and share gathered
+// lines in L1.  (Tried and measured on B200, round 2: "even rounds" — parking warps so that n_chunks is a whole number of
+// rounds, 1073 of 1184 warps for the 8582 slices of a 64^3 block — shortens the wait at the barrier behind the inner passes
+// from 8 to 5 us but lengthens every pass by 2.7 us, because the streaming rate follows the number of warps in flight; the
+// spread of the warps' finishing times is about one slice whatever the round structure.  All warps take part.)
+__device__ __forceinline__ void stream_roles(int n_chunks, int cta, int n_ctas, int warp, int& rank, int& n_active) {
+  n_active = min(n_chunks, n_ctas * WARPS);
+  const int q = n_active / n_ctas, rem = n_active % n_ctas;
+  rank = (warp < q + (cta < rem ? 1 : 0)) ? cta * q + min(cta, rem) + warp : -1;
+}
+
 template <int B, typename T>
-__device__ __forceinline__ void stream_begin(Stream& S, const Mat& m, unsigned* claim, int gwarp, int n_warps, Ring& R, int lane, uint64_t policy) {
+__device__ __forceinline__ void stream_begin(Stream& S, const Mat& m, unsigned* claim, int cta, int n_ctas, int warp, Ring& R, int lane, uint64_t policy) {
   typedef Cfg<B, T> C;
   S.panels = m.panels;
   S.slice_ptr = m.slice_ptr;
@@ -219,15 +239,17 @@ __device__ __forceinline__ void stream_begin(Stream& S, const Mat& m, unsigned* 
   S.n_slices = m.n_slices;
   S.CH = m.chunk;
   S.n_chunks = (m.n_slices + m.chunk - 1) / m.chunk;
-  S.n_warps = n_warps;
+  int rank, n_active;
+  stream_roles(S.n_chunks, cta, n_ctas, warp, rank, n_active);
+  S.n_warps = n_active;
   S.panel = C::PANEL;
   S.sj = C::SJ;
   S.resident = m.l2_resident != 0;
-  S.c_cur = gwarp;            // the first two chunks of a warp are static: nothing to wait for at the start of a pass
+  S.c_cur = rank >= 0 ? rank : S.n_chunks;  // the first two chunks of a warp are static: nothing to wait for at the start of a pass
   S.sp_cur = stream_load_ptrs(S, S.c_cur, lane);
-  S.c_next = gwarp + n_warps;
+  S.c_next = rank >= 0 ? rank + n_active : S.n_chunks;
   S.sp_next = stream_load_ptrs(S, S.c_next, lane);
-  S.a_nn = stream_claim(S, lane);  // chunk ids from here on: 2 n_warps + ticket
+  S.a_nn = S.c_next < S.n_chunks ? stream_claim(S, lane) : 0u;  // chunk ids from here on: 2 n_active + ticket
   S.q = -1;
   S.nq = S.c_cur < S.n_chunks ? min(S.CH, S.n_slices - S.c_cur * S.CH) : 0;
   S.exhausted = S.c_cur >= S.n_chunks;
@@ -239,12 +261,93 @@ __device__ __forceinline__ void stream_begin(Stream& S, const Mat& m, unsigned* 
   for (int st = 0; st < NST; ++st) stream_issue(S, st, R, lane, policy);
 }
 
-// Consumes the stream.  `before(slice)` runs once per slice ahead of its first gather (halo wait of boundary slices, epilogue
-// operand prefetch); `done(slice, acc, chunk)` receives the B row sums of block row 32*slice + lane and, when the slice is the
-// last one of its chunk, the chunk's number (else -1): partial sums are formed per CHUNK.  x is gathered with plain cached
-// loads.  All control flow is warp-uniform.
-template <int B, typename T, class Before, class Done>
-__device__ __forceinline__ void stream_run(Stream& S, const double* __restrict__ x, Ring& R, int lane, uint64_t policy, Before&& before, Done&& done) {
+// Consumes the stream.  Hooks, each called once per slice by all lanes (warp-uniform control flow):
+//   ready(slice)  ahead of the slice's first gather (halo wait of boundary slices);
+//   pre(slice)    operand prefetch of the fused epilogue — issued as soon as the PREVIOUS slice's done() has run, i.e. while
+//                 the slice's own first stage is already being gathered, so the loads fly for the whole slice;
+//   done(slice, acc, chunk)  receives the B row sums of block row 32*slice + lane and, when the slice is the last one of its
+//                 chunk, the chunk's number (else -1): partial sums are formed per CHUNK.
+// Software pipeline (scalar matrices, Cfg::PIPELINED): a stage is consumed in GROUPS of Cfg::G panels, and the gathers of the
+// next group (column loads from shared memory, then the x loads) are issued BEFORE the multiply-adds of the current one,
+// across stage and slice boundaries, so a lane always has two groups' gathers in flight.  One CTA per SM has only 8 warps;
+// a scalar pass has one gather per 12 bytes of matrix and was waiting on gather latency (3.9 of 6.5 TB/s at 128^3).
+// x is gathered with plain cached loads.
+template <int B, typename T, class Ready, class Pre, class Done>
+__device__ __forceinline__ void stream_run_pipelined(Stream& S, const double* __restrict__ x, Ring& R, int lane, uint64_t policy, Ready&& ready, Pre&& pre,
+                                                     Done&& done) {
+  typedef Cfg<B, T> C;
+  constexpr int G = C::G, NG = C::NG;
+  constexpr int UNR = ((NST * NG) % 2 == 0) ? NST * NG : 2 * NST * NG;  // whole ring cycles, even (two gather buffers)
+  if (S.d_cnt[0] == 0) return;
+  double acc[B];
+  double xv[2][G][B];
+  // gathers of group g of the stage in ring slot st into buffer buf (all three compile-time after unrolling); panels beyond
+  // the stage's count read nothing and contribute zeros
+  auto fetch = [&](int st, int g, int buf) {
+    if (g == 0) {
+      if (S.d_first[st]) ready(S.d_slice[st]);
+      while (!mbar_try_wait(R.bar + 8 * st, (R.parity >> st) & 1u)) {}
+      R.parity ^= 1u << st;
+    }
+    const int cnt = S.d_cnt[st];
+    const uint32_t sb = R.base + (uint32_t)st * STAGE_BYTES;
+    int col[G];
+#pragma unroll
+    for (int jj = 0; jj < G; ++jj) col[jj] = g * G + jj < cnt ? lds_i32(sb + (g * G + jj) * C::PANEL + lane * 4) : 0;
+#pragma unroll
+    for (int jj = 0; jj < G; ++jj)
+#pragma unroll
+      for (int cc = 0; cc < B; ++cc) xv[buf][jj][cc] = g * G + jj < cnt ? ld_gather(x + (size_t)col[jj] * B + cc) : 0.0;
+  };
+  fetch(0, 0, 0);
+  pre(S.d_slice[0]);
+  bool more = true;
+  while (more) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int st = (u / NG) % NST, g = u % NG, nx = (st + 1) % NST, cur = u & 1;
+      const int cnt = S.d_cnt[st];
+      // the next group's gathers fly during this group's arithmetic
+      if (g + 1 < NG) fetch(st, g + 1, cur ^ 1);
+      else if (S.d_cnt[nx]) fetch(nx, 0, cur ^ 1);
+      if (g == 0 && S.d_first[st]) {
+#pragma unroll
+        for (int r = 0; r < B; ++r) acc[r] = 0.0;
+      }
+      const uint32_t sb = R.base + (uint32_t)st * STAGE_BYTES;
+#pragma unroll
+      for (int jj = 0; jj < G; ++jj) {
+        if (g * G + jj < cnt) {
+#pragma unroll
+          for (int r = 0; r < B; ++r)
+#pragma unroll
+            for (int cc = 0; cc < B; ++cc)
+              acc[r] += lds_val(sb + (g * G + jj) * C::PANEL + 128 + ((r * B + cc) * 32 + lane) * (int)sizeof(T), T()) * xv[cur][jj][cc];
+        }
+      }
+      if (g == NG - 1) {  // the stage is consumed
+        const bool last = S.d_last[st];
+        const int slice = S.d_slice[st], chunk = S.d_cend[st] ? S.d_chunk[st] : -1;
+        const int ncnt = S.d_cnt[nx];
+        __syncwarp();  // every lane has read the stage: lane 0 may re-arm it
+        stream_issue(S, st, R, lane, policy);
+        if (last) {
+          done(slice, acc, chunk);
+          if (ncnt) pre(S.d_slice[nx]);  // the stage after a slice's last one is the first of the next slice
+        }
+        if (!ncnt) {
+          more = false;
+          break;
+        }
+      }
+    }
+  }
+}
+
+// One stage at a time: all gathers of the stage are issued (independent loads in flight), then values + FMAs.
+template <int B, typename T, class Ready, class Pre, class Done>
+__device__ __forceinline__ void stream_run_staged(Stream& S, const double* __restrict__ x, Ring& R, int lane, uint64_t policy, Ready&& ready, Pre&& pre,
+                                                  Done&& done) {
   typedef Cfg<B, T> C;
   double acc[B];
   bool more = true;
@@ -258,14 +361,14 @@ __device__ __forceinline__ void stream_run(Stream& S, const double* __restrict__
       }
       const int cnt = S.d_cnt[st];
       if (S.d_first[st]) {
-        before(S.d_slice[st]);
+        ready(S.d_slice[st]);
+        pre(S.d_slice[st]);
 #pragma unroll
         for (int r = 0; r < B; ++r) acc[r] = 0.0;
       }
       while (!mbar_try_wait(R.bar + 8 * st, (R.parity >> st) & 1u)) {}
       R.parity ^= 1u << st;
       const uint32_t sb = R.base + (uint32_t)st * STAGE_BYTES;
-      // columns, then all gathers of the stage (independent loads in flight), then values + FMAs
       int col[C::SJ];
 #pragma unroll
       for (int jj = 0; jj < C::SJ; ++jj) col[jj] = jj < cnt ? lds_i32(sb + jj * C::PANEL + lane * 4) : 0;
@@ -293,6 +396,13 @@ __device__ __forceinline__ void stream_run(Stream& S, const double* __restrict__
   }
 }
 
+template <int B, typename T, class Ready, class Pre, class Done>
+__device__ __forceinline__ void stream_run(Stream& S, const double* __restrict__ x, Ring& R, int lane, uint64_t policy, Ready&& ready, Pre&& pre,
+                                           Done&& done) {
+  if constexpr (Cfg<B, T>::PIPELINED) stream_run_pipelined<B, T>(S, x, R, lane, policy, ready, pre, done);
+  else stream_run_staged<B, T>(S, x, R, lane, policy, ready, pre, done);
+}
+
 // Waits for the copies of a stream that was begun but is not going to be consumed.
 __device__ __forceinline__ void stream_drain(Stream& S, Ring& R) {
 #pragma unroll
@@ -304,12 +414,12 @@ __device__ __forceinline__ void stream_drain(Stream& S, Ring& R) {
 }
 
 // one pass, start to end (the stand-alone SpMV kernels)
-template <int B, typename T, class Before, class Done>
-__device__ __forceinline__ void stream(const Mat& m, const double* __restrict__ x, unsigned* claim, int gwarp, int n_warps, Ring& R, int lane,
-                                       uint64_t policy, Before&& before, Done&& done) {
+template <int B, typename T, class Ready, class Pre, class Done>
+__device__ __forceinline__ void stream(const Mat& m, const double* __restrict__ x, unsigned* claim, int cta, int n_ctas, int warp, Ring& R, int lane,
+                                       uint64_t policy, Ready&& ready, Pre&& pre, Done&& done) {
   Stream S;
-  stream_begin<B, T>(S, m, claim, gwarp, n_warps, R, lane, policy);
-  stream_run<B, T>(S, x, R, lane, policy, before, done);
+  stream_begin<B, T>(S, m, claim, cta, n_ctas, warp, R, lane, policy);
+  stream_run<B, T>(S, x, R, lane, policy, ready, pre, done);
 }
 
 // Deterministic sums with dynamic work distribution, in two halves so that the atomic's round trip overlaps the next slice:

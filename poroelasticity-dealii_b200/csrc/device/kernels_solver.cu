@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_spmv_sell(SpmvArgs a, sell
   bool waited = false;
   double p0[B], p1[B], p2[B], p3[B];
   sell::Pending pend{0u, -1};
-  auto before = [&](int slice) {
+  auto ready = [&](int slice) {
     // boundary slices gather ghost values: wait (once per warp) until every neighbour's halo of this epoch has landed
     if (a.ctl && !waited && slice >= m.first_boundary_slice) {
       bool ok = true;
@@ -468,6 +468,8 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_spmv_sell(SpmvArgs a, sell
       __threadfence_system();
       waited = true;
     }
+  };
+  auto pre = [&](int slice) {
     // operands of the fused epilogue: requested now, in flight while the slice streams
     const int64_t brow = (int64_t)slice * 32 + lane;
     if (brow < m.n_brows) {
@@ -506,7 +508,7 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_spmv_sell(SpmvArgs a, sell
       v[0] = 0.0;
     }
   };
-  sell::stream<B, T>(m, a.x, w.claim, (int)blockIdx.x * sell::WARPS + warp, (int)gridDim.x * sell::WARPS, R, lane, policy, before, done);
+  sell::stream<B, T>(m, a.x, w.claim, (int)blockIdx.x, (int)gridDim.x, warp, R, lane, policy, ready, pre, done);
   if (EPI == EPI_DOT || EPI == EPI_RESID) sell::sums_finish<1>(w, n_chunks, pend, lane);
   // the last CTA adds the group totals in a fixed order, publishes, and re-arms the claim counter
   __syncthreads();
@@ -935,12 +937,15 @@ void launch_sell_t(pe_ctx* c, const SpmvArgs& a, const sell::Mat& m, const sell:
   k_spmv_sell<B, T, EPI><<<grid, sell::THREADS, sell::SMEM_BYTES, c->stream>>>(a, m, w);
 }
 
-inline sell::Mat sell_mat(const SellMat& S) {
+inline sell::Mat sell_mat(const SellMat& S, int sm_count) {
   const double slice_bytes = (double)S.n_panels * S.panel_bytes / std::max(1, S.n_slices);
   // ~32 KB per claim: the claim's round trip is prefetched (kernels_sell.cuh), so small units cost nothing and keep the
   // end-of-pass tail (at most one unit per warp) short
   static const double chunk_bytes = std::getenv("PE_CHUNK_KB") ? 1024.0 * std::atof(std::getenv("PE_CHUNK_KB")) : 32768.0;
-  const int chunk = (int)std::min(16.0, std::max(1.0, std::floor(chunk_bytes / slice_bytes + 0.5)));
+  int chunk = (int)std::min(16.0, std::max(1.0, std::floor(chunk_bytes / slice_bytes + 0.5)));
+  // small matrices (8-GPU blocks, the pressure matrices of small meshes): at least ~8 claims per warp, or the last round
+  // of claims leaves most of the grid idle (2860 chunks on 1184 warps = 2.4 per warp was 1/3 of the pass lost)
+  chunk = std::max(1, std::min(chunk, S.n_slices / (8 * sm_count * sell::WARPS)));
   static const double l2_mb = std::getenv("PE_L2_RESIDENT_MB") ? std::atof(std::getenv("PE_L2_RESIDENT_MB")) : 64.0;
   const int resident = (double)S.n_panels * S.panel_bytes <= l2_mb * 1048576.0 ? 1 : 0;
   return sell::Mat{S.panels.p, S.slice_ptr.p, S.n_slices, S.first_boundary_slice, chunk, resident, S.n_brows};
@@ -951,7 +956,7 @@ inline sell::Work sell_work(pe_ctx* c, int parity = 0) {
 
 template <int EPI>
 void launch_sell(pe_ctx* c, const SellMat& S, const SpmvArgs& a) {
-  const sell::Mat m = sell_mat(S);
+  const sell::Mat m = sell_mat(S, c->sm_count);
   const sell::Work w = sell_work(c);
   if (S.f32) {  // only the Chebyshev inner passes read the FP32 copy
     if constexpr (EPI == EPI_CHEB) {
@@ -1382,8 +1387,8 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
   if (use_pcg2) {
     P2PField& PF = c->p2p.f[fi];
     Pcg2Args pa{};
-    pa.m64 = sell_mat(*S64);
-    if (S32) pa.m32 = sell_mat(*S32);
+    pa.m64 = sell_mat(*S64, c->sm_count);
+    if (S32) pa.m32 = sell_mat(*S32, c->sm_count);
     pa.work = sell_work(c);
     pa.invdiag = invdiag;
     pa.x = x; pa.g = g; pa.d = d; pa.s = c->w_s.p; pa.w = h; pa.z = z; pa.r = r; pa.c0 = d2; pa.c1 = c->w_c1.p;
@@ -1466,6 +1471,10 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
         c->st.inner_passes_u += (int64_t)h_timing[3];
         c->st.update_ms_u += (double)h_timing[4] * 1e-6;
         c->st.reduce_ms_u += (double)h_timing[5] * 1e-6;
+        c->st.wait_inner_ms_u += (double)h_timing[6] * 1e-6;
+        c->st.wait_cg_ms_u += (double)h_timing[7] * 1e-6;
+        c->st.wait_peer_ms_u += (double)h_timing[8] * 1e-6;
+        c->st.wait_update_ms_u += (double)h_timing[9] * 1e-6;
         const SellMat* Sin = S32 ? S32 : S64;
         c->st.inner_bytes_u = (double)Sin->nnzb * (Sin->B * Sin->B * (Sin->f32 ? 4.0 : 8.0) + 4.0) + (double)Sin->n_slices * 4.0 + (double)n * 56.0;
       }

@@ -303,6 +303,7 @@ int64_t pe_exclusive_scan_i32(pe_ctx* c, int32_t* data, int64_t n);  // in place
 // (Re)builds sell slot `slot` of F from the matrix `val` (CSR for scalar fields, the block-CSR copy otherwise); returns false
 // and clears the slot when padding would cost more than PE_SELL_MAX_PAD (default 1.5) times the real blocks.
 bool pe_build_sell(pe_ctx* c, Field& F, int slot, const double* val, bool f32);
+bool pe_all_ranks_agree(pe_ctx* c, bool mine);  // collective AND of a rank-local flag (kernels_comm.cu)
 
 // ---- kernels_constraints.cu (hanging-node lines; active only when a field has lines with entries)
 void pe_hanging_upload(pe_ctx* c, Field& F);

@@ -265,6 +265,8 @@ inline Part make_part_structured(int dim, const double* size, const int* n_axis,
   // sweep 1
   std::vector<int32_t> vnum((size_t)n_lat, -1);
   std::vector<int8_t> vowner((size_t)n_lat, -1);
+  const bool balanced = balanced_ownership_requested() && nranks > 1;
+  std::vector<uint32_t> vtouch(balanced ? (size_t)n_lat : 0, 0u);  // ranks whose cells touch the vertex
   {
     int32_t next = 0;
     int r = 0;
@@ -278,8 +280,22 @@ inline Part make_part_structured(int dim, const double* size, const int* n_axis,
           vnum[lv] = next++;
           vowner[lv] = (int8_t)r;
         }
+        if (balanced) vtouch[lv] |= 1u << r;
       }
     }
+  }
+  if (balanced) {  // interface vertices are dealt out among the ranks that touch them: the same hash as dof_owner()
+    for (int64_t lv = 0; lv < n_lat; ++lv) {
+      const uint32_t m = vtouch[lv];
+      if ((m & (m - 1)) == 0) continue;  // one toucher
+      int t[32], n = 0;
+      for (int r = 0; r < nranks; ++r)
+        if (m & (1u << r)) t[n++] = r;   // ascending
+      uint64_t h = (uint64_t)vnum[lv] * 0x9e3779b97f4a7c15ull;
+      h ^= h >> 29;
+      vowner[lv] = (int8_t)t[(h >> 8) % (uint64_t)n];
+    }
+    std::vector<uint32_t>().swap(vtouch);
   }
   // sweep 2
   std::vector<uint32_t> cell_mask;  // ranks that keep each local cell

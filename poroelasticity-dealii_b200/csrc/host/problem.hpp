@@ -89,8 +89,7 @@ class PoroElasticProblem {
   // global mesh, no global dof maps.  PE_STRUCTURED_PART=0 forces the general path.
   bool structured_fast_path() const {
     const char* e = std::getenv("PE_STRUCTURED_PART");
-    return nranks > 1 && nranks <= 32 && data.refine_every == 0 && !data.mesh_from_file && data.displacement_degree == 1 &&
-           !partition::balanced_ownership_requested() && !(e && e[0] == '0');
+    return nranks > 1 && nranks <= 32 && data.refine_every == 0 && !data.mesh_from_file && data.displacement_degree == 1 && !(e && e[0] == '0');
   }
   void setup_dofs_structured() {
     int n[3] = {1, 1, 1};

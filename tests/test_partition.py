@@ -250,9 +250,11 @@ class StructuredPart(Part):
 @pytest.mark.parametrize("dim,cells,morton", [(3, [4, 4, 4], True), (3, [8, 8, 8], True), (3, [5, 3, 4], False), (3, [7, 5, 6], False),
                                               (2, [8, 8], True), (2, [6, 4], False), (3, [3, 3, 12], False)])
 @pytest.mark.parametrize("nranks", [2, 3, 4, 8])
-def test_structured_part_equals_the_general_partition(dim, cells, morton, nranks):
+@pytest.mark.parametrize("balanced", [False, True])
+def test_structured_part_equals_the_general_partition(dim, cells, morton, nranks, balanced, monkeypatch):
     """The per-rank structured builder (no global mesh / dof maps on the rank) reproduces make_part() array by array: local
     sub-mesh, cell lists, local numbering [owned interior | owned boundary | ghosts by owner], global ids, send / receive plans."""
+    monkeypatch.setenv("PE_BALANCED_OWNERSHIP", "1" if balanced else "0")
     size = [10.0, 7.0, 13.0][:dim]
     if morton:
         level = int(np.log2(cells[0]))
