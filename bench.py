@@ -526,6 +526,9 @@ def main():
                          "phase_ms_per_step": {"fp64_passes": stats["spmv_ms_u"] / args.steps, "preconditioner_passes": stats["inner_ms_u"] / args.steps,
                                                "vector_updates": stats["update_ms_u"] / args.steps, "reductions": stats["reduce_ms_u"] / args.steps,
                                                "displacement_solves": stats["pcg_ms_u"] / args.steps, "pressure_and_projection_solves": stats["pcg_ms_p"] / args.steps,
+                                               "pressure_and_projection_phases": dict(zip(("cg_pass_streams", "inner_passes", "updates", "reductions", "wait_barrier_inner", "wait_barrier_cg",
+                                                                                           "wait_peer_mailboxes", "wait_barrier_update", "n_cg_passes", "n_inner_passes"),
+                                                                                          [v / args.steps for v in stats["phase_ms_p"]])),
                                                "waits_inside_the_phases": {"barrier_behind_inner_passes": stats["wait_inner_ms_u"] / args.steps,
                                                                            "barrier_behind_cg_pass": stats["wait_cg_ms_u"] / args.steps,
                                                                            "peer_mailboxes": stats["wait_peer_ms_u"] / args.steps,

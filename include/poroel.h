@@ -119,6 +119,9 @@ typedef struct pe_stats {
   /* time CTA 0 of that kernel spent WAITING (a subset of the phase times above): at the grid barrier behind the inner
      passes, at the one behind the CG pass, for the peers' reduction mailboxes, at the barrier behind the updates */
   double  wait_inner_ms_u, wait_cg_ms_u, wait_peer_ms_u, wait_update_ms_u;
+  /* the same clock of the pressure / projection solves: [0] CG passes (own stream), [1] inner passes, [2] updates, [3] reductions,
+     [4..7] the four waits in the order above; [8] number of CG passes, [9] number of inner passes */
+  double  phase_ms_p[10];
 } pe_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------- */

@@ -57,10 +57,11 @@ class PeStats(C.Structure):
         ("inner_ms_u", C.c_double), ("inner_passes_u", C.c_int64), ("inner_bytes_u", C.c_double), ("update_ms_u", C.c_double),
         ("reduce_ms_u", C.c_double), ("sell_format_u", C.c_int64),
         ("wait_inner_ms_u", C.c_double), ("wait_cg_ms_u", C.c_double), ("wait_peer_ms_u", C.c_double), ("wait_update_ms_u", C.c_double),
+        ("phase_ms_p", C.c_double * 10),
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if k == "phase_ms_p" else getattr(self, k)) for k, _ in self._fields_}
 
 
 class InputView(C.Structure):
@@ -116,7 +117,7 @@ class StepReport(C.Structure):
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if k == "phase_ms_p" else getattr(self, k)) for k, _ in self._fields_}
 
 
 # symbols declared in include/poroel.h (checked by tests/test_abi.py)

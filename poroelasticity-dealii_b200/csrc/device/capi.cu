@@ -761,6 +761,7 @@ int pe_reset_stats(pe_ctx* c) {
   c->st.pcg_iterations_p = c->st.pcg_iterations_u = 0;
   c->st.inner_ms_u = c->st.update_ms_u = c->st.reduce_ms_u = 0;
   c->st.wait_inner_ms_u = c->st.wait_cg_ms_u = c->st.wait_peer_ms_u = c->st.wait_update_ms_u = 0;
+  for (double& v : c->st.phase_ms_p) v = 0;
   c->st.inner_passes_u = 0;
   PE_LEAVE(c)
 }

@@ -25,7 +25,7 @@
 
 struct Pcg2Args {
   sell::Mat m64, m32;  // m32.panels == nullptr: the inner passes stream m64
-  sell::Work work;     // work.claim points at THREE counters (pass number mod 3)
+  sell::Work work;     // work.claim points at SIX counters: [0..2] claims (pass number mod 3), [3..5] boundary slices completed in that pass
   const double* invdiag;
   double *x, *g, *d, *s, *w, *z, *r, *c0, *c1;
   int64_t n, n_interior;
@@ -36,6 +36,8 @@ struct Pcg2Args {
   unsigned* tickets;          // [1] grid barrier
   int* bar_flag;
   int* abort;
+  unsigned long long* trace;  // diagnostic (PE_PCG_TRACE), else nullptr: 8 words per warp — inner pass 1: start, end of own stream, barrier passed,
+                              // (smid << 32 | slices); the CG pass: the same four.  Overwritten every iteration: the last one survives.
   unsigned long long* timing; // [0] ns in CG passes (CTA 0), [1] CG passes, [2] ns in inner passes, [3] inner passes, [4] ns in updates,
                               // [5] ns in allreduces, [6..9] ns CTA 0 waited at the barrier behind inner passes / behind the CG pass / for the
                               // peer mailboxes / at the barrier behind updates, [10] halo exchanges posted, [11] reductions posted
@@ -84,6 +86,20 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
   };
   // second clock for the waits INSIDE a phase (slots 4..7: barrier behind an inner pass, barrier behind the CG pass, peer
   // mailboxes, barrier behind the update) — what CTA 0 spends waiting for the slowest warp of the grid / the slowest rank
+  unsigned long long* tr = a.trace ? a.trace + ((size_t)blockIdx.x * sell::WARPS + warp) * 8 : nullptr;
+  int tr_slices = 0;
+  auto trace = [&](int slot) {
+    if (tr && lane == 0) {
+      if ((slot & 3) == 3) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        tr[slot] = ((unsigned long long)smid << 32) | (unsigned)tr_slices;
+        tr_slices = 0;
+      } else {
+        tr[slot] = now();
+      }
+    }
+  };
   auto mark = [&]() { if (timer) t_mark = now(); };
   auto since_mark = [&](int slot) { if (timer) t_acc[slot] += now() - t_mark; };
 
@@ -95,9 +111,11 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
       dst[a.push_dest[e]] = v;
     }
   };
-  // grid barrier; with `publish` the releasing CTA also posts the epoch of the halo exchange that the phase just stored
-  auto barrier = [&](bool publish) {
-    const bool remote = publish && a.n_neigh > 0;
+  const int n_boundary_slices = a.m64.n_slices - min(a.m64.first_boundary_slice, a.m64.n_slices);
+  // grid barrier; with `publish` the phase stored a halo: it counts as one more exchange, and unless the phase has already
+  // published it itself (`early`: the matrix passes, see boundary_done) the releasing CTA posts its epoch to the neighbours
+  auto barrier = [&](bool publish, bool early = false) {
+    const bool remote = publish && a.n_neigh > 0 && (!early || n_boundary_slices == 0);
     if (publish) ++halo_seq;
     ++bar_epoch;
     __syncthreads();
@@ -118,6 +136,27 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
       __threadfence();  // acquire (also drops this SM's stale L1 lines)
     }
     __syncthreads();
+  };
+  // Early publication of a matrix pass's halo.  Boundary slices are claimed in the middle of a pass (Mat::boundary_early); a
+  // warp counts the ones it finishes and, when its claims have moved past them (claims only move forward), fences its lanes'
+  // remote stores once and adds its count; the warp that completes the count posts the epoch — inside the pass, not at the
+  // barrier behind it.  The neighbours' next pass then finds the halo long delivered, the barriers need no system-scope fence,
+  // and the only thing that still couples the ranks' clocks is the one reduction per iteration.  Safe to overwrite the
+  // neighbour's ghost segment that early: only boundary slices read ghost columns, and a rank's boundary slices of pass k wait
+  // for the neighbours' epoch of pass k-1, i.e. for the neighbours having finished THEIR boundary slices — their last
+  // readers of the buffer pass k overwrites.
+  int my_boundary = 0;  // boundary slices this warp has finished and not yet reported (warp-uniform)
+  auto boundary_flush = [&]() {  // all lanes; `pass` = the running pass
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_system();  // cumulative over the warp's pushes (ordered by the __syncwarp)
+      if ((int)atomicAdd(&a.work.claim[3 + pass % 3], (unsigned)my_boundary) + my_boundary == n_boundary_slices) {
+        __threadfence_system();
+        for (int q = 0; q < a.n_neigh; ++q)
+          pe_st_flag(&reinterpret_cast<P2PControl*>(a.peer[a.neigh_rank[q]])->halo_flag[a.field][a.me], a.halo_epoch0 + halo_seq + 1);
+      }
+    }
+    my_boundary = 0;
   };
   // first polynomial term from a fresh g_i (Jacobi: the whole preconditioner)
   auto precond_first = [&](int64_t i, double gi) {
@@ -146,7 +185,10 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
   // when it has been idle since pass k-2 ended, and that store is published by the barrier between passes k-1 and k.
   auto begin_pass = [&]() {
     waited = false;
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.work.claim[(pass + 2) % 3] = 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      a.work.claim[(pass + 2) % 3] = 0u;
+      a.work.claim[3 + (pass + 2) % 3] = 0u;  // the previous pass's count of boundary slices
+    }
   };
   const sell::Mat& m_in = a.m32.panels ? a.m32 : a.m64;
   sell::Stream S;  // the upcoming pass, begun ahead of the barrier in front of it
@@ -190,6 +232,7 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
         }
       };
       auto done = [&](int slice, double (&acc)[B], int) {
+        ++tr_slices;
         const int64_t brow = (int64_t)slice * 32 + lane;
         if (brow < m_in.n_brows) {
 #pragma unroll
@@ -206,14 +249,22 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
             }
           }
         }
+        if (a.n_neigh) {
+          if (slice >= m_in.first_boundary_slice) ++my_boundary;
+          else if (my_boundary) boundary_flush();  // first interior slice behind the boundary ones
+        }
       };
+      if (j == 1) trace(0);
       if (a.m32.panels) sell::stream_run<B, TI>(S, cin, R, lane, policy, ready, pre, done);
       else sell::stream_run<B, double>(S, cin, R, lane, policy, ready, pre, done);
+      if (my_boundary) boundary_flush();
+      if (j == 1) trace(1);
       ++pass;
       begin_stream(!last_inner);  // the next pass's first copies fly while this warp waits for the slowest one
       mark();
-      barrier(true);
+      barrier(true, true);
       since_mark(4);
+      if (j == 1) { trace(2); trace(3); } else tr_slices = 0;
       if (timer) ++n_in;
       lap(1);
     }
@@ -232,6 +283,7 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
       };
       double v[3] = {0.0, 0.0, 0.0};  // this lane's contributions to the current chunk's partial sums
       auto done = [&](int slice, double (&acc)[B], int chunk) {
+        ++tr_slices;
         const int64_t brow = (int64_t)slice * 32 + lane;
         if (brow < a.m64.n_brows) {
 #pragma unroll
@@ -248,8 +300,10 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
           v[0] = v[1] = v[2] = 0.0;
         }
       };
+      trace(4);
       sell::stream_run<B, double>(S, a.z, R, lane, policy, ready, pre, done);
       sell::sums_finish<3>(a.work, n_chunks, pend, lane);
+      trace(5);
       ++pass;
       begin_stream(a.degree > 1);  // first pass of the next iteration (drained below if the solve ends here)
     }
@@ -259,6 +313,8 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
     mark();
     barrier(false);
     since_mark(5);
+    trace(6);
+    trace(7);
     double tot[3];
     sell::sum_groups<3>(a.work, (n_chunks + 31) >> 5, tot, s_buf);
     if (threadIdx.x < 32) {
@@ -317,12 +373,16 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
     const double alpha = first ? gamma / delta : gamma / (delta - beta * gamma / alpha_old);
     // four rows per thread and trip: all 28 loads are issued before the first use (one CTA per SM has only 8 warps to
     // hide DRAM latency with)
+    // boundary rows first (multi-GPU): their remote stores are long acknowledged when the system-scope fence of the barrier
+    // behind this phase asks for them
+    const int64_t rot = a.n_neigh ? a.n_interior : 0;
+    auto rotated = [&](int64_t i) { const int64_t r = i + rot; return r >= a.n ? r - a.n : r; };
     for (int64_t i0 = gtid; i0 < a.n; i0 += 4 * gsize) {
       double zi[4], wi[4], di[4], si[4], xi[4], gi[4], vi[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int64_t i = i0 + u * gsize;
-        const bool in = i < a.n;
+        const bool in = i0 + u * gsize < a.n;
+        const int64_t i = in ? rotated(i0 + u * gsize) : 0;
         zi[u] = in ? a.z[i] : 0.0;
         wi[u] = in ? a.w[i] : 0.0;
         di[u] = (in && !first) ? a.d[i] : 0.0;
@@ -333,8 +393,8 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int64_t i = i0 + u * gsize;
-        if (i < a.n) {
+        if (i0 + u * gsize < a.n) {
+          const int64_t i = rotated(i0 + u * gsize);
           const double dn = beta * di[u] - zi[u], sn = beta * si[u] - wi[u];
           const double gn = gi[u] + alpha * sn;
           a.d[i] = dn;
@@ -362,9 +422,7 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
     lap(2);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    a.work.claim[0] = 0u;
-    a.work.claim[1] = 0u;
-    a.work.claim[2] = 0u;
+    for (int q = 0; q < 6; ++q) a.work.claim[q] = 0u;
     a.timing[0] += t_acc[0];
     a.timing[1] += n_cg;
     a.timing[2] += t_acc[1];

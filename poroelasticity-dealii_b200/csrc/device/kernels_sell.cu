@@ -100,7 +100,7 @@ bool pe_build_sell(pe_ctx* c, Field& F, int slot, const double* val, bool f32) {
     c->red.gpart.alloc((size_t)PE_SELL_NV * c->red.gcap);
     c->red.gcnt.alloc_zero((size_t)c->red.gcap, c->stream);
   }
-  if (!c->red.claim.p) c->red.claim.alloc_zero(3, c->stream);
+  if (!c->red.claim.p) c->red.claim.alloc_zero(6, c->stream);
   PE_CUDA(cudaStreamSynchronize(c->stream));
   return true;
 }

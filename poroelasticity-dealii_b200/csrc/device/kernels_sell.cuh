@@ -59,6 +59,9 @@ struct Mat {
   int first_boundary_slice;  // slices before this one reference no ghost column
   int chunk;                 // slices per claim (~64 KB of panels), 1..16
   int l2_resident;           // the panels are small enough to live in L2 between passes: no evict-first hint
+  int boundary_early;        // multi-GPU: claim order [interior | boundary | interior] with the boundary slices ending at ~70 % of the
+                             // pass instead of [interior | boundary]: the halo they produce leaves well before the pass ends, and the
+                             // halo they consume (published at the end of the phase before) has ~60 % of a pass to arrive
   int64_t n_brows;
 };
 
@@ -160,7 +163,8 @@ struct Stream {
   const int32_t* slice_ptr;
   unsigned* claim;
   int n_slices, CH, n_chunks, n_warps, panel, sj;
-  int c_cur, c_next, sp_cur, sp_next, q, nq;
+  int v_a, v_nb, v_fb;       // claim order -> slice: [0, v_a) | [v_fb, v_fb + v_nb) | [v_a, v_fb)   (identity when v_a == v_fb)
+  int c_cur, c_next, sp_cur, sp_cur_e, sp_next, sp_next_e, q, nq;
   unsigned a_nn;
   bool exhausted;
   int f_slice, f_j, f_np;  // fetch cursor: slice, next panel, panels of the slice
@@ -170,9 +174,18 @@ struct Stream {
   bool resident;
 };
 
-__device__ __forceinline__ int stream_load_ptrs(const Stream& S, int chunk, int lane) {  // lane q: slice_ptr[first slice of the chunk + q], q <= CH
-  const int s = chunk * S.CH + lane;
-  return (chunk < S.n_chunks && lane <= S.CH) ? S.slice_ptr[min(s, S.n_slices)] : 0;
+__device__ __forceinline__ int stream_map(const Stream& S, int v) {  // position in the claim order -> slice
+  return v < S.v_a ? v : (v < S.v_a + S.v_nb ? S.v_fb + (v - S.v_a) : v - S.v_nb);
+}
+// lane q < CH: first panel (and one past the last) of the q-th slice of the chunk
+__device__ __forceinline__ void stream_load_ptrs(const Stream& S, int chunk, int lane, int& b, int& e) {
+  const int v = chunk * S.CH + lane;
+  b = e = 0;
+  if (chunk < S.n_chunks && lane < S.CH && v < S.n_slices) {
+    const int s = stream_map(S, v);
+    b = S.slice_ptr[s];
+    e = S.slice_ptr[s + 1];
+  }
 }
 __device__ __forceinline__ unsigned stream_claim(const Stream& S, int lane) {
   unsigned v = 0;
@@ -184,18 +197,19 @@ __device__ __forceinline__ void stream_issue(Stream& S, int st, Ring& R, int lan
     if (++S.q >= S.nq) {  // next chunk
       S.c_cur = S.c_next;
       S.sp_cur = S.sp_next;
+      S.sp_cur_e = S.sp_next_e;
       if (S.c_cur >= S.n_chunks) {  // checked BEFORE the next claim: a ticket taken by a warp that is done would be a lost chunk
         S.exhausted = true;
         break;
       }
       S.c_next = 2 * S.n_warps + (int)__shfl_sync(0xffffffffu, S.a_nn, 0);  // a_nn is valid: it was claimed when c_cur proved valid
-      S.sp_next = stream_load_ptrs(S, S.c_next, lane);
+      stream_load_ptrs(S, S.c_next, lane, S.sp_next, S.sp_next_e);
       if (S.c_next < S.n_chunks) S.a_nn = stream_claim(S, lane);
       S.q = 0;
       S.nq = min(S.CH, S.n_slices - S.c_cur * S.CH);
     }
-    S.f_slice = S.c_cur * S.CH + S.q;
-    const int p0 = __shfl_sync(0xffffffffu, S.sp_cur, S.q), p1 = __shfl_sync(0xffffffffu, S.sp_cur, S.q + 1);
+    S.f_slice = stream_map(S, S.c_cur * S.CH + S.q);
+    const int p0 = __shfl_sync(0xffffffffu, S.sp_cur, S.q), p1 = __shfl_sync(0xffffffffu, S.sp_cur_e, S.q);
     S.f_base = p0;
     S.f_np = p1 - p0;
     S.f_j = 0;
@@ -245,10 +259,13 @@ __device__ __forceinline__ void stream_begin(Stream& S, const Mat& m, unsigned* 
   S.panel = C::PANEL;
   S.sj = C::SJ;
   S.resident = m.l2_resident != 0;
+  S.v_fb = min(m.first_boundary_slice, m.n_slices);
+  S.v_nb = m.n_slices - S.v_fb;
+  S.v_a = m.boundary_early ? max(0, min(S.v_fb, (int)(0.7f * (float)m.n_slices) - S.v_nb)) : S.v_fb;
   S.c_cur = rank >= 0 ? rank : S.n_chunks;  // the first two chunks of a warp are static: nothing to wait for at the start of a pass
-  S.sp_cur = stream_load_ptrs(S, S.c_cur, lane);
+  stream_load_ptrs(S, S.c_cur, lane, S.sp_cur, S.sp_cur_e);
   S.c_next = rank >= 0 ? rank + n_active : S.n_chunks;
-  S.sp_next = stream_load_ptrs(S, S.c_next, lane);
+  stream_load_ptrs(S, S.c_next, lane, S.sp_next, S.sp_next_e);
   S.a_nn = S.c_next < S.n_chunks ? stream_claim(S, lane) : 0u;  // chunk ids from here on: 2 n_active + ticket
   S.q = -1;
   S.nq = S.c_cur < S.n_chunks ? min(S.CH, S.n_slices - S.c_cur * S.CH) : 0;

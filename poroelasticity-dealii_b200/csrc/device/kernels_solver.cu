@@ -943,12 +943,13 @@ inline sell::Mat sell_mat(const SellMat& S, int sm_count) {
   // end-of-pass tail (at most one unit per warp) short
   static const double chunk_bytes = std::getenv("PE_CHUNK_KB") ? 1024.0 * std::atof(std::getenv("PE_CHUNK_KB")) : 32768.0;
   int chunk = (int)std::min(16.0, std::max(1.0, std::floor(chunk_bytes / slice_bytes + 0.5)));
-  // small matrices (8-GPU blocks, the pressure matrices of small meshes): at least ~8 claims per warp, or the last round
-  // of claims leaves most of the grid idle (2860 chunks on 1184 warps = 2.4 per warp was 1/3 of the pass lost)
-  chunk = std::max(1, std::min(chunk, S.n_slices / (8 * sm_count * sell::WARPS)));
+  // small matrices: never fewer chunks than warps.  (Measured, round 2: asking for ~8 chunks per warp instead — single-slice
+  // chunks for the pressure matrices of a 64^3 block — made their CG pass slower, 0.038 -> 0.042 ms: every chunk ends with a
+  // release + ticket for the deterministic sums, and a scalar slice is only 10 KB.)
+  chunk = std::max(1, std::min(chunk, S.n_slices / (sm_count * sell::WARPS)));
   static const double l2_mb = std::getenv("PE_L2_RESIDENT_MB") ? std::atof(std::getenv("PE_L2_RESIDENT_MB")) : 64.0;
   const int resident = (double)S.n_panels * S.panel_bytes <= l2_mb * 1048576.0 ? 1 : 0;
-  return sell::Mat{S.panels.p, S.slice_ptr.p, S.n_slices, S.first_boundary_slice, chunk, resident, S.n_brows};
+  return sell::Mat{S.panels.p, S.slice_ptr.p, S.n_slices, S.first_boundary_slice, chunk, resident, 0, S.n_brows};
 }
 inline sell::Work sell_work(pe_ctx* c, int parity = 0) {
   return sell::Work{c->red.claim.p + parity, c->red.spart.p, c->red.gcnt.p, c->red.gpart.p, c->red.cap, c->red.gcap};
@@ -1389,6 +1390,8 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
     Pcg2Args pa{};
     pa.m64 = sell_mat(*S64, c->sm_count);
     if (S32) pa.m32 = sell_mat(*S32, c->sm_count);
+    static const bool early_off = std::getenv("PE_HALO_EARLY") && std::string(std::getenv("PE_HALO_EARLY")) == "0";
+    pa.m64.boundary_early = pa.m32.boundary_early = (multi && F.halo.n_neigh > 0 && !early_off) ? 1 : 0;
     pa.work = sell_work(c);
     pa.invdiag = invdiag;
     pa.x = x; pa.g = g; pa.d = d; pa.s = c->w_s.p; pa.w = h; pa.z = z; pa.r = r; pa.c0 = d2; pa.c1 = c->w_c1.p;
@@ -1410,6 +1413,12 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
     pa.bar_flag = c->pcg_flags.p;
     pa.abort = c->pcg_flags.p + 1;
     pa.timing = c->pcg_timing.p;
+    static const char* trace_prefix = std::getenv("PE_PCG_TRACE");
+    const size_t trace_words = (size_t)c->sm_count * sell::WARPS * 8;
+    if (trace_prefix && fi == 1) {
+      if (!c->pcg_trace.p) c->pcg_trace.alloc_zero(trace_words, c->stream);
+      pa.trace = c->pcg_trace.p;
+    }
     pa.peer = c->p2p.d_peer.p;
     pa.nranks = c->nranks;
     pa.me = c->rank;
@@ -1448,9 +1457,18 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
     const CgState last = c->h_state[0];
     if (last.pad) {  // a wait timed out: barriers, claim counters and group counters may be half-used; start clean next time
       PE_CUDA(cudaMemsetAsync(c->pcg_tickets.p, 0, 4 * sizeof(unsigned), c->stream));
-      PE_CUDA(cudaMemsetAsync(c->red.claim.p, 0, 3 * sizeof(unsigned), c->stream));
+      PE_CUDA(cudaMemsetAsync(c->red.claim.p, 0, 6 * sizeof(unsigned), c->stream));
       PE_CUDA(cudaMemsetAsync(c->red.gcnt.p, 0, (size_t)c->red.gcap * sizeof(unsigned), c->stream));
       PE_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (pa.trace) {  // diagnostic dump: <prefix>_rank<r>.bin, 8 u64 per warp (kernels_pcg2.cuh), last iteration of this solve
+      std::vector<unsigned long long> h(trace_words);
+      PE_CUDA(cudaMemcpy(h.data(), c->pcg_trace.p, trace_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      const std::string path = std::string(trace_prefix) + "_rank" + std::to_string(c->rank) + ".bin";
+      if (FILE* f = std::fopen(path.c_str(), "wb")) {
+        std::fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+        std::fclose(f);
+      }
     }
     c->p2p.red_epoch += (unsigned)h_timing[11];  // identical on every rank
     if (multi) PF.epoch += (unsigned)h_timing[10];
@@ -1466,6 +1484,12 @@ CgResult pe_cg_solve(pe_ctx* c, Field& F, const double* val, const double* invdi
       // in-kernel %globaltimer of CTA 0: the FP64 CG passes including the reduction that ends them
       (fi ? c->st.spmv_ms_u : c->st.spmv_ms_p) += (double)(h_timing[0] + h_timing[5]) * 1e-6;
       (fi ? c->st.spmv_timed_u : c->st.spmv_timed_p) += (int64_t)h_timing[1];
+      if (!fi) {
+        const int src[8] = {0, 2, 4, 5, 6, 7, 8, 9};
+        for (int k = 0; k < 8; ++k) c->st.phase_ms_p[k] += (double)h_timing[src[k]] * 1e-6;
+        c->st.phase_ms_p[8] += (double)h_timing[1];
+        c->st.phase_ms_p[9] += (double)h_timing[3];
+      }
       if (fi) {
         c->st.inner_ms_u += (double)h_timing[2] * 1e-6;
         c->st.inner_passes_u += (int64_t)h_timing[3];

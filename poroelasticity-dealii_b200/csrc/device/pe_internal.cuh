@@ -169,7 +169,7 @@ struct Reducer {
   DBuf<unsigned> counter;  // 1
   DBuf<double> out;        // PE_RED_SLOTS (+ scratch)
   // deterministic sums of the dynamically distributed sliced kernels (kernels_sell.cuh): per-slice and per-group slots
-  DBuf<unsigned> claim;    // 3 (the persistent kernel rotates them by pass number)
+  DBuf<unsigned> claim;    // 6: three claim counters the persistent kernel rotates by pass number + three counts of finished boundary slices
   DBuf<double> spart, gpart;
   DBuf<unsigned> gcnt;
   int cap = 0, gcap = 0;   // slices / groups the slot arrays hold
@@ -268,6 +268,7 @@ struct pe_ctx {
   DBuf<unsigned> pcg_tickets;
   DBuf<int> pcg_flags;
   DBuf<unsigned long long> pcg_timing;
+  DBuf<unsigned long long> pcg_trace;  // PE_PCG_TRACE=<file prefix>: per-warp timestamps of the last passes of a displacement solve (diagnostic)
   int pcg_grid[2] = {0, 0};  // cooperative grid size per field (0 = not queried yet)
   double pcg_phase_ns[2][8] = {{0}};  // CTA-0 sub-phase times of the persistent kernel (printed with PE_PCG_TIMING=1)
   long long pcg_phase_its[2] = {0, 0};

@@ -47,7 +47,7 @@ def test_device_library_is_sm100a_only_and_has_no_oracle_dependency():
 def test_struct_layouts_match_the_header():
     # sizes computed from the C declarations (8-byte aligned PODs)
     assert C.sizeof(capi.PeParams) == 8 * 4 + 12 * 8
-    assert C.sizeof(capi.PeStats) == 14 * 8 + 6 * 8 + 4 * 8 + 4 * 8 + 8 + 6 * 8
+    assert C.sizeof(capi.PeStats) == 14 * 8 + 6 * 8 + 4 * 8 + 4 * 8 + 8 + 6 * 8 + 4 * 8 + 10 * 8
 
 
 def test_product_fails_loudly_without_a_gpu():
