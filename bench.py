@@ -291,7 +291,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--refine", type=int, default=None)
     ap.add_argument("--precond", type=int, default=1, help="0 Jacobi, 1 Chebyshev-Jacobi polynomial (default)")
-    ap.add_argument("--cheb-degree", type=int, default=3)
+    ap.add_argument("--cheb-degree", type=int, default=4)
     ap.add_argument("--eig-ratio", type=float, default=30.0)
     ap.add_argument("--max-its", type=int, default=4000)
     ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4", "c5"],

@@ -322,14 +322,23 @@ void pe_comm_setup(pe_ctx* c, size_t n_work) {
         if (P.push_ok) {
           for (int64_t r = 0; r < n_b; ++r) ptr[r + 1] += ptr[r];
           std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+          std::vector<unsigned long long> paddr((size_t)ns);
+          std::vector<int32_t> psrc((size_t)ns);
+          const int64_t per_slice = 32 * (int64_t)F.ncomp;
           for (int64_t i = 0; i < ns; ++i) {
-            const int32_t at = fill[h_idx[i] - F.n_interior]++;
+            const int64_t rel = h_idx[i] - F.n_interior;
+            const int32_t at = fill[rel]++;
             pdest[at] = dest[i];
             pnb[at] = nb[i];
+            // resolved once: the kernels store through one table load instead of chasing neighbour slot -> rank -> region
+            paddr[at] = (unsigned long long)(uintptr_t)(M.peer[H.rank[nb[i]]] + M.ctrl_bytes) + 8ull * (unsigned long long)dest[i];
+            psrc[at] = (int32_t)(rel % per_slice);
           }
           P.push_ptr.upload(ptr, s);
           P.push_dest.upload(pdest, s);
           P.push_nb.upload(pnb, s);
+          P.push_addr.upload(paddr, s);
+          P.push_src.upload(psrc, s);
         }
       }
     }

@@ -48,6 +48,8 @@ struct Pcg2Args {
   const int32_t* push_ptr;    // per boundary row (row - n_interior): its entries in push_dest / push_nb
   const int32_t* push_dest;   // index in the receiver's vector
   const int32_t* push_nb;     // neighbour slot
+  const unsigned long long* push_addr;  // the same entry resolved: address of the ghost copy in the receiver's first work vector
+  const int32_t* push_src;    // lane * B + component of the entry's row inside its slice
   size_t ctrl_bytes, off_z, off_c0, off_c1;  // offsets (in doubles) of the exchanged vectors inside every rank's work area
   int max_iterations;
 };
@@ -103,12 +105,32 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
   auto mark = [&]() { if (timer) t_mark = now(); };
   auto since_mark = [&](int slot) { if (timer) t_acc[slot] += now() - t_mark; };
 
-  // store v into the ghost copies of (boundary) row `row` on the neighbour ranks
+  // store v into the ghost copies of (boundary) row `row` on the neighbour ranks (the vector phases: one row per thread)
   auto push = [&](int64_t row, double v, size_t off) {
     const int64_t k = row - a.n_interior;
-    for (int e = a.push_ptr[k]; e < a.push_ptr[k + 1]; ++e) {
-      double* dst = reinterpret_cast<double*>(a.peer[a.neigh_rank[a.push_nb[e]]] + a.ctrl_bytes) + off;
-      dst[a.push_dest[e]] = v;
+    for (int e = a.push_ptr[k]; e < a.push_ptr[k + 1]; ++e) reinterpret_cast<double*>(a.push_addr[e])[off] = v;
+  };
+  // the same for a whole boundary slice of a matrix pass, by the warp that owns it: the slice's entries are contiguous in the
+  // table, the lanes take them 32 at a time (one coalesced table load, the value fetched from the lane that holds the row) —
+  // a handful of independent stores per lane instead of every lane walking its rows' entries one dependent load after another
+  auto push_slice = [&](int slice, const double (&v)[B], size_t off) {
+    const int per = 32 * B;
+    const int64_t n_b = a.n - a.n_interior;
+    const int64_t k0 = (int64_t)(slice - a.m64.first_boundary_slice) * per;
+    const int e0 = a.push_ptr[k0], e1 = a.push_ptr[min(k0 + per, n_b)];
+    for (int eb = e0; eb < e1; eb += 32) {
+      const int e = eb + lane;
+      const bool on = e < e1;
+      const int src = on ? a.push_src[e] : 0;
+      const unsigned long long addr = on ? a.push_addr[e] : 0ull;
+      const int sl = src / B, sr = src - sl * B;
+      double val = 0.0;
+#pragma unroll
+      for (int r = 0; r < B; ++r) {
+        const double t = __shfl_sync(0xffffffffu, v[r], sl);
+        if (r == sr) val = t;
+      }
+      if (on) reinterpret_cast<double*>(addr)[off] = val;
     }
   };
   const int n_boundary_slices = a.m64.n_slices - min(a.m64.first_boundary_slice, a.m64.n_slices);
@@ -234,6 +256,9 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
       auto done = [&](int slice, double (&acc)[B], int) {
         ++tr_slices;
         const int64_t brow = (int64_t)slice * 32 + lane;
+        double out[B];  // what the neighbours need of this row: the next pass's input
+#pragma unroll
+        for (int r = 0; r < B; ++r) out[r] = 0.0;
         if (brow < m_in.n_brows) {
 #pragma unroll
           for (int r = 0; r < B; ++r) {
@@ -244,14 +269,16 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
             a.r[row] = rn;
             cout[row] = cn;
             a.z[row] = zn;
-            if (a.n_neigh && row >= a.n_interior) {
-              if (last_inner) push(row, zn, a.off_z); else push(row, cn, off_out);
-            }
+            out[r] = last_inner ? zn : cn;
           }
         }
         if (a.n_neigh) {
-          if (slice >= m_in.first_boundary_slice) ++my_boundary;
-          else if (my_boundary) boundary_flush();  // first interior slice behind the boundary ones
+          if (slice >= m_in.first_boundary_slice) {
+            push_slice(slice, out, last_inner ? a.off_z : off_out);
+            ++my_boundary;
+          } else if (my_boundary) {
+            boundary_flush();  // first interior slice behind the boundary ones
+          }
         }
       };
       if (j == 1) trace(0);

@@ -196,6 +196,8 @@ struct P2PField {
   // the same plan indexed by the SOURCE row (boundary rows only, row - n_interior): the persistent CG kernel lets the
   // thread that produces an entry store it to the neighbours itself
   DBuf<int32_t> push_ptr, push_dest, push_nb;
+  DBuf<unsigned long long> push_addr;  // per entry: address of the ghost copy inside the owner-of-the-copy's FIRST work vector (add the vector's offset)
+  DBuf<int32_t> push_src;              // per entry: (row - n_interior) mod (32 * ncomp) = lane * ncomp + component inside its slice
   bool push_ok = false;      // every sent row is a boundary row (>= n_interior); true for symmetric patterns
   unsigned epoch = 0;        // halo exchanges posted so far
 };

@@ -36,13 +36,13 @@ def _worker(rank, world, nccl_id, text, q, cwd=None):
 
 
 @pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("case", ["3d_q1_morton", "3d_q1_ragged", "2d_q2", "3d_q1_jacobi", "3d_q1_general_partition", "3d_q1_balanced"])
+@pytest.mark.parametrize("case", ["3d_q1_morton", "3d_q1_ragged", "2d_q2", "3d_q1_jacobi", "3d_q1_general_partition", "3d_q1_lowest_rank_owns"])
 def test_partitioned_run_matches_single_gpu_and_oracle(world, case):
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     kw = {"3d_q1_morton": dict(dim=3, refine=3, degree_u=1), "3d_q1_ragged": dict(dim=3, refine=2, degree_u=1, cells=[7, 5, 6]),
           "2d_q2": dict(dim=2, refine=4, degree_u=2), "3d_q1_jacobi": dict(dim=3, refine=4, degree_u=1),
-          "3d_q1_general_partition": dict(dim=3, refine=3, degree_u=1), "3d_q1_balanced": dict(dim=3, refine=3, degree_u=1)}[case]
+          "3d_q1_general_partition": dict(dim=3, refine=3, degree_u=1), "3d_q1_lowest_rank_owns": dict(dim=3, refine=3, degree_u=1)}[case]
     extra = "  set CG max iterations = 5000\n"
     if case == "3d_q1_jacobi":  # the other cases run the default: Chebyshev polynomial with FP32 inner passes, one halo per pass
         extra += "  set Preconditioner = 0\n"
@@ -50,7 +50,7 @@ def test_partitioned_run_matches_single_gpu_and_oracle(world, case):
     # Q1 boxes build their parts from the lattice (partition.hpp::make_part_structured); one case keeps the general path covered
     os.environ["PE_STRUCTURED_PART"] = "0" if case == "3d_q1_general_partition" else "1"
     # interface nodes dealt out among the ranks that touch them (partition.hpp::balanced_ownership_requested), structured builder
-    os.environ["PE_BALANCED_OWNERSHIP"] = "1" if case == "3d_q1_balanced" else "0"
+    os.environ["PE_BALANCED_OWNERSHIP"] = "1" if case == "3d_q1_lowest_rank_owns" else "0"
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
