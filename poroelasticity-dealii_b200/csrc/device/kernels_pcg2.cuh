@@ -60,10 +60,13 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
   __shared__ double s_buf[4 * 32];
   __shared__ double s_tot[4];
   __shared__ int s_ok;
+  __shared__ int s_halo_seen;  // newest halo epoch a warp of this CTA has waited for AND acquired (system-scope fence)
   CgState* st = a.state;
   if (st->done) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsize = (int64_t)gridDim.x * blockDim.x;
+  if (threadIdx.x == 0) s_halo_seen = a.halo_epoch0;
+  __syncthreads();
   sell::Ring R = sell::ring_setup(sell_smem, warp, lane);
   const uint64_t policy = sell::evict_first_policy();
   const double tol = st->tol;
@@ -171,9 +174,12 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
   auto boundary_flush = [&]() {  // all lanes; `pass` = the running pass
     __syncwarp();
     if (lane == 0) {
-      __threadfence_system();  // cumulative over the warp's pushes (ordered by the __syncwarp)
-      if ((int)atomicAdd(&a.work.claim[3 + pass % 3], (unsigned)my_boundary) + my_boundary == n_boundary_slices) {
-        __threadfence_system();
+      // release at system scope, cumulative over the warp's pushes (ordered by the __syncwarp) — as an atomic, not a fence: a
+      // fence is also an acquire and would drop this SM's L1 once per warp and pass
+      unsigned old;
+      asm volatile("atom.release.sys.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(a.work.claim + 3 + pass % 3), "r"((unsigned)my_boundary) : "memory");
+      if ((int)old + my_boundary == n_boundary_slices) {
+        __threadfence_system();  // acquire of the other warps' releases (once per pass), then publish
         for (int q = 0; q < a.n_neigh; ++q)
           pe_st_flag(&reinterpret_cast<P2PControl*>(a.peer[a.neigh_rank[q]])->halo_flag[a.field][a.me], a.halo_epoch0 + halo_seq + 1);
       }
@@ -193,12 +199,25 @@ __global__ void __launch_bounds__(sell::THREADS, 1) k_pcg2(Pcg2Args a) {
       if (a.n_neigh && i >= a.n_interior) push(i, ci, a.off_c0);
     }
   };
+  // The acquire behind a halo flag is a system-scope fence, which drops the whole SM's L1 — all eight warps' cached lines of
+  // the gathered vector, not only the ghost segment.  So the first warp of the CTA that needs an epoch waits and fences, then
+  // leaves the epoch in shared memory; the others find it there and order themselves behind it with a CTA-scope fence (the
+  // L1 is the SM's: lines fetched after the first warp's fence are fresh for every warp).
   bool waited = false;
   auto halo_wait = [&](int slice, const sell::Mat& m) {
     if (a.n_neigh && !waited && slice >= m.first_boundary_slice) {
-      if (lane < a.n_neigh) pcg_wait(&my_ctl->halo_flag[a.field][a.neigh_rank[lane]], a.halo_epoch0 + halo_seq, a.abort);
-      __syncwarp();
-      __threadfence_system();  // acquire; drops stale L1 lines of the ghost segment
+      const int need = a.halo_epoch0 + halo_seq;
+      int seen = 0;
+      if (lane == 0) seen = *(volatile int*)&s_halo_seen;
+      seen = __shfl_sync(0xffffffffu, seen, 0);
+      if ((int)(seen - need) < 0) {
+        if (lane < a.n_neigh) pcg_wait(&my_ctl->halo_flag[a.field][a.neigh_rank[lane]], need, a.abort);
+        __syncwarp();
+        __threadfence_system();  // acquire; drops stale L1 lines of the ghost segment
+        if (lane == 0) *(volatile int*)&s_halo_seen = need;  // every writer of an epoch writes the same value
+      } else {
+        __threadfence_block();
+      }
       waited = true;
     }
   };
