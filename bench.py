@@ -40,7 +40,11 @@ sys.path.insert(0, str(ROOT))
 METRIC = "fixed_stress_time_steps_per_second"
 UNIT = "steps/s"
 PARITY_TOL = 1e-8
-WORKLOADS = {"c4": 7, "c3": 6}  # refine level of the cube workloads
+
+
+def golden_tag(args):
+    """Name of the recorded oracle run of a workload under tests/golden (None: the CPU oracle cannot hold it, no record)."""
+    return {"c2": f"c2_r{args.refine}", "c3": f"r{args.refine}", "c4": f"r{args.refine}"}.get(args.workload)
 
 
 def input_text(args, world):
@@ -116,32 +120,33 @@ class ClockSampler:
 COUNT_KEYS = ("pressure_iterations", "cg_its_pressure", "cg_its_displacement", "cg_its_projection")
 
 
-def golden_record(refine):
-    p = ROOT / "tests" / "golden" / f"oracle_counts_r{refine}.json"
-    return json.loads(p.read_text()) if p.exists() else None
+def golden_record(tag):
+    p = ROOT / "tests" / "golden" / f"oracle_counts_{tag}.json"
+    return json.loads(p.read_text()) if tag and p.exists() else None
 
 
-def golden_counts(refine, steps):
+def golden_counts(tag, steps):
     """Oracle iteration counts of TIME STEPS 1..steps (the bench's pinned window), per step.  Steps beyond the end of the
     record repeat its last step (flagged: the counts only fall as the transient decays, so this cannot flatter the GPU)."""
-    rec = golden_record(refine)
+    rec = golden_record(tag)
     if rec is None:  # no record at this size: scale the largest recorded mesh with 2^levels (kappa ~ h^-1 at best); flagged
-        for r in range(refine - 1, 3, -1):
-            if golden_record(r) is not None:
-                g = golden_counts(r, steps)
-                f = 2.0 ** (refine - r)
+        stem, refine = tag.rsplit("r", 1)
+        for r in range(int(refine) - 1, 3, -1):
+            if golden_record(f"{stem}r{r}") is not None:
+                g = golden_counts(f"{stem}r{r}", steps)
+                f = 2.0 ** (int(refine) - r)
                 per = [{k: (s[k] * f if k.startswith("cg_its_p") or k == "cg_its_displacement" else s[k]) for k in COUNT_KEYS} for s in g["per_step"]]
                 return {"per_step": per, "recorded_steps": 0, "source": g["source"] + f" x{f:g} (extrapolated in mesh size)", "extrapolated": True}
-        raise RuntimeError("no oracle count record under tests/golden")
+        raise RuntimeError(f"no oracle count record for {tag} under tests/golden")
     rs = rec["steps"]
     per = [{k: rs[min(i, len(rs) - 1)][k] for k in COUNT_KEYS} for i in range(steps)]
-    return {"per_step": per, "recorded_steps": len(rs), "source": f"oracle_counts_r{refine}.json steps 1..{min(steps, len(rs))}"
+    return {"per_step": per, "recorded_steps": len(rs), "source": f"oracle_counts_{tag}.json steps 1..{min(steps, len(rs))}"
             + ("" if steps <= len(rs) else f", steps {len(rs) + 1}..{steps} repeat step {len(rs)}"), "extrapolated": steps > len(rs)}
 
 
-def golden_fields(refine):
-    p = ROOT / "tests" / "golden" / f"oracle_fields_r{refine}.npz"
-    return np.load(p) if p.exists() else None
+def golden_fields(tag):
+    p = ROOT / "tests" / "golden" / f"oracle_fields_{tag}.npz"
+    return np.load(p) if tag and p.exists() else None
 
 
 def oracle_setup(args, threads):
@@ -216,7 +221,7 @@ def extrapolation_check(args, threads):
     few-iteration sample is from a real run."""
     a3 = argparse.Namespace(**vars(args))
     a3.workload, a3.refine = "c3", 6
-    counts = golden_counts(6, 1)
+    counts = golden_counts("r6", 1)
     _, thr, detail, _ = cpu_sample(a3, threads, counts)
     H, b, inp, prm, thr, _ = oracle_setup(a3, threads)
     prm.cg_max_iterations = 4000
@@ -242,8 +247,10 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    refine = args.refine
-    counts = golden_counts(refine, args.steps)
+    if golden_tag(args) is None:
+        print(json.dumps({"impl": "reference", "unavailable": f"no recorded oracle run for workload {args.workload} (a full CPU step at this size takes hours)"}), flush=True)
+        return
+    counts = golden_counts(golden_tag(args), args.steps)
     vals, thr, detail = [], 0, None
     for _ in range(max(1, min(args.steps, 2))):  # each sample is bounded; two are enough for a stable number
         v, thr, detail, _ = cpu_sample(args, cores, counts)
@@ -367,8 +374,8 @@ def main():
             be._ck(lib.pe_set_vector(be.ctx, which, ptr(src[k]), n), "set_vector")
 
     # ---- parity record: sample dofs this rank owns
-    gold_f = golden_fields(args.refine) if args.workload in WORKLOADS else None
-    gold_c = golden_record(args.refine) if args.workload in WORKLOADS else None
+    gold_f = golden_fields(golden_tag(args))
+    gold_c = golden_record(golden_tag(args))
     sample = None
     if gold_f is not None:
         gp, gu = prob.global_ids(capi.FIELD_PRESSURE), prob.global_ids(capi.FIELD_DISPLACEMENT)
@@ -472,7 +479,7 @@ def main():
                 worst = max(worst, *errs.values())
                 n_cmp += 1
             parity = {"checked": n_cmp > 0, "parity_max_rel": worst if n_cmp else None, "tolerance": PARITY_TOL, "steps_compared": n_cmp,
-                      "samples": int(gold_f["p"].shape[1]), "against": f"tests/golden/oracle_counts_r{args.refine}.json + oracle_fields_r{args.refine}.npz (CPU oracle, SSOR-CG)",
+                      "samples": int(gold_f["p"].shape[1]), "against": f"tests/golden/oracle_counts_{golden_tag(args)}.json + oracle_fields_{golden_tag(args)}.npz (CPU oracle, SSOR-CG)",
                       "per_step": per if len(per) <= 4 else per[:2] + per[-2:], "ok": bool(n_cmp == 0 or worst <= PARITY_TOL)}
             if n_cmp and worst > PARITY_TOL:
                 rc = 3
@@ -545,9 +552,9 @@ def main():
                                     "fp64_pass_equivalents_u": (stats["spmv_timed_u"] + stats["inner_passes_u"] * (stats["inner_bytes_u"] / stats["spmv_bytes_u"] if stats["spmv_bytes_u"] else 1.0)) / args.steps},
             "init_s": t_init, "setup_ms": stats["setup_ms"],
         }
-        if world == 1 and not args.no_cpu_baseline and args.workload in WORKLOADS:
+        if world == 1 and not args.no_cpu_baseline and golden_tag(args) is not None:
             try:
-                counts = golden_counts(args.refine, args.steps)
+                counts = golden_counts(golden_tag(args), args.steps)
                 v, thr, detail, _ = cpu_sample(args, os.cpu_count() or 1, counts)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample_text(counts), "detail": detail}
             except Exception as exc:  # the baseline must never take the GPU number down with it
