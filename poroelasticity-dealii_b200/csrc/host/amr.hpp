@@ -157,6 +157,11 @@ struct Forest {
     if (!cells[c].active || cells[c].dead) throw std::runtime_error("amr: refine of a non-active cell");
     const int nv = vpc();
     const int32_t first = (int32_t)cells.size();
+    // every vertex of the 3^dim lattice is looked up (line / quad maps) or created once, at its first use by a child — the
+    // creation order of new vertices is that of the children's corners, as it always was
+    const int n_lat = dim == 2 ? 9 : 27;
+    int32_t lat[27];
+    for (int i = 0; i < n_lat; ++i) lat[i] = -1;
     Cell kids[8];
     for (int ci = 0; ci < nv; ++ci) {
       Cell& k = kids[ci];
@@ -166,15 +171,17 @@ struct Forest {
       for (int v = 0; v < nv; ++v) {
         int idx[3] = {0, 0, 0};
         for (int a = 0; a < dim; ++a) idx[a] = ((ci >> a) & 1) + ((v >> a) & 1);
-        k.v[v] = lattice_vertex(c, idx);
+        int32_t& lv = lat[idx[0] + 3 * idx[1] + 9 * idx[2]];
+        if (lv < 0) lv = lattice_vertex(c, idx);
+        k.v[v] = lv;
       }
       for (int f = 0; f < 2 * dim; ++f) k.bid[f] = (((ci >> (f / 2)) & 1) == (f % 2)) ? cells[c].bid[f] : -1;
     }
     // solution transfer: vertices that carried no dof get the parent's Q1 interpolant (mean of the parent entity)
     if (n_transfer)
-      for (int i = 0; i < (dim == 2 ? 9 : 27); ++i) {
+      for (int i = 0; i < n_lat; ++i) {
         int idx[3] = {i % 3, (i / 3) % 3, dim == 3 ? i / 9 : 0};
-        const int32_t v = lattice_vertex(c, idx);
+        const int32_t v = lat[i];
         if (vknown[v]) continue;
         int n = 0;
         double acc[MAX_TRANSFER] = {0};
@@ -224,55 +231,101 @@ struct Forest {
     std::vector<int32_t> half;           // 2 per line: id of the half line or -1
     int64_t n_lines() const { return (int64_t)ptr.size() - 1; }
   };
+  // Built concurrently: the keys of all (cell, line) pairs are computed once and bucketed by a hash of the key (a counting
+  // sort that keeps the cell order inside a bucket); every bucket is searched by one thread for the FIRST pair of each key.
+  // Lines are then numbered in the order of their first pair, i.e. in cell order — the numbering a serial first-seen sweep
+  // gives, whatever the number of threads, and the one that keeps the members of consecutive lines close in memory for the
+  // closure sweeps of prepare().
+  static constexpr int N_LINE_SHARDS = 64;
+  static int line_shard(const dofs::EntityKey& k) {
+    const uint64_t h = (uint64_t)k.first * 0xd6e8feb86659fd93ull + (uint64_t)k.second * 0xa0761d6478bd642full;
+    return (int)((h >> 40) & (N_LINE_SHARDS - 1));
+  }
   LineTable line_table() const {
     dofs::RefElement ref = dofs::make_ref_element(dim, 1);
     const int nl = (int)ref.lines.size();
-    dofs::FlatMap<int32_t> line_id;
     std::vector<int32_t> act;
     for (size_t i = 0; i < cells.size(); ++i)
       if (cells[i].active && !cells[i].dead) act.push_back((int32_t)i);
-    line_id.reserve(act.size() * (dim == 2 ? 2 : 3) + 16);
-    std::vector<int32_t> cell_line(act.size() * nl), count;
-    std::vector<dofs::EntityKey> keys;
-    for (size_t i = 0; i < act.size(); ++i) {
+    const int64_t na = (int64_t)act.size(), nk = na * nl;
+    if (nk >= (int64_t)1 << 31) throw std::runtime_error("amr: too many cells for 32-bit line slots");
+    std::vector<dofs::EntityKey> key((size_t)nk);
+    std::vector<uint8_t> shard((size_t)nk);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < na; ++i) {
       const Cell& c = cells[act[i]];
       for (int l = 0; l < nl; ++l) {
-        const dofs::EntityKey k = dofs::edge_key(c.v[ref.lines[l][0]], c.v[ref.lines[l][1]]);
-        auto it = line_id.find(k);
-        int32_t id;
-        if (it == line_id.end()) {
-          id = (int32_t)keys.size();
-          line_id[k] = id;
-          keys.push_back(k);
-          count.push_back(0);
-        } else
-          id = it->second;
-        cell_line[i * nl + l] = id;
-        count[id]++;
+        key[(size_t)i * nl + l] = dofs::edge_key(c.v[ref.lines[l][0]], c.v[ref.lines[l][1]]);
+        shard[(size_t)i * nl + l] = (uint8_t)line_shard(key[(size_t)i * nl + l]);
       }
     }
+    std::vector<int64_t> bptr(N_LINE_SHARDS + 1, 0);
+    for (int64_t q = 0; q < nk; ++q) bptr[shard[q] + 1]++;
+    for (int sh = 0; sh < N_LINE_SHARDS; ++sh) bptr[sh + 1] += bptr[sh];
+    std::vector<int32_t> bucket((size_t)nk);
+    {
+      std::vector<int64_t> fill_pos(bptr.begin(), bptr.end() - 1);
+      for (int64_t q = 0; q < nk; ++q) bucket[fill_pos[shard[q]]++] = (int32_t)q;
+    }
+    // pass 1: the first pair of every key (buckets keep the cell order, so the first hit in a bucket is the first overall)
+    std::vector<dofs::FlatMap<int32_t>> first_of(N_LINE_SHARDS);  // key -> its first pair q
+    std::vector<int32_t> slot_line((size_t)nk);                    // pair -> first pair of its key, later the line number
+    std::vector<int32_t> number((size_t)nk + 1, 0);                // 1 at first pairs, then their exclusive prefix sum
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int sh = 0; sh < N_LINE_SHARDS; ++sh) {
+      dofs::FlatMap<int32_t>& M = first_of[sh];
+      M.reserve((size_t)(bptr[sh + 1] - bptr[sh]) / (dim == 2 ? 2 : 4) + 64);
+      for (int64_t b = bptr[sh]; b < bptr[sh + 1]; ++b) {
+        const int32_t q = bucket[b];
+        auto it = M.find(key[q]);
+        if (it == M.end()) { M[key[q]] = q; slot_line[q] = q; number[q + 1] = 1; }
+        else slot_line[q] = it->second;
+      }
+    }
+    for (int64_t q = 0; q < nk; ++q) number[q + 1] += number[q];  // number[q] = line number of the key whose first pair is q
+    const int64_t n_lines = number[nk];
     LineTable T;
-    T.ptr.assign(keys.size() + 1, 0);
-    for (size_t l = 0; l < keys.size(); ++l) T.ptr[l + 1] = T.ptr[l] + count[l];
-    T.members.resize(T.ptr.back());
-    std::vector<int32_t> fill(T.ptr.begin(), T.ptr.end() - 1);
-    for (size_t i = 0; i < act.size(); ++i)
-      for (int l = 0; l < nl; ++l) T.members[fill[cell_line[i * nl + l]]++] = act[i];
+    T.ptr.assign((size_t)n_lines + 1, 0);
+    std::vector<dofs::EntityKey> line_key((size_t)n_lines);
+    // pass 2: line numbers of all pairs and member counts (all pairs of a key sit in one bucket: no two threads touch a line)
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int sh = 0; sh < N_LINE_SHARDS; ++sh)
+      for (int64_t b = bptr[sh]; b < bptr[sh + 1]; ++b) {
+        const int32_t q = bucket[b], first = slot_line[q], id = number[first];
+        if (first == q) line_key[id] = key[q];
+        slot_line[q] = id;
+        T.ptr[id + 1]++;
+      }
+    for (int64_t l = 0; l < n_lines; ++l) T.ptr[l + 1] += T.ptr[l];
+    T.members.resize((size_t)T.ptr.back());
+    // pass 3: members, in cell order inside every line
+    {
+      std::vector<int32_t> fill(T.ptr.begin(), T.ptr.end() - 1);
+#pragma omp parallel for schedule(dynamic, 1)
+      for (int sh = 0; sh < N_LINE_SHARDS; ++sh)
+        for (int64_t b = bptr[sh]; b < bptr[sh + 1]; ++b) {
+          const int32_t q = bucket[b];
+          T.members[fill[slot_line[q]]++] = act[q / nl];
+        }
+    }
     // a line can only have a used midpoint when a finer cell touches one of its ends
     std::vector<int8_t> vmax(n_vertices(), -1);
     for (int32_t ci : act)
       for (int k = 0; k < vpc(); ++k) vmax[cells[ci].v[k]] = std::max<int8_t>(vmax[cells[ci].v[k]], (int8_t)cells[ci].level);
-    T.half.assign(2 * keys.size(), -1);
-    for (size_t l = 0; l < keys.size(); ++l) {
+    auto line_number = [&](const dofs::EntityKey& k) -> int32_t {
+      const dofs::FlatMap<int32_t>& M = first_of[line_shard(k)];
+      auto it = M.find(k);
+      return it == M.end() ? -1 : number[it->second];
+    };
+    T.half.assign(2 * (size_t)n_lines, -1);
+#pragma omp parallel for schedule(static)
+    for (int64_t l = 0; l < n_lines; ++l) {
       const int lev = cells[T.members[T.ptr[l]]].level;
-      const int64_t ends[2] = {keys[l].first, keys[l].second};
+      const int64_t ends[2] = {line_key[l].first, line_key[l].second};
       if (vmax[ends[0]] <= lev && vmax[ends[1]] <= lev) continue;
-      auto mid = edge_mid.find(keys[l]);
+      auto mid = edge_mid.find(line_key[l]);
       if (mid == edge_mid.end()) continue;
-      for (int e = 0; e < 2; ++e) {
-        auto h = line_id.find(dofs::edge_key(ends[e], mid->second));
-        if (h != line_id.end()) T.half[2 * l + e] = h->second;
-      }
+      for (int e = 0; e < 2; ++e) T.half[2 * l + e] = line_number(dofs::edge_key(ends[e], mid->second));
     }
     return T;
   }
