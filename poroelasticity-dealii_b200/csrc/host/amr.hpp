@@ -68,11 +68,17 @@ struct Forest {
   }
 
   // active cells in deal.II's iteration order: level by level
-  std::vector<int32_t> active_cells() const {
-    std::vector<int32_t> a;
+  std::vector<int32_t> active_cells() const {  // a counting sort by level: stable, so creation order inside a level
+    std::vector<int64_t> start(2, 0);
+    for (const Cell& c : cells)
+      if (c.active && !c.dead) {
+        if ((size_t)c.level + 2 > start.size()) start.resize((size_t)c.level + 2, 0);
+        start[c.level + 1]++;
+      }
+    for (size_t l = 1; l < start.size(); ++l) start[l] += start[l - 1];
+    std::vector<int32_t> a((size_t)start.back());
     for (size_t i = 0; i < cells.size(); ++i)
-      if (cells[i].active && !cells[i].dead) a.push_back((int32_t)i);
-    std::stable_sort(a.begin(), a.end(), [&](int32_t x, int32_t y) { return cells[x].level < cells[y].level; });
+      if (cells[i].active && !cells[i].dead) a[start[cells[i].level]++] = (int32_t)i;
     return a;
   }
   int n_levels() const {
@@ -565,31 +571,40 @@ inline double det_inv_T(int dim, const double* J, double* JiT) {  // J[a*dim+b] 
   return det;
 }
 
-// Q1 geometry and field gradient of one cell at a reference point
-inline double cell_gradient(const Forest& F, const Cell& c, const double* xi, const double* vertex_value, double* grad, double* JiT) {
-  const int dim = F.dim, vpc = 1 << dim;
+// Q1 geometry and field gradient of one cell at a reference point.  The dimension is a template parameter so that the
+// loops unroll (the estimator evaluates this eight times per interior face); the order of the floating-point operations
+// is the same for both instantiations as in a plain loop over (vertex, axis), so the indicators do not depend on it.
+template <int DIM>
+inline double cell_gradient_t(const Forest& F, const Cell& c, const double* xi, const double* vertex_value, double* grad, double* JiT) {
+  constexpr int vpc = 1 << DIM;
+  double w[DIM][2];
+  for (int b = 0; b < DIM; ++b) { w[b][0] = 1 - xi[b]; w[b][1] = xi[b]; }
   double J[9] = {0}, gref[3] = {0, 0, 0};
   for (int v = 0; v < vpc; ++v) {
-    double dN[3];
-    for (int a = 0; a < dim; ++a) {
+    double dN[DIM];
+    for (int a = 0; a < DIM; ++a) {
       double g = ((v >> a) & 1) ? 1.0 : -1.0;
-      for (int b = 0; b < dim; ++b)
-        if (b != a) g *= ((v >> b) & 1) ? xi[b] : 1 - xi[b];
+      for (int b = 0; b < DIM; ++b)
+        if (b != a) g *= w[b][(v >> b) & 1];
       dN[a] = g;
     }
-    const double* X = &F.xyz[(int64_t)c.v[v] * dim];
-    for (int a = 0; a < dim; ++a) {
-      gref[a] += vertex_value[c.v[v]] * dN[a];
-      for (int b = 0; b < dim; ++b) J[a * dim + b] += X[a] * dN[b];
+    const double* X = &F.xyz[(int64_t)c.v[v] * DIM];
+    const double val = vertex_value[c.v[v]];
+    for (int a = 0; a < DIM; ++a) {
+      gref[a] += val * dN[a];
+      for (int b = 0; b < DIM; ++b) J[a * DIM + b] += X[a] * dN[b];
     }
   }
-  const double det = det_inv_T(dim, J, JiT);
-  for (int a = 0; a < dim; ++a) {
+  const double det = det_inv_T(DIM, J, JiT);
+  for (int a = 0; a < DIM; ++a) {
     double s = 0;
-    for (int b = 0; b < dim; ++b) s += JiT[a * dim + b] * gref[b];
+    for (int b = 0; b < DIM; ++b) s += JiT[a * DIM + b] * gref[b];
     grad[a] = s;
   }
   return det;
+}
+inline double cell_gradient(const Forest& F, const Cell& c, const double* xi, const double* vertex_value, double* grad, double* JiT) {
+  return F.dim == 2 ? cell_gradient_t<2>(F, c, xi, vertex_value, grad, JiT) : cell_gradient_t<3>(F, c, xi, vertex_value, grad, JiT);
 }
 
 // parametric position of vertex v inside face f of cell N (corner, line midpoint or face centre)

@@ -38,5 +38,18 @@ int main(int argc, char** argv) {
   t = clk::now(); F.prepare(); printf("prepare %.2f\n", since(t));
   t = clk::now(); auto r = F.execute(); printf("execute %.2f (coarsened %d refined %d)\n", since(t), r.first, r.second);
   t = clk::now(); am = F.active_mesh(); printf("active_mesh %.2f (%lld cells)\n", since(t), (long long)am.n_cells());
+  // setup_dofs() of the new mesh (problem.hpp): numbering of both handlers, hanging-node + Dirichlet tables, flattening
+  dofs::NodeMaps mp, mu;
+  t = clk::now(); dofs::DofMap np_ = dofs::distribute_dofs(am, 1, 1, &mp); dofs::DofMap nu = dofs::distribute_dofs(am, 1, 3, &mu);
+  printf("distribute_dofs p+u %.2f (%lld + %lld dofs)\n", since(t), (long long)np_.n_dofs, (long long)nu.n_dofs);
+  std::vector<int32_t> ld, ed; std::vector<int64_t> ep; std::vector<double> ew, lg;
+  t = clk::now();
+  dofs::ConstraintTable tp; tp.init(np_.n_dofs); amr::hanging_node_constraints(F, am, np_, mp, tp); tp.close(); tp.flatten(ld, ep, ed, ew, lg);
+  printf("constraints p %.2f (%zu lines)\n", since(t), ld.size());
+  t = clk::now();
+  dofs::ConstraintTable tu; tu.init(nu.n_dofs); amr::hanging_node_constraints(F, am, nu, mu, tu);
+  dofs::add_dirichlet(tu, am, nu, {0, 1, 2, 3, 4, 5}, {0, 0, 1, 1, 2, 2}, {0, -1e-5, 0, -1e-5, 0, -1e-5});
+  tu.close(); tu.flatten(ld, ep, ed, ew, lg);
+  printf("constraints u %.2f (%zu lines)\n", since(t), ld.size());
   return 0;
 }
