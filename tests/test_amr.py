@@ -533,3 +533,20 @@ def test_random_refine_coarsen_sequences_keep_every_invariant(dim, seed):
             v[d] = v[ed] @ ew
         samples = fe_eval_on_lattice(m, d2, v, 2)
         assert max(max(vals) - min(vals) for vals in samples.values()) < 1e-12
+
+
+def test_refinement_pass_does_not_depend_on_the_thread_count(tmp_path):
+    """The estimator's face table and the 2:1 closure's line table are built by all host threads (hash buckets, one thread per
+    bucket).  Everything a pass produces — indicators, line numbering, the executed mesh, transferred values, constraint lines —
+    has to be the same bytes for 1, 3 and 8 threads (tests/amr_dump.cpp)."""
+    import subprocess
+    exe = tmp_path / "amr_dump"
+    subprocess.check_call(["g++", "-O2", "-fopenmp", "-std=c++17", "-o", str(exe), str(H.ROOT / "tests" / "amr_dump.cpp")])
+    for dim, base in ((2, 4), (3, 3)):
+        dumps = []
+        for threads in (1, 3, 8):
+            out = tmp_path / f"dump_{dim}_{threads}.bin"
+            subprocess.check_call([str(exe), str(dim), str(base), str(out)], env={"OMP_NUM_THREADS": str(threads), "PATH": "/usr/bin:/bin"},
+                                  stdout=subprocess.DEVNULL)
+            dumps.append(out.read_bytes())
+        assert len(dumps[0]) > 100000 and dumps[0] == dumps[1] == dumps[2]
