@@ -1,0 +1,148 @@
+"""Golden vectors produced by THE REFERENCE'S OWN CODE: runs oracle/_ref/fss_ref — the unmodified sources of
+/root/reference/lib/include compiled against the deal.II API shim of oracle/dealii_shim (NOT deal.II; oracle/Makefile, target
+`ref`) with oracle/ref_main.cpp as the missing Runner.cpp — on a handful of parameter files, and records what
+`PoroElasticProblem<dim>::run()` prints and writes:
+
+  reference_run_<case>.json   the parameter file, the loop's own prints per time step ("pressure converged; iterations", "Solution
+                              limits", "Error", FSS:368-405) and the iteration count + final residual of every CG solve in call
+                              order (the shim's solver log; the reference's own prints of them are commented out)
+  reference_run_<case>.npz    every vector handed to DataOut at FSS:411 (p, u, projected strains, stresses) after every time
+                              step, dof by dof, with the support point of each dof
+
+Every run ends before the reference's first mesh refinement (time step 5, FSS:333), which the shim does not provide.
+/root/reference exists only in the build container, so the records are committed; tests/test_reference_run.py compares the CPU
+oracle with them and tests/test_zzz_gpu_reference_run.py the CUDA path.   usage: python tests/golden/make_reference_run.py"""
+import json
+import re
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parents[1]
+
+SHIPPED = (Path("/root/reference/input.data").read_text() if Path("/root/reference/input.data").exists() else "")
+
+PROPERTIES = """
+subsection Properties
+  set Young modulus         = {E}
+  set Biot coefficient      = {biot}
+  set Bulk density          = 2700
+  set Fluid compressibility = 5.8e-10
+  set Permeability          = {perm}
+  set Poisson ratio         = {nu}
+  set Porosity              = 0.3
+  set Viscosity             = 1e-3
+  set Well radius           = {rw}
+  set Flow rate             = {q}
+end
+"""
+
+
+def text(dim, size, refine, dirichlet, neumann=("", "", ""), dt=60, steps=3, E="1.4e10", biot="0.9", perm="10", nu="0.3", rw="1", q="1e-5"):
+    return f"""
+subsection Mesh
+  set Dimensions               = {dim}
+  set Domain size              = {size}
+  set Initial refinement level = {refine}
+  set Max refinement level     = 6
+end
+subsection In situ
+  set Displacement boundary labels     = {dirichlet[0]}
+  set Displacement boundary components = {dirichlet[1]}
+  set Displacement boundary values     = {dirichlet[2]}
+  set Initial pressure                 = 10e6
+  set Stress boundary labels           = {neumann[0]}
+  set Stress boundary components       = {neumann[1]}
+  set Stress boundary values           = {neumann[2]}
+end
+{PROPERTIES.format(E=E, biot=biot, perm=perm, nu=nu, rw=rw, q=q)}
+subsection Solver
+  set Time step  = {dt}
+  set Time max   = {dt * steps}
+end
+"""
+
+
+CASES = {
+    # the reference's input.data exactly as shipped, cut to the four time steps before its first refinement
+    "shipped_4steps": lambda: SHIPPED.replace("set Time max   = 1e3", "set Time max   = 240"),
+    # 3D (the reference's well source is written for 2D but compiles for 3D in release mode; Q2 displacement, 512 cells)
+    "box3d_r3": lambda: text(3, "10, 10, 10", 3, ("0, 1, 2, 3, 4, 5", "0, 0, 1, 1, 2, 2", "0, -1e-5, 0, -1e-5, 0, -1e-5"), steps=3),
+    # BASELINE configs[1] in small: traction on the top face (DS:249-277), rollers elsewhere
+    "neumann2d_r4": lambda: text(2, "10, 10", 4, ("0, 1, 2", "0, 0, 1", "0, 0, 0"), ("3", "1", "-1e6"), steps=3),
+    # anisotropic cells, other material, a condition list in which two conditions claim the corner dofs (first one wins)
+    "rect2d_r3": lambda: text(2, "10, 6", 3, ("3, 2, 0, 1, 0", "1, 1, 0, 0, 1", "-2e-5, 0, 0, 1e-5, 0"), dt=30, steps=4, E="2.1e10", biot="0.8",
+                              perm="25", nu="0.25", rw="1.5", q="2e-5"),
+}
+
+
+def parse_dump(path, dim):
+    fields, cur = {}, None
+    for line in Path(path).read_text().splitlines():
+        if line.startswith("#"):
+            continue
+        if line.startswith("field "):
+            _, name, _, ncomp, _, ndofs = line.split()
+            while name in fields:   # FSS:262 adds stresses[0] twice (as sigma_xx and as sigma_yy); names are kept as printed
+                name += "'"
+            cur = fields[name] = {"n_comp": int(ncomp), "rows": []}
+            continue
+        cur["rows"].append([float(x) for x in line.split()])
+    out = {}
+    for name, f in fields.items():
+        a = np.array(f["rows"])
+        out[name] = {"x": a[:, :dim], "comp": a[:, dim].astype(np.int32), "v": a[:, dim + 1]}
+    return out
+
+
+def run_case(name, exe):
+    inp = CASES[name]()
+    dim = int(re.search(r"set Dimensions\s*=\s*(\d)", inp).group(1))
+    with tempfile.TemporaryDirectory() as tmp:
+        tmp = Path(tmp)
+        (tmp / "solution").mkdir()
+        (tmp / "input.data").write_text(inp)
+        env = {"DEALII_SHIM_SOLVER_LOG": str(tmp / "solver.log"), "PATH": "/usr/bin:/bin"}
+        res = subprocess.run([str(exe), "input.data"], cwd=tmp, env=env, capture_output=True, text=True, timeout=3600)
+        if res.returncode != 0:
+            raise RuntimeError(f"{name}: fss_ref failed: {res.stderr[-2000:]}")
+        steps, cur = [], None
+        for line in res.stdout.splitlines():
+            line = line.strip()
+            if line.startswith("Time: "):
+                cur = {"time": float(line.split()[1]), "coupling_iterations": 0, "pressure_converged_iterations": [], "solution_limits": [], "error": []}
+                steps.append(cur)
+            elif line.startswith("Coupling iteration:"):
+                cur["coupling_iterations"] += 1
+            elif line.startswith("pressure converged; iterations:"):
+                cur["pressure_converged_iterations"].append(int(line.split()[-1]))
+            elif line.startswith("Solution limits:"):
+                cur["solution_limits"].append(float(line.split()[2]))
+            elif line.startswith("Error:"):
+                cur["error"].append(float(line.split()[1]))
+        cg = [{"n": int(m.group(1)), "its": int(m.group(2)), "res": float(m.group(3))}
+              for m in re.finditer(r"cg n=(\d+) its=(\d+) res=(\S+)", (tmp / "solver.log").read_text())]
+        dumps = [parse_dump(tmp / "solution" / f"solution-{k + 1:04d}.vtk", dim) for k in range(len(steps))]
+    arrays = {}
+    for fname, f in dumps[0].items():
+        arrays[f"{fname}__x"] = f["x"]
+        arrays[f"{fname}__comp"] = f["comp"]
+        arrays[f"{fname}__v"] = np.stack([d[fname]["v"] for d in dumps])
+    np.savez_compressed(HERE / f"reference_run_{name}.npz", **arrays)
+    rec = {"case": name, "dim": dim, "input": inp, "n_steps": len(steps), "steps": steps, "cg_solves": cg, "fields": sorted(dumps[0].keys()),
+           "produced_by": "oracle/_ref/fss_ref = /root/reference/lib/include/*.h (unmodified) + oracle/dealii_shim (deal.II API shim, NOT deal.II) + oracle/ref_main.cpp"}
+    (HERE / f"reference_run_{name}.json").write_text(json.dumps(rec, indent=1))
+    return rec
+
+
+if __name__ == "__main__":
+    subprocess.check_call(["make", "-s", "-C", str(ROOT / "oracle"), "ref"])
+    exe = ROOT / "oracle" / "_ref" / "fss_ref"
+    for name in (sys.argv[1:] or CASES):
+        rec = run_case(name, exe)
+        print(name, "steps", rec["n_steps"], "cg solves", len(rec["cg_solves"]), "its", [c["its"] for c in rec["cg_solves"]][:12], "...",
+              "limits", [s["solution_limits"] for s in rec["steps"]])

@@ -1,0 +1,70 @@
+"""The CPU oracle against golden vectors produced by the reference's own code.
+
+oracle/_ref/fss_ref is /root/reference/lib/include/*.h, unmodified, compiled against the deal.II API shim of oracle/dealii_shim
+(NOT deal.II) with oracle/ref_main.cpp as the Runner.cpp the reference names and does not ship; `PoroElasticProblem<dim>::run()`
+executed in the build container and tests/golden/make_reference_run.py recorded what it prints and writes.  The oracle — the
+restatement every GPU parity test is measured against — has to reproduce those runs: the same dof numbering, the same
+inner-loop counts, the same number of CG iterations in every solve, the numbers the loop prints to all printed digits, and the
+fields to rounding.  (What stays a restatement on both sides is deal.II itself: the shim and the oracle are two readings of its
+documented algorithms by the same author; the poroelastic operators, the loop and their quirks are the reference's own text.)"""
+import numpy as np
+import pytest
+
+import reference_run as R
+from reference_run import capi, fss, H
+
+
+@pytest.mark.parametrize("case", R.CASES)
+def test_oracle_reproduces_the_reference_run(case):
+    rec, gold = R.load(case)
+    dim = rec["dim"]
+    b = H.create_oracle_backend()
+    try:
+        inp, dofs_p, dofs_u = R.problem(rec, b)
+        # deal.II's cell-by-cell first-touch numbering (shim: dof_handler_policy.cc) == the host library's (dofs.hpp)
+        order_p = R.dof_order(gold["p__x"], gold["p__comp"], dofs_p.support_points(), 1)
+        order_u = R.dof_order(gold["u__x"], gold["u__comp"], dofs_u.support_points(), dim)
+        assert np.array_equal(order_p, np.arange(dofs_p.n_dofs)) and np.array_equal(order_u, np.arange(dofs_u.n_dofs))
+        ref_init, ref_steps = R.split_cg_log(rec, dofs_p.n_dofs, dofs_u.n_dofs)
+        init = fss.initialize(b, inp)
+        assert init["cg_its_displacement"] == ref_init["displacement"] and init["cg_its_projection"] == ref_init["projection"]
+        entries = [fss.TENSOR_TO_ENTRY[dim][c] for c in fss.VOLUMETRIC_COMPONENTS[dim]]
+        names = {2: ["eps_xx", "eps_yy"], 3: ["eps_xx", "eps_yy", "eps_zz"]}[dim]
+        for k in range(rec["n_steps"]):
+            rep = fss.time_step(b, inp)
+            printed, cg = rec["steps"][k], ref_steps[k]
+            # control flow of FSS:345-405 and SolverCG / SSOR iteration counts, solve by solve
+            assert rep["fss_iterations"] == printed["coupling_iterations"]
+            assert [n - 1 for n in rep["inner_counts"]] == printed["pressure_converged_iterations"]
+            assert rep["cg_its_pressure"] == sum(cg["pressure"])
+            assert rep["cg_its_displacement"] == cg["displacement"]
+            assert rep["cg_its_projection"] == cg["projection"]
+            # what the loop prints (6 significant digits)
+            assert float(f"{rep['pressure_linfty']:.6g}") == printed["solution_limits"][-1]
+            assert float(f"{rep['pressure_error']:.6g}") == printed["error"][-1]
+            # fields, dof by dof
+            p, u = b.get_vector(capi.VEC_P), b.get_vector(capi.VEC_U)
+            assert fss.rel_l2(p, gold["p__v"][k]) <= 1e-13
+            assert fss.rel_l2(u, gold["u__v"][k]) <= 1e-11
+            for e, name in zip(entries, names):
+                assert fss.rel_l2(b.get_vector(capi.VEC_STRAIN0 + e), gold[f"{name}__v"][k]) <= 1e-10
+            # sigma_xx = lambda tr(eps) + 2 G eps_xx from the projected strains (FSS:189-224); the shear strains stay zero in the
+            # reference as shipped, which the stresses do not see on the diagonal
+            b.effective_stresses()
+            assert fss.rel_l2(b.get_vector(capi.VEC_STRESS0 + 0), gold["sigma_xx__v"][k]) <= 1e-10
+    finally:
+        b.close()
+
+
+def test_reference_run_records_show_the_as_is_quirks():
+    """Things SURVEY §0 reads out of the source, seen here in the reference's own output."""
+    rec, gold = R.load("shipped_4steps")
+    # FSS:262: stresses[0] is written twice, as sigma_xx and as sigma_yy
+    assert np.array_equal(gold["sigma_xx__v"], gold["sigma_yy__v"])
+    # FSS:167-176: the shear projections solve a zero right-hand side, so eps_xy stays zero
+    assert not gold["eps_xy__v"].any()
+    # FSS:399 commented out: one coupling iteration per time step
+    assert all(s["coupling_iterations"] == 1 for s in rec["steps"])
+    # 3D: body force identically zero (right_hand_side.h:76-82 writes component 3 of a 3-vector) — u stays symmetric in z
+    rec3, gold3 = R.load("box3d_r3")
+    assert rec3["dim"] == 3 and np.isfinite(gold3["u__v"]).all()
