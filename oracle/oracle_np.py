@@ -1,7 +1,8 @@
 """oracle_np.py — an INDEPENDENT numpy/scipy restatement of the reference's discrete problem.
 
 TEST INFRASTRUCTURE ONLY (guards the C++ oracle against restatement bugs; deal.II itself
-is not available, so parity is otherwise unpinned).  Deliberately written differently from
+is not available — the reference's own sources run against an API shim, tests/test_reference_run.py, and this file
+is the check that does not share deal.II's algorithms with either).  Deliberately written differently from
 oracle/oracle.cpp and from the CUDA kernels:
 
 * structured box meshes only, nodes keyed by their coordinates (no deal.II numbering at all);

@@ -61,10 +61,14 @@ def upload_problem(backend: capi.OperatorBackend, inp: capi.InputData, mesh: cap
     return dofs_p, dofs_u, (line_dof, g)
 
 
-def get_normal_strain_components(b: capi.OperatorBackend, dim):  # FSS:153-164
+def get_normal_strain_components(b: capi.OperatorBackend, dim, each=None):  # FSS:153-164
+    """returns the CG iterations of the dim projection solves summed; `each` (a list) also receives them one by one"""
     comps = VOLUMETRIC_COMPONENTS[dim]
     b.project_assemble_rhs(comps)
-    return sum(b.project_solve(TENSOR_TO_ENTRY[dim][c]) for c in comps)
+    its = [b.project_solve(TENSOR_TO_ENTRY[dim][c]) for c in comps]
+    if each is not None:
+        each.extend(its)
+    return sum(its)
 
 
 def get_volumetric_strain(b: capi.OperatorBackend, dim, as_initial=False):  # FSS:179-186 (+317)
@@ -86,7 +90,7 @@ def time_step(b: capi.OperatorBackend, inp: capi.InputData, log=None):
     """One pass of FSS:328-407 (as-is semantics)."""
     dt = inp.time_step
     rep = {"fss_iterations": 0, "pressure_iterations": 0, "cg_its_pressure": 0, "cg_its_displacement": 0, "cg_its_projection": 0,
-           "inner_counts": [], "residual_history": []}
+           "inner_counts": [], "residual_history": [], "cg_each": {"pressure": [], "displacement": [], "projection": []}}
     b.pressure_begin_step()  # FSS:342
     pressure_error = inp.pressure_tol * 2  # FSS:345
     fss_iteration = 0
@@ -105,13 +109,16 @@ def time_step(b: capi.OperatorBackend, inp: capi.InputData, log=None):
             b.assemble_jacobian(dt)
             its, _ = b.pressure_solve()
             rep["cg_its_pressure"] += its
+            rep["cg_each"]["pressure"].append(its)
             b.pressure_add_update()  # FSS:379
         rep["inner_counts"].append(pressure_iteration)
         rep["pressure_linfty"] = b.pressure_linfty()
         b.displacement_assemble()  # FSS:395
-        its, _ = b.displacement_solve()
+        its, res = b.displacement_solve()
         rep["cg_its_displacement"] += its
-        rep["cg_its_projection"] += get_normal_strain_components(b, inp.dim)  # FSS:398
+        rep["cg_each"]["displacement"].append(its)
+        rep["displacement_residual"] = res
+        rep["cg_its_projection"] += get_normal_strain_components(b, inp.dim, rep["cg_each"]["projection"])  # FSS:398
         if inp.couple_volumetric_strain:
             get_volumetric_strain(b, inp.dim)  # FSS:399, commented out in the reference
         pressure_error = b.assemble_residual(dt)  # FSS:402-405

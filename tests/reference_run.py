@@ -53,6 +53,6 @@ def split_cg_log(rec, n_p, n_u):
         assert all(c["n"] == n_p for c in pressure + proj + shear) and disp[0]["n"] == n_u
         assert all(c["its"] == 0 and c["res"] == 0.0 for c in shear)  # FSS:167-176 never assembles these right-hand sides
         steps.append({"pressure": [c["its"] for c in pressure], "displacement": disp[0]["its"], "displacement_res": disp[0]["res"],
-                      "projection": sum(c["its"] for c in proj)})
+                      "projection": [c["its"] for c in proj]})
     assert not log
     return init, steps
