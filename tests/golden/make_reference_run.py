@@ -42,7 +42,7 @@ end
 """
 
 
-def text(dim, size, refine, dirichlet, neumann=("", "", ""), dt=60, steps=3, E="1.4e10", biot="0.9", perm="10", nu="0.3", rw="1", q="1e-5"):
+def text(dim, size, refine, dirichlet, neumann=("", "", ""), dt=60, steps=3, E="1.4e10", biot="0.9", perm="10", nu="0.3", rw="1", q="1e-5", solver=""):
     return f"""
 subsection Mesh
   set Dimensions               = {dim}
@@ -63,7 +63,7 @@ end
 subsection Solver
   set Time step  = {dt}
   set Time max   = {dt * steps}
-end
+{solver}end
 """
 
 
@@ -77,6 +77,10 @@ CASES = {
     # anisotropic cells, other material, a condition list in which two conditions claim the corner dofs (first one wins)
     "rect2d_r3": lambda: text(2, "10, 6", 3, ("3, 2, 0, 1, 0", "1, 1, 0, 0, 1", "-2e-5, 0, 0, 1e-5, 0"), dt=30, steps=4, E="2.1e10", biot="0.8",
                               perm="25", nu="0.25", rw="1.5", q="2e-5"),
+    # the loop's other exits (FSS:349-381): an FSS tolerance that is never met, so the coupling loop runs to its cap, and a pressure
+    # loop that hits its cap of 2 passes before the residual is below tolerance
+    "caps2d_r3": lambda: text(2, "10, 10", 3, ("0, 1, 2, 3", "0, 0, 1, 1", "0, -1e-5, 0, -1e-5"), steps=2,
+                              solver="  set FSS tolerance = 1e-20\n  set Max FSS iterations = 3\n  set Max pressure iterations = 2\n"),
 }
 
 
@@ -133,7 +137,9 @@ def run_case(name, exe):
         arrays[f"{fname}__comp"] = f["comp"]
         arrays[f"{fname}__v"] = np.stack([d[fname]["v"] for d in dumps])
     np.savez_compressed(HERE / f"reference_run_{name}.npz", **arrays)
+    loop_log = res.stdout[res.stdout.index("starting time loop"):]  # run()'s own prints, FSS:325-406
     rec = {"case": name, "dim": dim, "input": inp, "n_steps": len(steps), "steps": steps, "cg_solves": cg, "fields": sorted(dumps[0].keys()),
+           "time_loop_stdout": loop_log,
            "produced_by": "oracle/_ref/fss_ref = /root/reference/lib/include/*.h (unmodified) + oracle/dealii_shim (deal.II API shim, NOT deal.II) + oracle/ref_main.cpp"}
     (HERE / f"reference_run_{name}.json").write_text(json.dumps(rec, indent=1))
     return rec

@@ -33,16 +33,28 @@ def test_oracle_reproduces_the_reference_run(case):
         for k in range(rec["n_steps"]):
             rep = fss.time_step(b, inp)
             printed, cg = rec["steps"][k], ref_steps[k]
-            # control flow of FSS:345-405 and SolverCG / SSOR iteration counts, solve by solve
+            # control flow of FSS:345-405: coupling iterations, passes of the pressure loop (a pass that finds the residual below
+            # tolerance prints "pressure converged; iterations: passes - 1" and leaves without solving; a loop that runs into
+            # `Max pressure iterations` prints nothing and has solved in every pass)
             assert rep["fss_iterations"] == printed["coupling_iterations"]
-            assert [n - 1 for n in rep["inner_counts"]] == printed["pressure_converged_iterations"]
+            expect_printed, expect_solves = R.expected_prints(rep, inp.pressure_tol)
+            assert expect_printed == printed["pressure_converged_iterations"]
+            assert expect_solves == cg["pressure_solves_per_coupling_iteration"]
+            # SolverCG / SSOR iteration counts, solve by solve
             assert rep["cg_each"]["pressure"] == cg["pressure"]
-            assert rep["cg_each"]["displacement"] == [cg["displacement"]]
+            assert rep["cg_each"]["displacement"][0] == cg["displacement"][0]
+            # a second and third coupling iteration (only the capped case has them) re-solve an unchanged system from a converged
+            # start: the true residual A u - b of that start is rounding noise above the absolute 1e-12 stop (DS:298), and so is
+            # the number of iterations it takes to get back under it
+            assert np.abs(np.array(rep["cg_each"]["displacement"][1:]) - np.array(cg["displacement"][1:])).max(initial=0) <= 3
             assert rep["cg_each"]["projection"] == cg["projection"]
-            assert rep["displacement_residual"] == pytest.approx(cg["displacement_res"], rel=1e-3)  # ||A u - b|| at the 1e-12 stop
+            assert rep["displacement_residual"] == pytest.approx(cg["displacement_res"][-1], rel=1e-3)  # ||A u - b|| at the 1e-12 stop
             # what the loop prints (6 significant digits)
             assert float(f"{rep['pressure_linfty']:.6g}") == printed["solution_limits"][-1]
-            assert float(f"{rep['pressure_error']:.6g}") == printed["error"][-1]
+            if printed["error"][-1] > 1e-12:
+                assert float(f"{rep['pressure_error']:.6g}") == printed["error"][-1]
+            else:  # a residual at the rounding floor of its own terms (the capped case): its digits are summation order
+                assert rep["pressure_error"] == pytest.approx(printed["error"][-1], rel=1e-3)
             # fields, dof by dof
             p, u = b.get_vector(capi.VEC_P), b.get_vector(capi.VEC_U)
             assert fss.rel_l2(p, gold["p__v"][k]) <= 1e-13
@@ -91,3 +103,27 @@ def test_fss_ref_reproduces_its_records(case, tmp_path):
         for name in ("p", "u", "eps_xx", "sigma_xx"):
             assert np.allclose(dump[name]["v"], gold[f"{name}__v"][k], rtol=1e-12, atol=0)
     assert out.stdout.count("Coupling iteration:") == sum(s["coupling_iterations"] for s in rec["steps"])
+
+
+def test_product_driver_prints_the_reference_log(tmp_path):
+    """`fss-poroel <input.data>` — the product's C++ driver (csrc/host/main.cpp + problem.hpp), here linked against the oracle-backed
+    pe_* shim of tests/driver_on_oracle.cpp — fed the parameter files of the recorded runs exactly as the reference got them (no GPU
+    subsection): from "starting time loop" on, its standard output is the reference's, character for character."""
+    import subprocess
+    H.load_oracle()
+    exe = tmp_path / "fss-poroel-on-oracle"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", str(exe), str(H.ROOT / "poroelasticity-dealii_b200" / "csrc" / "host" / "main.cpp"),
+                           str(H.ROOT / "tests" / "driver_on_oracle.cpp"), "-L", str(H.ROOT / "oracle"), "-loracle", f"-Wl,-rpath,{H.ROOT / 'oracle'}"])
+    for case in R.CASES:
+        rec, _ = R.load(case)
+        work = tmp_path / case
+        work.mkdir()
+        (work / "input.data").write_text(rec["input"])
+        out = subprocess.run([str(exe), "input.data"], capture_output=True, text=True, timeout=900, cwd=work)
+        assert out.returncode == 0, out.stderr[-1000:]
+        mine, theirs = out.stdout[out.stdout.index("starting time loop"):].splitlines(), rec["time_loop_stdout"].splitlines()
+        assert len(mine) == len(theirs), case
+        for a, b in zip(mine, theirs):
+            if a != b:  # only a residual at the rounding floor (the capped case prints 2e-15) may differ, and only in its last digits
+                assert a.split()[0] == b.split()[0] == "Error:" and float(b.split()[1]) < 1e-12, (case, a, b)
+                assert float(a.split()[1]) == pytest.approx(float(b.split()[1]), rel=1e-3)

@@ -29,9 +29,12 @@ def test_device_reproduces_the_reference_run(case, precond):
             rep = fss.time_step(dev, inp)
             printed = rec["steps"][k]
             assert rep["fss_iterations"] == printed["coupling_iterations"]
-            assert [n - 1 for n in rep["inner_counts"]] == printed["pressure_converged_iterations"]
+            assert R.expected_prints(rep, inp.pressure_tol)[0] == printed["pressure_converged_iterations"]
             assert rep["pressure_linfty"] == pytest.approx(printed["solution_limits"][-1], rel=2e-6)   # printed with 6 digits
-            assert rep["pressure_error"] == pytest.approx(printed["error"][-1], rel=1e-3)              # a residual at the 1e-9 level
+            if printed["error"][-1] > 1e-12:
+                assert rep["pressure_error"] == pytest.approx(printed["error"][-1], rel=1e-3)          # a residual at the 1e-9 level
+            else:
+                assert rep["pressure_error"] < 1e-12                                                   # rounding floor (capped case)
             p, u = dev.get_vector(capi.VEC_P), dev.get_vector(capi.VEC_U)
             assert fss.rel_l2(p[order_p], gold["p__v"][k]) <= 1e-8
             assert fss.rel_l2(u[order_u], gold["u__v"][k]) <= 1e-8
