@@ -164,10 +164,13 @@ def oracle_setup(args, threads):
     return H, b, inp, prm, thr, time.perf_counter() - t0
 
 
-def cpu_sample(args, threads, counts, cg_sample_its=(2, 5, 5)):
+def cpu_sample(args, threads, counts, cg_sample_its=((1, 3), (2, 6), (2, 6))):
     """Bounded CPU sample of the same workload with the oracle (the reference's SSOR-CG algorithm): builds the full-size
-    systems, times a few iterations of each solver and one call of each assembly operator, and prices TIME STEPS 1..K with
-    the oracle's own recorded per-step iteration counts (a full oracle step at 128^3 takes ~15 minutes)."""
+    systems, times each solver twice from a zero start — capped at `lo` and at `hi` iterations — and one call of each assembly
+    operator, and prices TIME STEPS 1..K with the oracle's own recorded per-step iteration counts (a full oracle step at 128^3
+    takes ~15 minutes).  Cost per CG iteration = (t_hi - t_lo) / (hi - lo); what a solve costs besides its iterations (the
+    first preconditioner application, norms) = t_lo - lo * that.  (Round 1 divided one short run by its + 1, which prices the
+    start-up like an iteration and came out 20-25 % low against a full step.)"""
     H, b, inp, prm, thr, t_setup = oracle_setup(args, threads)
     capi, fss = H.capi, H.fss
     dt = inp.time_step
@@ -181,34 +184,41 @@ def cpu_sample(args, threads, counts, cg_sample_its=(2, 5, 5)):
                 raise
         return time.perf_counter() - t
 
-    its_u, its_p, its_m = cg_sample_its
+    def solver_cost(solve, reset, lo_hi):
+        lo, hi = lo_hi
+        t = []
+        for cap in (lo, hi):
+            prm.cg_max_iterations = cap
+            b.set_params(prm)
+            reset()
+            t.append(timed(solve))
+        per_it = (t[1] - t[0]) / (hi - lo)
+        return per_it, max(0.0, t[0] - lo * per_it)
+
     b.pressure_set_uniform(inp.p_init)
     t_asm_u_first = timed(b.displacement_assemble)      # matrix + rhs (once per run)
-    prm.cg_max_iterations = its_u
-    b.set_params(prm)
-    t_u = timed(b.displacement_solve) / (its_u + 1)     # +1: the initial residual vmult and SSOR apply
+    zero_u, zero_p = np.zeros(b.n_u), np.zeros(b.n_p)
+    t_u, f_u = solver_cost(b.displacement_solve, lambda: b.set_vector(capi.VEC_U, zero_u), cg_sample_its[0])
     t_asm_u = timed(b.displacement_assemble)            # rhs only (every FSS iteration)
     b.project_assemble_matrix()
     t_proj_rhs = timed(lambda: b.project_assemble_rhs(fss.VOLUMETRIC_COMPONENTS[inp.dim]))
-    prm.cg_max_iterations = its_m
-    b.set_params(prm)
-    t_m = timed(lambda: b.project_solve(0)) / (its_m + 1)
+    t_m, f_m = solver_cost(lambda: b.project_solve(0), lambda: b.set_vector(capi.VEC_STRAIN0, zero_p), cg_sample_its[2])
     b.volumetric_strain_from_projection([fss.TENSOR_TO_ENTRY[inp.dim][c] for c in fss.VOLUMETRIC_COMPONENTS[inp.dim]], True)
     b.pressure_begin_step(); b.pressure_zero_update(); b.update_volumetric_strain()
     t_res = timed(lambda: b.assemble_residual(dt))
     t_jac = timed(lambda: b.assemble_jacobian(dt))
-    prm.cg_max_iterations = its_p
-    b.set_params(prm)
-    t_p = timed(b.pressure_solve) / (its_p + 1)
+    t_p, f_p = solver_cost(b.pressure_solve, b.pressure_zero_update, cg_sample_its[1])
     b.close()
 
     def price(g):
-        return (g["pressure_iterations"] * (t_res + t_jac) + g["cg_its_pressure"] * t_p + t_asm_u + g["cg_its_displacement"] * t_u +
-                t_proj_rhs + g["cg_its_projection"] * t_m + t_res)
+        n_p_solves = max(0, g["pressure_iterations"] - 1)  # the pass that finds the residual converged does not solve (FSS:366-371)
+        return (g["pressure_iterations"] * t_res + n_p_solves * (t_jac + f_p) + g["cg_its_pressure"] * t_p + t_asm_u + f_u + g["cg_its_displacement"] * t_u +
+                t_proj_rhs + inp.dim * f_m + g["cg_its_projection"] * t_m + t_res)
 
     per_step = [price(g) for g in counts["per_step"]]
     mean = float(np.mean(per_step))
-    detail = {"setup_s": round(t_setup, 2), "s_per_cg_it_u": t_u, "s_per_cg_it_p": t_p, "s_per_cg_it_proj": t_m, "s_residual": t_res,
+    detail = {"setup_s": round(t_setup, 2), "s_per_cg_it_u": t_u, "s_per_cg_it_p": t_p, "s_per_cg_it_proj": t_m, "s_per_solve_u": f_u, "s_per_solve_p": f_p,
+              "s_per_solve_proj": f_m, "cg_sample_its_lo_hi": list(map(list, cg_sample_its)), "s_residual": t_res,
               "s_jacobian": t_jac, "s_u_rhs": t_asm_u, "s_u_matrix_and_rhs": t_asm_u_first, "s_proj_rhs": t_proj_rhs,
               "counts_source": counts["source"], "counts_extrapolated": counts["extrapolated"],
               "mean_counts": {k: float(np.mean([g[k] for g in counts["per_step"]])) for k in COUNT_KEYS},
@@ -238,8 +248,9 @@ def extrapolation_check(args, threads):
 
 
 def sample_text(counts):
-    return ("oracle (SSOR-CG, reference settings) at full size: 2/5/5 CG iterations of the u/p/projection solvers and one call of each assembly "
-            "operator timed; time steps 1..K (the GPU arm's window) priced with the oracle's recorded per-step iteration counts (%s)" % counts["source"])
+    return ("oracle (SSOR-CG, reference settings) at full size: the u/p/projection solvers timed at 1 and 3 / 2 and 6 / 2 and 6 CG iterations from a "
+            "zero start (cost per iteration = the difference) and one call of each assembly operator; time steps 1..K (the GPU arm's window) priced "
+            "with the oracle's recorded per-step iteration counts (%s)" % counts["source"])
 
 
 def run_reference(args, rank, world):
