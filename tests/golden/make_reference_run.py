@@ -77,6 +77,11 @@ CASES = {
     # anisotropic cells, other material, a condition list in which two conditions claim the corner dofs (first one wins)
     "rect2d_r3": lambda: text(2, "10, 6", 3, ("3, 2, 0, 1, 0", "1, 1, 0, 0, 1", "-2e-5, 0, 0, 1e-5, 0"), dt=30, steps=4, E="2.1e10", biot="0.8",
                               perm="25", nu="0.25", rw="1.5", q="2e-5"),
+    # traction on the top face of a 3D box (3D face quadrature and normals in DS:249-277), rollers on the other five faces
+    "neumann3d_r2": lambda: text(3, "10, 8, 6", 2, ("0, 1, 2, 3, 4", "0, 0, 1, 1, 2", "0, 0, 0, 0, 0"), ("5", "2", "-2e6"), steps=2),
+    # the shipped case two levels finer (64^2 cells, 33,282 displacement dofs): the same agreement at a size where SSOR-CG needs
+    # several hundred iterations
+    "shipped_r6": lambda: SHIPPED.replace("set Time max   = 1e3", "set Time max   = 180").replace("set Initial refinement level = 4", "set Initial refinement level = 6"),
     # the loop's other exits (FSS:349-381): an FSS tolerance that is never met, so the coupling loop runs to its cap, and a pressure
     # loop that hits its cap of 2 passes before the residual is below tolerance
     "caps2d_r3": lambda: text(2, "10, 10", 3, ("0, 1, 2, 3", "0, 0, 1, 1", "0, -1e-5, 0, -1e-5"), steps=2,

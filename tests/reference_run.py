@@ -9,7 +9,7 @@ import helpers as H
 
 capi, fss = H.capi, H.fss
 GOLD = H.ROOT / "tests" / "golden"
-CASES = ["shipped_4steps", "box3d_r3", "neumann2d_r4", "rect2d_r3", "caps2d_r3"]
+CASES = ["shipped_4steps", "box3d_r3", "neumann2d_r4", "rect2d_r3", "caps2d_r3", "neumann3d_r2", "shipped_r6"]
 # what the reference leaves to its defaults / hard-codes: FE_Q(2) displacement (DS:67), uniform mesh until time step 5 (FSS:333)
 GPU_SECTION = "\nsubsection GPU\n  set Displacement FE degree = 2\n  set Refine every = 0\n{extra}end\n"
 
