@@ -31,6 +31,7 @@ template <int dim> class Triangulation {
     unsigned int index = 0;
     FaceRef face(unsigned int f) const { return tria->face_of(index, f); }
     Point<dim> vertex(unsigned int v) const { return tria->vertex_of(index, v); }
+    unsigned int vertex_index(unsigned int v) const { return (unsigned int)tria->vertex_number(index, v); }
     void clear_refine_flag() const { shim_unsupported("clear_refine_flag"); }
     void clear_coarsen_flag() const { shim_unsupported("clear_coarsen_flag"); }
   };
@@ -46,6 +47,16 @@ template <int dim> class Triangulation {
   void refine_global(unsigned int times) { level += times; }
   unsigned int n_active_cells() const { return have_mesh ? 1u << (dim * level) : 0u; }
   unsigned int n_levels() const { return level + 1; }
+  unsigned int n_vertices() const { unsigned int n = 1; for (int a = 0; a < dim; ++a) n *= cells_per_axis() + 1; return n; }
+  std::vector<Point<dim>> get_vertices() const {  // indexed by vertex_index(): lexicographic over the lattice
+    std::vector<Point<dim>> out(n_vertices());
+    const unsigned int n1 = cells_per_axis() + 1;
+    for (unsigned int id = 0; id < out.size(); ++id) {
+      unsigned int r = id;
+      for (int a = 0; a < dim; ++a) { out[id][a] = lo[a] + (hi[a] - lo[a]) * ((r % n1) / (double)cells_per_axis()); r /= n1; }
+    }
+    return out;
+  }
   unsigned int cells_per_axis() const { return 1u << level; }
   active_cell_iterator begin_active(unsigned int = 0) const { return active_cell_iterator{CellAccessor{this, 0}}; }
   active_cell_iterator end() const { return active_cell_iterator{CellAccessor{this, n_active_cells()}}; }
@@ -270,6 +281,7 @@ template <int dim> class DoFHandler {
   void clear() { cell_dofs.clear(); total = 0; }
   unsigned int n_dofs() const { return total; }
   const Triangulation<dim>& get_tria() const { return *tria; }
+  const FiniteElement<dim>& get_fe() const { return *fe; }
   active_cell_iterator begin_active() const { return active_cell_iterator{CellAccessor{this, 0}}; }
   active_cell_iterator end() const { return active_cell_iterator{CellAccessor{this, tria->n_active_cells()}}; }
   void distribute_dofs(const FiniteElement<dim>& fe_) {

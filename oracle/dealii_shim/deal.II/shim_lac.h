@@ -183,6 +183,9 @@ class ConstraintMatrix {
   void set_inhomogeneity(size_type i, double g) { line_of[i] = g; }
   unsigned int n_constraints() const { return (unsigned int)line_of.size(); }
   double inhomogeneity(size_type i) const { auto it = line_of.find(i); return it == line_of.end() ? 0.0 : it->second; }
+  double get_inhomogeneity(size_type i) const { return inhomogeneity(i); }
+  // (master, weight) pairs of a line; Dirichlet lines have none (the only kind on meshes without hanging nodes)
+  const std::vector<std::pair<size_type, double>>* get_constraint_entries(size_type i) const { return is_constrained(i) ? &no_entries : nullptr; }
   // condense(): with no entries in any line, a constrained row/column keeps only its diagonal and the vector entry is zeroed.
   // The reference calls these on the PRESSURE constraints only, which are empty on meshes without hanging nodes.
   template <class V> void condense(V& v) const { for (const auto& l : line_of) v(l.first) = 0; }
@@ -238,6 +241,7 @@ class ConstraintMatrix {
   }
  private:
   std::map<size_type, double> line_of;
+  std::vector<std::pair<size_type, double>> no_entries;
   bool closed = false;
 };
 

@@ -42,3 +42,33 @@ def test_device_reproduces_the_reference_run(case, precond):
                 assert fss.rel_l2(dev.get_vector(capi.VEC_STRAIN0 + e)[order_p], gold[f"{name}__v"][k]) <= 1e-6
     finally:
         dev.close()
+
+
+@pytest.mark.parametrize("case", ["shipped_4steps", "box3d_r3", "neumann2d_r4"])
+@pytest.mark.parametrize("precond", [1, 0])
+def test_reference_side_binding_on_the_device(case, precond, tmp_path):
+    """integration/_build/fss_gpu — INTEGRATION.md's binding (GpuBackend.h) and the reference's run() rewritten against pe_*,
+    compiled in the build container against the reference's own InputDataPoroel.h and the deal.II API shim, linked with
+    libporoel.so: mesh, numbering and boundary conditions come from (shim) deal.II objects exactly as a maintainer of the
+    reference would hand them over, the hot path runs on the GPU, and the result is the reference's own."""
+    import subprocess
+    from test_integration_binding import read_fields
+    exe = R.H.ROOT / "integration" / "_build" / "fss_gpu"
+    if not exe.exists():
+        pytest.skip("integration/_build/fss_gpu was not built (needs /root/reference at build time)")
+    rec, gold = R.load(case)
+    (tmp_path / "solution").mkdir()
+    (tmp_path / "input.data").write_text(rec["input"])
+    out = subprocess.run([str(exe), "input.data", str(precond)], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-1000:]
+    mine, theirs = out.stdout[out.stdout.index("starting time loop"):].splitlines(), rec["time_loop_stdout"].splitlines()
+    assert len(mine) == len(theirs)
+    for a, b in zip(mine, theirs):
+        ta, tb = a.split(), b.split()
+        if ta[0] in ("Error:", "Solution"):  # numbers: "Solution limits: x" to its printed digits, the residual to 0.1 %
+            assert ta[:-1] == tb[:-1] and float(ta[-1]) == pytest.approx(float(tb[-1]), rel=2e-6 if ta[0] == "Solution" else 1e-3)
+        else:
+            assert a == b
+    for k in range(rec["n_steps"]):
+        p, u = read_fields(tmp_path / "solution" / f"fields-{k + 1:04d}.txt")
+        assert fss.rel_l2(p, gold["p__v"][k]) <= 1e-8 and fss.rel_l2(u, gold["u__v"][k]) <= 1e-8
