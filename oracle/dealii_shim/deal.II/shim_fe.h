@@ -102,6 +102,11 @@ template <int dim> class Triangulation {
 };
 
 namespace GridGenerator {
+template <int dim> inline void hyper_cube(Triangulation<dim>& tria, const double left = 0., const double right = 1., const bool colorize = false) {
+  Point<dim> p1, p2;
+  for (int i = 0; i < dim; ++i) { p1[i] = left; p2[i] = right; }
+  tria.create_box(p1, p2, colorize);
+}
 // grid_generator.cc, hyper_rectangle: the two corners need not be ordered (FSS:422-425 passes the upper one first)
 template <int dim> inline void hyper_rectangle(Triangulation<dim>& tria, const Point<dim>& p_1, const Point<dim>& p_2, const bool colorize = false) {
   Point<dim> p1, p2;
@@ -338,6 +343,8 @@ template <int dim> class FEValuesBase {
     return g;
   }
   const Tensor<1, dim>& normal_vector(unsigned int q) const { return normals[q]; }
+  Tensor<1, dim> shape_grad(unsigned int i, unsigned int q) const { return shape_grad_component(i, q, i % fe.n_comp); }
+  const Point<dim>& quadrature_point(unsigned int q) const { return qpoints[q]; }
   // fe_values.cc, do_function_values: values[q] += dof_value(i) * shape_value(i, q), shape functions in the outer loop
   template <class V> void get_function_values(const V& u, std::vector<double>& out) const {
     std::fill(out.begin(), out.end(), 0.0);

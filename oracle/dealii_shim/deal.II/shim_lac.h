@@ -103,6 +103,10 @@ template <typename MatrixType = SparseMatrix<double>> class PreconditionSSOR {
   std::vector<size_t> pos_right_of_diagonal;
 };
 
+struct PreconditionIdentity {
+  template <class V> void vmult(V& dst, const V& src) const { dst = src; }
+};
+
 // solver_control.cc, SolverControl::check: success as soon as the value is <= tol, failure when the step count is exhausted
 class SolverControl {
  public:

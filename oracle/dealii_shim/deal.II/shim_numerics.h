@@ -15,6 +15,9 @@ template <int dim> inline void make_sparsity_pattern(const DoFHandler<dim>& dh, 
     for (unsigned int i = 0; i < n; ++i)
       for (unsigned int j = 0; j < n; ++j) dsp.add(dh.cell_dofs[(size_t)c * n + i], dh.cell_dofs[(size_t)c * n + j]);
 }
+template <int dim> inline void make_sparsity_pattern(const DoFHandler<dim>& dh, DynamicSparsityPattern& dsp) {
+  make_sparsity_pattern(dh, dsp, ConstraintMatrix(), true);
+}
 }  // namespace DoFTools
 
 namespace MatrixCreator {
@@ -94,7 +97,46 @@ template <int dim> inline void interpolate_boundary_values(const DoFHandler<dim>
       constraints.set_inhomogeneity(bv.first, bv.second);
     }
 }
+// the std::map variant (vector_tools.templates.h): later cells overwrite earlier ones with the same value
+template <int dim> inline void interpolate_boundary_values(const DoFHandler<dim>& dh, const types::boundary_id id, const Function<dim>& f,
+                                                           std::map<types::global_dof_index, double>& boundary_values) {
+  ConstraintMatrix tmp;
+  interpolate_boundary_values(dh, id, f, tmp);
+  for (types::global_dof_index i = 0; i < dh.n_dofs(); ++i)
+    if (tmp.is_constrained(i)) boundary_values[i] = tmp.get_inhomogeneity(i);
+}
 }  // namespace VectorTools
+
+namespace MatrixTools {
+// matrix_tools.cc, apply_boundary_values(boundary_values, matrix, solution, rhs, eliminate_columns = true): the row of a boundary
+// dof keeps only its diagonal, rhs_i = a_ii g_i, solution_i = g_i; its column is eliminated into the right-hand side of the
+// other rows (symmetric pattern assumed, as deal.II does)
+inline void apply_boundary_values(const std::map<types::global_dof_index, double>& boundary_values, SparseMatrix<double>& A, Vector<double>& solution,
+                                  Vector<double>& rhs, const bool eliminate_columns = true) {
+  const SparsityPattern& sp = A.get_sparsity_pattern();
+  double first_nonzero_diagonal_entry = 1;
+  for (unsigned int i = 0; i < A.m(); ++i)
+    if (A.diag_element(i) != 0) { first_nonzero_diagonal_entry = A.diag_element(i); break; }
+  for (const auto& bv : boundary_values) {
+    const unsigned int dof = bv.first;
+    for (size_t k = sp.rowstart[dof] + 1; k < sp.rowstart[dof + 1]; ++k) A.val[k] = 0;
+    double new_rhs;
+    if (A.diag_element(dof) != 0) new_rhs = bv.second * A.diag_element(dof);
+    else { A.val[sp.rowstart[dof]] = first_nonzero_diagonal_entry; new_rhs = bv.second * first_nonzero_diagonal_entry; }
+    rhs(dof) = new_rhs;
+    if (eliminate_columns) {
+      const double diagonal_entry = A.diag_element(dof);
+      for (size_t k = sp.rowstart[dof] + 1; k < sp.rowstart[dof + 1]; ++k) {  // rows that couple with `dof` (symmetric pattern)
+        const unsigned int row = sp.colnums[k];
+        const size_t pos = A.position(row, dof);
+        rhs(row) -= A.val[pos] / diagonal_entry * new_rhs;
+        A.val[pos] = 0;
+      }
+    }
+    solution(dof) = bv.second;
+  }
+}
+}  // namespace MatrixTools
 
 // ---------------------------------------------------------------------------------------------- output
 namespace DataComponentInterpretation {

@@ -127,3 +127,19 @@ def test_product_driver_prints_the_reference_log(tmp_path):
             if a != b:  # only a residual at the rounding floor (the capped case prints 2e-15) may differ, and only in its last digits
                 assert a.split()[0] == b.split()[0] == "Error:" and float(b.split()[1]) < 1e-12, (case, a, b)
                 assert float(a.split()[1]) == pytest.approx(float(b.split()[1]), rel=1e-3)
+
+
+def test_shim_prints_what_dealii_publishes_for_step4(tmp_path):
+    """EXTERNAL ANCHOR OF THE SHIM.  tests/poisson_on_shim.cpp is the problem of deal.II's tutorial step-4 written against the deal.II
+    API; the tutorial's "Results" section publishes what deal.II prints for it.  Compiled against oracle/dealii_shim the program
+    prints the same numbers — mesh, numbering, FEValues, QGauss(2), interpolate_boundary_values, apply_boundary_values, SolverCG
+    and SolverControl of the shim behave like the library's on this program (the oracle has the same anchor: test_oracle.py T10)."""
+    import subprocess
+    exe = tmp_path / "poisson_on_shim"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-I", str(H.ROOT / "oracle" / "dealii_shim"), "-o", str(exe), str(H.ROOT / "tests" / "poisson_on_shim.cpp")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300).stdout.splitlines()
+    assert [l.strip() for l in out] == [
+        "Solving problem in 2 space dimensions.", "Number of active cells: 256", "Number of degrees of freedom: 289",
+        "26 CG iterations needed to obtain convergence.",
+        "Solving problem in 3 space dimensions.", "Number of active cells: 4096", "Number of degrees of freedom: 4913",
+        "30 CG iterations needed to obtain convergence."]
