@@ -506,10 +506,14 @@ def main():
         spmv_ms_p = stats["spmv_ms_p"] / max(1, stats["spmv_timed_p"])
         inner_ms = stats["inner_ms_u"] / max(1, stats["inner_passes_u"])
         value = args.steps / (ms_total * 1e-3)
-        traffic = None
+        traffic, ncu_dram_peak = None, None
         tr = ROOT / "profiles" / "traffic_r2.json"
-        if tr.exists() and world == 1 and args.workload == "c4":
-            traffic = json.loads(tr.read_text()).get("k_spmv_sell<3,double> C4 (128^3 cells, 1 GPU)", {}).get("traffic")
+        if tr.exists():
+            cap = json.loads(tr.read_text()).get("k_spmv_sell<3,double> C4 (128^3 cells, 1 GPU)", {})
+            if world == 1 and args.workload == "c4":
+                traffic = cap.get("traffic")
+            if cap.get("dram_gbs") and cap.get("dram_pct_of_ncu_peak"):  # what ncu calls 100 % DRAM throughput on this part (a read-only stream
+                ncu_dram_peak = cap["dram_gbs"] / (cap["dram_pct_of_ncu_peak"] / 100.0)  # runs above the read+write copy the measured peak is)
         bsr = int(stats["bsr_block_size"])
         sell_fmt = bool(stats["sell_format_u"])
         fmt = (f"sliced block-ELL {bsr}x{bsr} (TMA-fed)" if sell_fmt else (f"block-CSR {bsr}x{bsr}" if bsr else "CSR"))
@@ -532,6 +536,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": kernel_name, "timing_source": timing_source,
                          "achieved": achieved, "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
+                         "frac_of_ncu_dram_peak": (achieved / ncu_dram_peak) if (achieved and ncu_dram_peak) else None, "ncu_dram_peak_gbs": ncu_dram_peak,
                          "traffic": traffic, "traffic_source": "profiles/traffic_r2.json (ncu --set full capture of this matrix pass as a stand-alone kernel on this workload)" if traffic else None,
                          "algorithmic_bytes_per_launch": stats["spmv_bytes_u"], "matrix_format": fmt, "avg_launch_ms": spmv_ms,
                          "csr_equivalent_gbs": ((stats["nnz_u"] * 12.0 + stats["n_dofs_u"] * 20.0) / (spmv_ms * 1e-3) / 1e9) if spmv_ms > 0 else None,
