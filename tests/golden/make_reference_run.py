@@ -82,6 +82,11 @@ CASES = {
     # the shipped case two levels finer (64^2 cells, 33,282 displacement dofs): the same agreement at a size where SSOR-CG needs
     # several hundred iterations
     "shipped_r6": lambda: SHIPPED.replace("set Time max   = 1e3", "set Time max   = 180").replace("set Initial refinement level = 4", "set Initial refinement level = 6"),
+    # BASELINE.json's benchmark configurations are Q1/Q1; the reference hard-codes FE_Q(2) at DS:67.  The q1_ cases run the same
+    # unmodified code with the shim's run-time override DEALII_SHIM_FESYSTEM_DEGREE=1 (configs[2]/[3] in small: 16^3 cells; configs[1]
+    # in small: 32^2 cells with the top traction)
+    "q1_box3d_r4": lambda: text(3, "10, 10, 10", 4, ("0, 1, 2, 3, 4, 5", "0, 0, 1, 1, 2, 2", "0, -1e-5, 0, -1e-5, 0, -1e-5"), steps=4),
+    "q1_neumann2d_r5": lambda: text(2, "10, 10", 5, ("0, 1, 2", "0, 0, 1", "0, 0, 0"), ("3", "1", "-1e6"), steps=4),
     # the loop's other exits (FSS:349-381): an FSS tolerance that is never met, so the coupling loop runs to its cap, and a pressure
     # loop that hits its cap of 2 passes before the residual is below tolerance
     "caps2d_r3": lambda: text(2, "10, 10", 3, ("0, 1, 2, 3", "0, 0, 1, 1", "0, -1e-5, 0, -1e-5"), steps=2,
@@ -116,6 +121,8 @@ def run_case(name, exe):
         (tmp / "solution").mkdir()
         (tmp / "input.data").write_text(inp)
         env = {"DEALII_SHIM_SOLVER_LOG": str(tmp / "solver.log"), "PATH": "/usr/bin:/bin"}
+        if name.startswith("q1_"):
+            env["DEALII_SHIM_FESYSTEM_DEGREE"] = "1"
         res = subprocess.run([str(exe), "input.data"], cwd=tmp, env=env, capture_output=True, text=True, timeout=3600)
         if res.returncode != 0:
             raise RuntimeError(f"{name}: fss_ref failed: {res.stderr[-2000:]}")
@@ -143,7 +150,8 @@ def run_case(name, exe):
         arrays[f"{fname}__v"] = np.stack([d[fname]["v"] for d in dumps])
     np.savez_compressed(HERE / f"reference_run_{name}.npz", **arrays)
     loop_log = res.stdout[res.stdout.index("starting time loop"):]  # run()'s own prints, FSS:325-406
-    rec = {"case": name, "dim": dim, "input": inp, "n_steps": len(steps), "steps": steps, "cg_solves": cg, "fields": sorted(dumps[0].keys()),
+    rec = {"case": name, "dim": dim, "degree_u": 1 if name.startswith("q1_") else 2, "input": inp, "n_steps": len(steps), "steps": steps, "cg_solves": cg,
+           "fields": sorted(dumps[0].keys()),
            "time_loop_stdout": loop_log,
            "produced_by": "oracle/_ref/fss_ref = /root/reference/lib/include/*.h (unmodified) + oracle/dealii_shim (deal.II API shim, NOT deal.II) + oracle/ref_main.cpp"}
     (HERE / f"reference_run_{name}.json").write_text(json.dumps(rec, indent=1))

@@ -9,9 +9,9 @@ import helpers as H
 
 capi, fss = H.capi, H.fss
 GOLD = H.ROOT / "tests" / "golden"
-CASES = ["shipped_4steps", "box3d_r3", "neumann2d_r4", "rect2d_r3", "caps2d_r3", "neumann3d_r2", "shipped_r6"]
+CASES = ["shipped_4steps", "box3d_r3", "neumann2d_r4", "rect2d_r3", "caps2d_r3", "neumann3d_r2", "shipped_r6", "q1_box3d_r4", "q1_neumann2d_r5"]
 # what the reference leaves to its defaults / hard-codes: FE_Q(2) displacement (DS:67), uniform mesh until time step 5 (FSS:333)
-GPU_SECTION = "\nsubsection GPU\n  set Displacement FE degree = 2\n  set Refine every = 0\n{extra}end\n"
+GPU_SECTION = "\nsubsection GPU\n  set Displacement FE degree = {degree}\n  set Refine every = 0\n{extra}end\n"
 
 
 def load(case):
@@ -19,7 +19,7 @@ def load(case):
 
 
 def problem(rec, backend, extra=""):
-    inp = capi.InputData(text=rec["input"] + GPU_SECTION.format(extra=extra))
+    inp = capi.InputData(text=rec["input"] + GPU_SECTION.format(extra=extra, degree=rec.get("degree_u", 2)))
     mesh = fss.make_mesh(inp)
     dofs_p, dofs_u, _ = fss.upload_problem(backend, inp, mesh)
     return inp, dofs_p, dofs_u

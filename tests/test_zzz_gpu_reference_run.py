@@ -44,7 +44,7 @@ def test_device_reproduces_the_reference_run(case, precond):
         dev.close()
 
 
-@pytest.mark.parametrize("case", ["shipped_4steps", "box3d_r3", "neumann2d_r4"])
+@pytest.mark.parametrize("case", ["shipped_4steps", "box3d_r3", "neumann2d_r4", "q1_box3d_r4"])
 @pytest.mark.parametrize("precond", [1, 0])
 def test_reference_side_binding_on_the_device(case, precond, tmp_path):
     """integration/_build/fss_gpu — INTEGRATION.md's binding (GpuBackend.h) and the reference's run() rewritten against pe_*,
@@ -59,7 +59,11 @@ def test_reference_side_binding_on_the_device(case, precond, tmp_path):
     rec, gold = R.load(case)
     (tmp_path / "solution").mkdir()
     (tmp_path / "input.data").write_text(rec["input"])
-    out = subprocess.run([str(exe), "input.data", str(precond)], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    import os
+    env = dict(os.environ)
+    if rec.get("degree_u", 2) == 1:
+        env["DEALII_SHIM_FESYSTEM_DEGREE"] = "1"
+    out = subprocess.run([str(exe), "input.data", str(precond)], cwd=tmp_path, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stderr[-1000:]
     mine, theirs = out.stdout[out.stdout.index("starting time loop"):].splitlines(), rec["time_loop_stdout"].splitlines()
     assert len(mine) == len(theirs)
