@@ -94,6 +94,25 @@ CASES = {
 }
 
 
+def parse_log(stdout):
+    """run()'s prints per time step (FSS:328-406)"""
+    steps, cur = [], None
+    for line in stdout.splitlines():
+        line = line.strip()
+        if line.startswith("Time: "):
+            cur = {"time": float(line.split()[1]), "coupling_iterations": 0, "pressure_converged_iterations": [], "solution_limits": [], "error": []}
+            steps.append(cur)
+        elif line.startswith("Coupling iteration:"):
+            cur["coupling_iterations"] += 1
+        elif line.startswith("pressure converged; iterations:"):
+            cur["pressure_converged_iterations"].append(int(line.split()[-1]))
+        elif line.startswith("Solution limits:"):
+            cur["solution_limits"].append(float(line.split()[2]))
+        elif line.startswith("Error:"):
+            cur["error"].append(float(line.split()[1]))
+    return steps
+
+
 def parse_dump(path, dim):
     fields, cur = {}, None
     for line in Path(path).read_text().splitlines():
@@ -113,6 +132,39 @@ def parse_dump(path, dim):
     return out
 
 
+# Full-size cases: too big to commit dof by dof.  They are run by hand (minutes to an hour) and reduced to what the oracle's own
+# full-size record holds (tests/golden/oracle_counts_r<refine>.json, oracle_fields_r<refine>.npz): norms and the values at the same
+# 4096 sample dofs — the numbering is the same on both sides (tests/test_reference_run.py checks that on the small cases).
+BIG_CASES = {
+    # BASELINE.json configs[2] (C3): 3D, 64^3 cells, Q1/Q1 — 823,875 displacement + 274,625 pressure dofs
+    "q1_c3_r6": (lambda: text(3, "10, 10, 10", 6, ("0, 1, 2, 3, 4, 5", "0, 0, 1, 1, 2, 2", "0, -1e-5, 0, -1e-5, 0, -1e-5"), steps=2), "r6"),
+}
+
+
+def reduce_big(name, workdir):
+    """workdir: where `DEALII_SHIM_FESYSTEM_DEGREE=1 DEALII_SHIM_SOLVER_LOG=solver.log fss_ref input.data > run.log` has finished"""
+    inp_fn, tag = BIG_CASES[name]
+    workdir = Path(workdir)
+    inp = (workdir / "input.data").read_text()
+    assert inp == inp_fn(), "the run was taken with another parameter file"
+    dim = int(re.search(r"set Dimensions\s*=\s*(\d)", inp).group(1))
+    sample = np.load(HERE / f"oracle_fields_{tag}.npz")
+    stdout = (workdir / "run.log").read_text()
+    cg = [{"n": int(m.group(1)), "its": int(m.group(2)), "res": float(m.group(3))}
+          for m in re.finditer(r"cg n=(\d+) its=(\d+) res=(\S+)", (workdir / "solver.log").read_text())]
+    steps = parse_log(stdout)
+    for k in range(1, len(steps) + 1):
+        d = parse_dump(workdir / "solution" / f"solution-{k:04d}.vtk", dim)
+        p, u = d["p"]["v"], d["u"]["v"]
+        steps[k - 1].update({"p_l2": float(np.linalg.norm(p)), "p_sum": float(p.sum()), "u_l2": float(np.linalg.norm(u)),
+                      "p_samples": p[sample["p_dof"]].tolist(), "u_samples": np.stack([u[sample["u_dof"] + a] for a in range(dim)], axis=1).tolist()})
+    rec = {"case": name, "dim": dim, "degree_u": 1, "input": inp, "n_steps": len(steps), "cg_solves": cg, "steps": steps,
+           "time_loop_stdout": stdout[stdout.index("starting time loop"):], "samples_of": f"oracle_fields_{tag}.npz (p_dof, u_dof)",
+           "produced_by": "oracle/_ref/fss_ref (reference sources, unmodified) with DEALII_SHIM_FESYSTEM_DEGREE=1; reduced by make_reference_run.py reduce_big"}
+    (HERE / f"reference_run_{name}.json").write_text(json.dumps(rec))
+    return rec
+
+
 def run_case(name, exe):
     inp = CASES[name]()
     dim = int(re.search(r"set Dimensions\s*=\s*(\d)", inp).group(1))
@@ -126,20 +178,7 @@ def run_case(name, exe):
         res = subprocess.run([str(exe), "input.data"], cwd=tmp, env=env, capture_output=True, text=True, timeout=3600)
         if res.returncode != 0:
             raise RuntimeError(f"{name}: fss_ref failed: {res.stderr[-2000:]}")
-        steps, cur = [], None
-        for line in res.stdout.splitlines():
-            line = line.strip()
-            if line.startswith("Time: "):
-                cur = {"time": float(line.split()[1]), "coupling_iterations": 0, "pressure_converged_iterations": [], "solution_limits": [], "error": []}
-                steps.append(cur)
-            elif line.startswith("Coupling iteration:"):
-                cur["coupling_iterations"] += 1
-            elif line.startswith("pressure converged; iterations:"):
-                cur["pressure_converged_iterations"].append(int(line.split()[-1]))
-            elif line.startswith("Solution limits:"):
-                cur["solution_limits"].append(float(line.split()[2]))
-            elif line.startswith("Error:"):
-                cur["error"].append(float(line.split()[1]))
+        steps = parse_log(res.stdout)
         cg = [{"n": int(m.group(1)), "its": int(m.group(2)), "res": float(m.group(3))}
               for m in re.finditer(r"cg n=(\d+) its=(\d+) res=(\S+)", (tmp / "solver.log").read_text())]
         dumps = [parse_dump(tmp / "solution" / f"solution-{k + 1:04d}.vtk", dim) for k in range(len(steps))]
@@ -157,6 +196,11 @@ def run_case(name, exe):
     (HERE / f"reference_run_{name}.json").write_text(json.dumps(rec, indent=1))
     return rec
 
+
+if __name__ == "__main__" and len(sys.argv) == 4 and sys.argv[1] == "reduce":
+    r = reduce_big(sys.argv[2], sys.argv[3])
+    print(r["case"], "steps", r["n_steps"], "cg", [c["its"] for c in r["cg_solves"]])
+    sys.exit(0)
 
 if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", str(ROOT / "oracle"), "ref"])

@@ -150,3 +150,31 @@ def test_shim_prints_what_dealii_publishes_for_step4(tmp_path):
         "26 CG iterations needed to obtain convergence.",
         "Solving problem in 3 space dimensions.", "Number of active cells: 4096", "Number of degrees of freedom: 4913",
         "30 CG iterations needed to obtain convergence."]
+
+
+def test_full_size_c3_record_of_the_oracle_equals_the_reference_run():
+    """BASELINE.json configs[2] (C3: 3D, 64^3 cells, Q1/Q1, 823,875 + 274,625 dofs) at full size: the reference's own code (with the
+    shim's Q1 override) against the oracle's committed full-size record — the one tests/test_gpu_golden.py and bench.py hold the
+    CUDA path to.  No solver runs here: both sides are records (the reference run took 20 minutes, the oracle run 5)."""
+    import json
+    rec = json.loads((R.GOLD / "reference_run_q1_c3_r6.json").read_text())
+    ora = json.loads((R.GOLD / "oracle_counts_r6.json").read_text())
+    fields = np.load(R.GOLD / "oracle_fields_r6.npz")
+    n_p, n_u = ora["stats"]["n_dofs_p"], ora["stats"]["n_dofs_u"]
+    init, steps = R.split_cg_log(rec, n_p, n_u)
+    assert init["displacement"] == ora["init"]["cg_its_displacement"] and init["projection"] == ora["init"]["cg_its_projection"]
+    assert rec["n_steps"] >= 2
+    for k, (mine, cg) in enumerate(zip(rec["steps"], steps)):
+        gold = ora["steps"][k]
+        assert len(cg["pressure"]) == gold["pressure_iterations"] - 1
+        assert sum(cg["pressure"]) == gold["cg_its_pressure"]
+        assert cg["displacement"] == [gold["cg_its_displacement"]]
+        assert sum(cg["projection"]) == gold["cg_its_projection"]
+        assert mine["p_l2"] == pytest.approx(gold["p_l2"], rel=1e-13) and mine["p_sum"] == pytest.approx(gold["p_sum"], rel=1e-13)
+        assert mine["u_l2"] == pytest.approx(gold["u_l2"], rel=1e-11)
+        assert R.fss.rel_l2(np.array(mine["p_samples"]), fields["p"][k + 1]) <= 1e-13
+        assert R.fss.rel_l2(np.array(mine["u_samples"]), fields["u"][k + 1]) <= 1e-11
+    # the loop's prints against the oracle's report
+    printed = [l.split()[-1] for l in rec["time_loop_stdout"].splitlines() if l.strip().startswith("Error:")]
+    for k, e in enumerate(printed):
+        assert float(e) == float(f"{ora['steps'][k]['pressure_error']:.6g}")
