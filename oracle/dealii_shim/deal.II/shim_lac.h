@@ -5,12 +5,27 @@
 
 namespace dealii {
 
+// rows are kept as unsorted lists that are sorted and made unique when they have doubled since the last clean-up (a std::set
+// per row costs ten times the memory at 128^3 cells)
 class DynamicSparsityPattern {
  public:
-  explicit DynamicSparsityPattern(unsigned int n) : rows(n) {}
-  void add(unsigned int i, unsigned int j) { rows[i].insert(j); }
+  explicit DynamicSparsityPattern(unsigned int n) : rows(n), clean(n, 0) {}
+  void add(unsigned int i, unsigned int j) {
+    std::vector<unsigned int>& r = rows[i];
+    r.push_back(j);
+    if (r.size() >= 64 && r.size() >= 2 * (size_t)clean[i]) compress(i);
+  }
   unsigned int n_rows() const { return (unsigned int)rows.size(); }
-  std::vector<std::set<unsigned int>> rows;
+  const std::vector<unsigned int>& row(unsigned int i) const { const_cast<DynamicSparsityPattern*>(this)->compress(i); return rows[i]; }  // ascending, unique
+ private:
+  void compress(unsigned int i) {
+    std::vector<unsigned int>& r = rows[i];
+    std::sort(r.begin(), r.end());
+    r.erase(std::unique(r.begin(), r.end()), r.end());
+    clean[i] = (unsigned int)r.size();
+  }
+  std::vector<std::vector<unsigned int>> rows;
+  std::vector<unsigned int> clean;
 };
 // sparsity_pattern.cc: in a square pattern the diagonal entry is stored first in its row, the others follow in ascending order
 class SparsityPattern {
@@ -18,12 +33,15 @@ class SparsityPattern {
   void copy_from(const DynamicSparsityPattern& d) {
     const unsigned int n = d.n_rows();
     rowstart.assign(n + 1, 0);
-    for (unsigned int i = 0; i < n; ++i) rowstart[i + 1] = rowstart[i] + d.rows[i].size() + (d.rows[i].count(i) ? 0 : 1);
+    for (unsigned int i = 0; i < n; ++i) {
+      const std::vector<unsigned int>& r = d.row(i);
+      rowstart[i + 1] = rowstart[i] + r.size() + (std::binary_search(r.begin(), r.end(), i) ? 0 : 1);
+    }
     colnums.resize(rowstart[n]);
     for (unsigned int i = 0; i < n; ++i) {
       size_t k = rowstart[i];
       colnums[k++] = i;
-      for (unsigned int j : d.rows[i]) if (j != i) colnums[k++] = j;
+      for (unsigned int j : d.row(i)) if (j != i) colnums[k++] = j;
     }
   }
   unsigned int n_rows() const { return (unsigned int)rowstart.size() - 1; }
