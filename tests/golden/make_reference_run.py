@@ -138,6 +138,9 @@ def parse_dump(path, dim):
 BIG_CASES = {
     # BASELINE.json configs[2] (C3): 3D, 64^3 cells, Q1/Q1 — 823,875 displacement + 274,625 pressure dofs
     "q1_c3_r6": (lambda: text(3, "10, 10, 10", 6, ("0, 1, 2, 3, 4, 5", "0, 0, 1, 1, 2, 2", "0, -1e-5, 0, -1e-5, 0, -1e-5"), steps=2), "r6"),
+    # BASELINE.json configs[3] (C4, the headline configuration): 128^3 cells, Q1/Q1 — 6,440,067 + 2,146,689 dofs; hours on one core
+    "q1_c4_r7": (lambda: text(3, "10, 10, 10", 7, ("0, 1, 2, 3, 4, 5", "0, 0, 1, 1, 2, 2", "0, -1e-5, 0, -1e-5, 0, -1e-5"), steps=1), "r7"),
+    "q1_c4_r7_2steps": (lambda: text(3, "10, 10, 10", 7, ("0, 1, 2, 3, 4, 5", "0, 0, 1, 1, 2, 2", "0, -1e-5, 0, -1e-5, 0, -1e-5"), steps=2), "r7"),
 }
 
 

@@ -152,18 +152,23 @@ def test_shim_prints_what_dealii_publishes_for_step4(tmp_path):
         "30 CG iterations needed to obtain convergence."]
 
 
-def test_full_size_c3_record_of_the_oracle_equals_the_reference_run():
-    """BASELINE.json configs[2] (C3: 3D, 64^3 cells, Q1/Q1, 823,875 + 274,625 dofs) at full size: the reference's own code (with the
-    shim's Q1 override) against the oracle's committed full-size record — the one tests/test_gpu_golden.py and bench.py hold the
-    CUDA path to.  No solver runs here: both sides are records (the reference run took 20 minutes, the oracle run 5)."""
+BIG = [("q1_c3_r6", "r6"), ("q1_c4_r7", "r7"), ("q1_c4_r7_2steps", "r7")]
+
+
+@pytest.mark.parametrize("case,tag", [b for b in BIG if (R.GOLD / f"reference_run_{b[0]}.json").exists()])
+def test_full_size_records_of_the_oracle_equal_the_reference_run(case, tag):
+    """BASELINE.json configs[2] and [3] at full size — C3: 3D, 64^3 cells, Q1/Q1, 823,875 + 274,625 dofs; C4, the headline
+    configuration: 128^3 cells, 6,440,067 + 2,146,689 dofs — from the reference's own code (with the shim's Q1 override), against the
+    oracle's committed full-size records: the ones tests/test_gpu_golden.py and every bench.py line hold the CUDA path to.  No
+    solver runs here: both sides are records (the reference runs took 10 minutes and a few hours on one core)."""
     import json
-    rec = json.loads((R.GOLD / "reference_run_q1_c3_r6.json").read_text())
-    ora = json.loads((R.GOLD / "oracle_counts_r6.json").read_text())
-    fields = np.load(R.GOLD / "oracle_fields_r6.npz")
+    rec = json.loads((R.GOLD / f"reference_run_{case}.json").read_text())
+    ora = json.loads((R.GOLD / f"oracle_counts_{tag}.json").read_text())
+    fields = np.load(R.GOLD / f"oracle_fields_{tag}.npz")
     n_p, n_u = ora["stats"]["n_dofs_p"], ora["stats"]["n_dofs_u"]
     init, steps = R.split_cg_log(rec, n_p, n_u)
     assert init["displacement"] == ora["init"]["cg_its_displacement"] and init["projection"] == ora["init"]["cg_its_projection"]
-    assert rec["n_steps"] >= 2
+    assert rec["n_steps"] >= 1
     for k, (mine, cg) in enumerate(zip(rec["steps"], steps)):
         gold = ora["steps"][k]
         assert len(cg["pressure"]) == gold["pressure_iterations"] - 1
@@ -174,7 +179,6 @@ def test_full_size_c3_record_of_the_oracle_equals_the_reference_run():
         assert mine["u_l2"] == pytest.approx(gold["u_l2"], rel=1e-11)
         assert R.fss.rel_l2(np.array(mine["p_samples"]), fields["p"][k + 1]) <= 1e-13
         assert R.fss.rel_l2(np.array(mine["u_samples"]), fields["u"][k + 1]) <= 1e-11
-    # the loop's prints against the oracle's report
-    printed = [l.split()[-1] for l in rec["time_loop_stdout"].splitlines() if l.strip().startswith("Error:")]
-    for k, e in enumerate(printed):
-        assert float(e) == float(f"{ora['steps'][k]['pressure_error']:.6g}")
+        # the loop's prints against the oracle's report
+        assert mine["error"] == [float(f"{gold['pressure_error']:.6g}")]
+        assert mine["solution_limits"] == [float(f"{gold['pressure_linfty']:.6g}")]
