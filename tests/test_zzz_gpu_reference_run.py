@@ -30,7 +30,7 @@ def test_device_reproduces_the_reference_run(case, precond):
             printed = rec["steps"][k]
             assert rep["fss_iterations"] == printed["coupling_iterations"]
             assert R.expected_prints(rep, inp.pressure_tol)[0] == printed["pressure_converged_iterations"]
-            assert rep["pressure_linfty"] == pytest.approx(printed["solution_limits"][-1], rel=2e-6)   # printed with 6 digits
+            assert rep["pressure_linfty"] == pytest.approx(printed["solution_limits"][-1], rel=6e-6)   # printed with 6 digits: half a unit of the last one is 5e-6
             if printed["error"][-1] > 1e-12:
                 assert rep["pressure_error"] == pytest.approx(printed["error"][-1], rel=1e-3)          # a residual at the 1e-9 level
             else:
@@ -70,7 +70,7 @@ def test_reference_side_binding_on_the_device(case, precond, tmp_path):
     for a, b in zip(mine, theirs):
         ta, tb = a.split(), b.split()
         if ta[0] in ("Error:", "Solution"):  # numbers: "Solution limits: x" to its printed digits, the residual to 0.1 %
-            assert ta[:-1] == tb[:-1] and float(ta[-1]) == pytest.approx(float(tb[-1]), rel=2e-6 if ta[0] == "Solution" else 1e-3)
+            assert ta[:-1] == tb[:-1] and float(ta[-1]) == pytest.approx(float(tb[-1]), rel=6e-6 if ta[0] == "Solution" else 1e-3)
         else:
             assert a == b
     for k in range(rec["n_steps"]):
