@@ -182,3 +182,27 @@ def test_full_size_records_of_the_oracle_equal_the_reference_run(case, tag):
         # the loop's prints against the oracle's report
         assert mine["error"] == [float(f"{gold['pressure_error']:.6g}")]
         assert mine["solution_limits"] == [float(f"{gold['pressure_linfty']:.6g}")]
+
+
+def test_the_reference_cannot_run_c2_and_the_oracle_fails_at_the_same_point():
+    """BASELINE.json configs[1] (C2: 2D, 512^2 cells, Q1/Q1, top traction) exceeds the reference's own CG cap: its first displacement
+    solve (FSS:313) stops at SolverControl(1000, 1e-12) (DS:298-299) and run() ends with SolverControl::NoConvergence — recorded from
+    the reference's own code.  With the reference's cap (the default of `CG max iterations`) the oracle returns
+    PE_ERR_NO_CONVERGENCE from the same solve, after the same 1000 iterations, at the same residual; the recorded C2 oracle run and
+    bench.py --workload c2 raise the cap (20000 / 4000), which is why they exist at all."""
+    import ctypes as C
+    import json
+    rec = json.loads((R.GOLD / "reference_run_q1_c2_r9_noconvergence.json").read_text())
+    assert "SolverControl::NoConvergence after 1000 steps" in rec["stderr"] and rec["cg_solves"][0]["its"] == 1000
+    b = H.create_oracle_backend()
+    try:
+        inp, dofs_p, dofs_u = R.problem(rec, b)
+        assert inp.params().cg_max_iterations == 1000 and dofs_u.n_dofs == rec["cg_solves"][0]["n"]
+        b.pressure_set_uniform(inp.p_init)
+        b.displacement_assemble()
+        its, res = C.c_int(), C.c_double()
+        rc = b._f("displacement_solve")(b.ctx, C.byref(its), C.byref(res))
+        assert rc == capi.PE_ERR_NO_CONVERGENCE and its.value == 1000
+        assert res.value == pytest.approx(rec["cg_solves"][0]["res"], rel=1e-8)
+    finally:
+        b.close()
