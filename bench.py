@@ -250,7 +250,8 @@ def extrapolation_check(args, threads):
 def sample_text(counts):
     return ("oracle (SSOR-CG, reference settings) at full size: the u/p/projection solvers timed at 1 and 3 / 2 and 6 / 2 and 6 CG iterations from a "
             "zero start (cost per iteration = the difference) and one call of each assembly operator; time steps 1..K (the GPU arm's window) priced "
-            "with the oracle's recorded per-step iteration counts (%s)" % counts["source"])
+            "with the oracle's recorded per-step iteration counts (%s); the oracle reproduces the reference's own sources run on a deal.II API shim "
+            "(oracle/_ref/fss_ref) iteration count for iteration count, at full size for the 64^3 configuration (tests/test_reference_run.py)" % counts["source"])
 
 
 def run_reference(args, rank, world):
