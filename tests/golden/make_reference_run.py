@@ -142,7 +142,9 @@ BIG_CASES = {
     # reference cannot run it: its first displacement solve hits SolverControl(1000, 1e-12) (DS:298-299) and run() throws
     # NoConvergence after 1000 iterations at a residual of 0.052 (recorded by hand in reference_run_q1_c2_r9_noconvergence.json;
     # the oracle needs 1779 iterations for that solve).  Kept here as the parameter file of that record.
-    "q1_c2_r9": (lambda: text(2, "10, 10", 9, ("0, 1, 2", "0, 0, 1", "0.0, 0.0, 0.0"), ("3", "1", "-1000000.0"), steps=3), "c2_r9"),
+    "q1_c2_r9_noconvergence": (lambda: text(2, "10, 10", 9, ("0, 1, 2", "0, 0, 1", "0.0, 0.0, 0.0"), ("3", "1", "-1000000.0"), steps=3), "c2_r9"),
+    # the same workload one level coarser (256^2 cells): the largest the reference's CG cap lets it run (894 iterations)
+    "q1_c2_r8": (lambda: text(2, "10, 10", 8, ("0, 1, 2", "0, 0, 1", "0.0, 0.0, 0.0"), ("3", "1", "-1000000.0"), steps=4), "c2_r8"),
     # BASELINE.json configs[3] (C4, the headline configuration): 128^3 cells, Q1/Q1 — 6,440,067 + 2,146,689 dofs; hours on one core
     "q1_c4_r7": (lambda: text(3, "10, 10, 10", 7, ("0, 1, 2, 3, 4, 5", "0, 0, 1, 1, 2, 2", "0, -1e-5, 0, -1e-5, 0, -1e-5"), steps=1), "r7"),
     "q1_c4_r7_2steps": (lambda: text(3, "10, 10, 10", 7, ("0, 1, 2, 3, 4, 5", "0, 0, 1, 1, 2, 2", "0, -1e-5, 0, -1e-5, 0, -1e-5"), steps=2), "r7"),
