@@ -146,7 +146,6 @@ BIG_CASES = {
     # the same workload one level coarser (256^2 cells): the largest the reference's CG cap lets it run (894 iterations)
     "q1_c2_r8": (lambda: text(2, "10, 10", 8, ("0, 1, 2", "0, 0, 1", "0.0, 0.0, 0.0"), ("3", "1", "-1000000.0"), steps=4), "c2_r8"),
     # BASELINE.json configs[3] (C4, the headline configuration): 128^3 cells, Q1/Q1 — 6,440,067 + 2,146,689 dofs; hours on one core
-    "q1_c4_r7": (lambda: text(3, "10, 10, 10", 7, ("0, 1, 2, 3, 4, 5", "0, 0, 1, 1, 2, 2", "0, -1e-5, 0, -1e-5, 0, -1e-5"), steps=1), "r7"),
     "q1_c4_r7_2steps": (lambda: text(3, "10, 10, 10", 7, ("0, 1, 2, 3, 4, 5", "0, 0, 1, 1, 2, 2", "0, -1e-5, 0, -1e-5, 0, -1e-5"), steps=2), "r7"),
 }
 

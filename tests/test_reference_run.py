@@ -152,7 +152,7 @@ def test_shim_prints_what_dealii_publishes_for_step4(tmp_path):
         "30 CG iterations needed to obtain convergence."]
 
 
-BIG = [("q1_c3_r6", "r6"), ("q1_c4_r7", "r7"), ("q1_c4_r7_2steps", "r7"), ("q1_c2_r8", "c2_r8")]
+BIG = [("q1_c3_r6", "r6"), ("q1_c4_r7_2steps", "r7"), ("q1_c2_r8", "c2_r8")]
 
 
 @pytest.mark.parametrize("case,tag", [b for b in BIG if (R.GOLD / f"reference_run_{b[0]}.json").exists()])
@@ -160,7 +160,7 @@ def test_full_size_records_of_the_oracle_equal_the_reference_run(case, tag):
     """BASELINE.json configs[1] at the largest size the reference's CG cap admits (256^2 cells) and configs[2] and [3] at full size — C3: 3D, 64^3 cells, Q1/Q1, 823,875 + 274,625 dofs; C4, the headline
     configuration: 128^3 cells, 6,440,067 + 2,146,689 dofs — from the reference's own code (with the shim's Q1 override), against the
     oracle's committed full-size records: the ones tests/test_gpu_golden.py and every bench.py line hold the CUDA path to.  No
-    solver runs here: both sides are records (the reference runs took 10 minutes and a few hours on one core)."""
+    solver runs here: both sides are records (the reference runs took 10 minutes and 114 minutes on one core)."""
     import json
     rec = json.loads((R.GOLD / f"reference_run_{case}.json").read_text())
     ora = json.loads((R.GOLD / f"oracle_counts_{tag}.json").read_text())
