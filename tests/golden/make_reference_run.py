@@ -137,7 +137,7 @@ def parse_dump(path, dim):
 # 4096 sample dofs — the numbering is the same on both sides (tests/test_reference_run.py checks that on the small cases).
 BIG_CASES = {
     # BASELINE.json configs[2] (C3): 3D, 64^3 cells, Q1/Q1 — 823,875 displacement + 274,625 pressure dofs
-    "q1_c3_r6": (lambda: text(3, "10, 10, 10", 6, ("0, 1, 2, 3, 4, 5", "0, 0, 1, 1, 2, 2", "0, -1e-5, 0, -1e-5, 0, -1e-5"), steps=2), "r6"),
+    "q1_c3_r6": (lambda: text(3, "10, 10, 10", 6, ("0, 1, 2, 3, 4, 5", "0, 0, 1, 1, 2, 2", "0, -1e-5, 0, -1e-5, 0, -1e-5"), steps=4), "r6"),
     # BASELINE.json configs[1] (C2): 2D consolidation, 512^2 cells, Q1/Q1, traction on the top face — 526,338 + 263,169 dofs.  The
     # reference cannot run it: its first displacement solve hits SolverControl(1000, 1e-12) (DS:298-299) and run() throws
     # NoConvergence after 1000 iterations at a residual of 0.052 (recorded by hand in reference_run_q1_c2_r9_noconvergence.json;

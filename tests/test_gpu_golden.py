@@ -19,6 +19,10 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("refine", [5, 6, 7])
 def test_steps_match_recorded_oracle(refine):
     rec = json.loads((H.ROOT / "tests" / "golden" / f"oracle_counts_r{refine}.json").read_text())
+    # the same configuration run by the reference's own code (oracle/_ref/fss_ref, tests/golden/make_reference_run.py): refine 6 = C3
+    # (4 time steps), refine 7 = C4, the headline configuration (2 time steps); values at the same 4096 sample dofs
+    ref_path = H.ROOT / "tests" / "golden" / {6: "reference_run_q1_c3_r6.json", 7: "reference_run_q1_c4_r7_2steps.json"}.get(refine, "none")
+    ref_run = json.loads(ref_path.read_text()) if ref_path.exists() else None
     max_steps = {5: 4, 6: 4, 7: 3}[refine]  # the records are longer (bench.py checks every step of its window against them)
     inp = capi.InputData(text=H.make_input(dim=3, refine=refine, degree_u=1, extra_gpu="  set CG max iterations = 20000\n"))
     prob = capi.Problem(inp, device=0)
@@ -51,6 +55,10 @@ def test_steps_match_recorded_oracle(refine):
                 ps, us = p[fields["p_dof"]], np.stack([u[fields["u_dof"] + a] for a in range(3)], axis=1)
                 assert fss.rel_l2(ps, fields["p"][k + 1]) <= 1e-8
                 assert fss.rel_l2(us, fields["u"][k + 1]) <= 1e-8
+                if ref_run is not None and k < ref_run["n_steps"]:  # directly against the reference's own run of this configuration
+                    assert fss.rel_l2(ps, np.array(ref_run["steps"][k]["p_samples"])) <= 1e-8
+                    assert fss.rel_l2(us, np.array(ref_run["steps"][k]["u_samples"])) <= 1e-8
+                    assert rep["pressure_iterations"] - 1 == ref_run["steps"][k]["pressure_converged_iterations"][0]
     finally:
         prob.close()
 
