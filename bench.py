@@ -19,7 +19,8 @@ Printed JSON (one line, rank 0): value = steps/s with all state resident in HBM 
 stream, max over ranks); e2e = the same K steps through the C-ABI with HOST buffers (pinned host -> device copy of
 the step's state and device -> host copy of the result inside the timed region); roofline = the displacement-matrix
 pass (dominant kernel); cpu_baseline = the CPU oracle on a bounded sample (see `sample`); parity = fields of this very
-run against the recorded oracle run (field samples at 4096 lattice nodes + norms); the run FAILS (rc 3) above 1e-8.
+run against the recorded oracle run (field samples at 4096 lattice nodes + norms); the run FAILS (rc 3) above 1e-8;
+parity.reference_run = the same samples against the reference's own sources run on a deal.II API shim (C3: 4 steps, C4: 2).
 """
 import argparse
 import ctypes as C
