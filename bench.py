@@ -264,17 +264,15 @@ def run_reference(args, rank, world):
         print(json.dumps({"impl": "reference", "unavailable": f"no recorded oracle run for workload {args.workload} (a full CPU step at this size takes hours)"}), flush=True)
         return
     counts = golden_counts(golden_tag(args), args.steps)
-    vals, thr, detail = [], 0, None
-    for _ in range(max(1, min(args.steps, 2))):  # each sample is bounded; two are enough for a stable number
-        v, thr, detail, _ = cpu_sample(args, cores, counts)
-        vals.append(v)
-    v = float(np.median(vals))
+    # one bounded sample (about a minute at 128^3 on 16 cores: full-size assembly once, ten CG iterations of each solver); the arm is
+    # launched at every N of a scaling run and measures the same thing each time
+    v, thr, detail, _ = cpu_sample(args, cores, counts)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, args.gpus),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample_text(counts)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "detail": detail}
-    if not args.no_extrapolation_check:
+    if not args.no_extrapolation_check and world == 1:  # one full oracle step at 64^3 (~2.5 min): once per scaling run is enough
         try:
             line["extrapolation_check"] = extrapolation_check(args, cores)
         except Exception as exc:
