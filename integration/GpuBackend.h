@@ -23,7 +23,8 @@ inline void check(pe_ctx* ctx, int rc, const char* what) {
 // setup_dofs() of the three solver classes (PS:68-111, DS:106-153, SP:82-98) -> one upload + pe_setup
 template <int dim>
 void upload_from_dealii(pe_ctx* ctx, const Triangulation<dim>& tria, const DoFHandler<dim>& p_dh, const DoFHandler<dim>& u_dh,
-                        const ConstraintMatrix& u_constraints, const input_data::InputDataPoroel& data, int preconditioner) {
+                        const ConstraintMatrix& u_constraints, const input_data::InputDataPoroel& data, int preconditioner,
+                        int cg_max_iterations = 1000 /* PS:175, DS:299, SP:209; Jacobi-CG needs more iterations than SSOR-CG */) {
   // vertices and cells in active-cell order, deal.II's lexicographic vertex order
   std::vector<double> xyz;
   for (const auto& v : tria.get_vertices())
@@ -55,7 +56,7 @@ void upload_from_dealii(pe_ctx* ctx, const Triangulation<dim>& tria, const DoFHa
   prm.perm_over_visc = data.perm / data.visc;
   prm.well_radius = data.r_well;
   prm.flow_rate = data.flow_rate;
-  prm.cg_max_iterations = 1000;          // PS:175, DS:299, SP:209
+  prm.cg_max_iterations = cg_max_iterations;
   prm.cg_rel_tol_pressure = 1e-8;        // PS:175
   prm.cg_abs_tol_displacement = 1e-12;   // DS:298
   prm.cg_rel_tol_projection = 1e-8;      // SP:209

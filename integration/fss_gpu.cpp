@@ -3,7 +3,7 @@
 // gpu_backend::upload_from_dealii (GpuBackend.h).  Mesh, dof numbering, boundary conditions and the parameter file stay what
 // they are in the reference: deal.II objects and the reference's own InputDataPoroel.h.  What a maintainer's patched
 // PoroelasticityFSS.h would look like, as one translation unit:
-//     fss_gpu <input.data> [preconditioner: 0 Jacobi | 1 Chebyshev-Jacobi (default)]
+//     fss_gpu <input.data> [preconditioner: 0 Jacobi | 1 Chebyshev-Jacobi (default)] [CG iteration cap, default the reference's 1000]
 // prints the reference's log and writes ./solution/fields-NNNN.txt (p and u, dof by dof) after every time step.
 // Built by tests/test_integration_binding.py against the deal.II API shim (oracle/dealii_shim; deal.II cannot be installed here),
 // linked once with the oracle-backed pe_* of tests/driver_on_oracle.cpp (CPU) and once with libporoel.so (GPU box).  The
@@ -27,8 +27,8 @@ using namespace dealii;
 template <int dim>
 class PoroElasticProblemGpu {
  public:
-  PoroElasticProblemGpu(input_data::InputDataPoroel& data_, int preconditioner)
-      : data(data_), p_dh(triangulation), u_dh(triangulation), p_fe(1), u_fe(FE_Q<dim>(2), dim), preconditioner(preconditioner) {
+  PoroElasticProblemGpu(input_data::InputDataPoroel& data_, int preconditioner, int cg_cap)
+      : data(data_), p_dh(triangulation), u_dh(triangulation), p_fe(1), u_fe(FE_Q<dim>(2), dim), preconditioner(preconditioner), cg_cap(cg_cap) {
     if (pe_create(&ctx, 0, 0, 1, nullptr, 0) != PE_OK) throw std::runtime_error(std::string("pe_create: ") + pe_last_error(nullptr));
     switch (dim) {  // FSS:100-110
       case 2: volumetric = {0, 3}; break;
@@ -116,7 +116,7 @@ class PoroElasticProblemGpu {
                                                ConstantFunction<dim>(data.displacement_boundary_values[cond], dim), constraints,
                                                mask[data.displacement_boundary_components[cond]]);
     constraints.close();
-    gpu_backend::upload_from_dealii(ctx, triangulation, p_dh, u_dh, constraints, data, preconditioner);
+    gpu_backend::upload_from_dealii(ctx, triangulation, p_dh, u_dh, constraints, data, preconditioner, cg_cap);
   }
   void solve_displacement() { int its; double res; ck(pe_displacement_solve(ctx, &its, &res)); }
   void get_normal_strain_components() {  // FSS:153-164
@@ -146,7 +146,7 @@ class PoroElasticProblemGpu {
   std::vector<int> volumetric;
   std::vector<int32_t> volumetric_entries;
   pe_ctx* ctx = nullptr;
-  int preconditioner;
+  int preconditioner, cg_cap;
 };
 
 int main(int argc, char** argv) {
@@ -155,8 +155,9 @@ int main(int argc, char** argv) {
     input_data::InputDataPoroel data;
     data.read_input_file(argv[1]);
     const int precond = argc > 2 ? std::atoi(argv[2]) : PE_PRECOND_CHEBYSHEV;
-    if (data.dim == 2) { PoroElasticProblemGpu<2> problem(data, precond); problem.run(); }
-    else if (data.dim == 3) { PoroElasticProblemGpu<3> problem(data, precond); problem.run(); }
+    const int cg_cap = argc > 3 ? std::atoi(argv[3]) : 1000;
+    if (data.dim == 2) { PoroElasticProblemGpu<2> problem(data, precond, cg_cap); problem.run(); }
+    else if (data.dim == 3) { PoroElasticProblemGpu<3> problem(data, precond, cg_cap); problem.run(); }
     else return 2;
   } catch (std::exception& exc) {
     std::cerr << "Exception on processing: " << exc.what() << std::endl;

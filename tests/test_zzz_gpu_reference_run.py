@@ -63,7 +63,7 @@ def test_reference_side_binding_on_the_device(case, precond, tmp_path):
     env = dict(os.environ)
     if rec.get("degree_u", 2) == 1:
         env["DEALII_SHIM_FESYSTEM_DEGREE"] = "1"
-    out = subprocess.run([str(exe), "input.data", str(precond)], cwd=tmp_path, capture_output=True, text=True, timeout=900, env=env)
+    out = subprocess.run([str(exe), "input.data", str(precond), "20000"], cwd=tmp_path, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stderr[-1000:]
     mine, theirs = out.stdout[out.stdout.index("starting time loop"):].splitlines(), rec["time_loop_stdout"].splitlines()
     assert len(mine) == len(theirs)
